@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json headline metric: 7x7 MLE spot-fits/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the MLE hot path (picasso.gaussmle.gaussmle, method
+sigmaxy, eps 1e-3, max_it 100) over one batch of synthetic 7x7 spots
+(BASELINE.json configs[1]: 10 M spots per GPU).
+
+  value     whole-job fits/s with the ROIs already resident in HBM
+            (CUDA-event timed, max over ranks)
+  e2e       the same metric through the host-buffer C-ABI call pb_mle_fit
+            (pinned host arrays; H2D of the ROIs and D2H of the results inside
+            the timed region)
+  roofline  algorithmic HBM bytes (252 B/spot) / kernel time vs the measured
+            copy bandwidth (the metric asks for HBM GB/s; the fit is FP64-pipe
+            bound, see `compute`)
+  cpu_baseline  the CPU oracle (C port of the reference's numba kernel, same
+            arithmetic, bit-identical results) on the host cores, bounded sample
+
+--impl reference times the reference algorithm on the host CPU (the oracle
+port with all host threads; the Python reference itself cannot travel to the
+GPU box) and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BOX = 7
+EPS = 0.001
+MAX_IT = 100
+METHOD = "sigmaxy"
+BYTES_PER_SPOT = BOX * BOX * 4 + 56   # 196 B ROI read + 56 B results written
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--spots", type=int, default=10_000_000, help="spots per GPU per step")
+    p.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    return p.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(seconds: float, threads: int):
+    """Time the CPU oracle on a bounded sample of the same workload."""
+    import oracle
+    from picasso_b200 import testing
+
+    oracle.build()
+    per_call = 4000 * threads
+    spots = testing.synthetic_spots(per_call, BOX, seed=12345)
+    oracle.gaussmle(spots[: 64 * threads], EPS, MAX_IT, METHOD, nthreads=threads)  # warm
+    done, t0 = 0, time.perf_counter()
+    while True:
+        oracle.gaussmle(spots, EPS, MAX_IT, METHOD, nthreads=threads)
+        done += per_call
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return done / el, done, el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm on the host CPU (oracle port)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    rates, n_done, t_tot = [], 0, 0.0
+    for i in range(args.warmup + args.steps):
+        r, d, el = cpu_oracle_rate(per_step_budget, threads)
+        if i >= args.warmup:
+            rates.append(r)
+            n_done += d
+            t_tot += el
+    value = n_done / t_tot
+    line = {
+        "impl": "reference", "metric": "MLE spot-fits/sec (7x7 ROI)", "value": value,
+        "unit": "fits/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 math / f32 state",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 7x7 MLE sigmaxy eps=1e-3 max_it=100 (bounded CPU sample)",
+                   "box": BOX, "method": METHOD},
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_done} spots in {t_tot:.1f} s, oracle C port of "
+                                   "picasso.gaussmle._mlefit_sigmaxy (bit-identical to the numba "
+                                   "reference), pthreads"},
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def gen_spots_device(torch, n, box, seed, device):
+    """Config-2 distribution generated on the GPU (torch) in chunks -> f32 (n, box, box)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, box, box), dtype=torch.float32, device=device)
+    c = box // 2
+    ii = torch.arange(box, device=device, dtype=torch.float64)[None, :]
+    step = 1_000_000
+    for lo in range(0, n, step):
+        m = min(step, n - lo)
+        u = torch.rand((6, m), generator=g, device=device, dtype=torch.float64)
+        x0 = c - 0.5 + u[0]
+        y0 = c - 0.5 + u[1]
+        sx = 0.9 + 0.4 * u[2]
+        sy = 0.9 + 0.4 * u[3]
+        ph = 500 + 4500 * u[4]
+        bg = 5 + 25 * u[5]
+
+        def dE(mu, s):
+            a = (ii - mu[:, None] + 0.5) / (math.sqrt(2) * s[:, None])
+            b = (ii - mu[:, None] - 0.5) / (math.sqrt(2) * s[:, None])
+            return 0.5 * (torch.erf(a) - torch.erf(b))
+
+        ex, ey = dE(x0, sx), dE(y0, sy)
+        mu = ph[:, None, None] * ey[:, :, None] * ex[:, None, :] + bg[:, None, None]
+        out[lo:lo + m] = torch.poisson(mu.float(), generator=g)
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from picasso_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    _lib.require_gpu()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.spots
+    spots = gen_spots_device(torch, n, BOX, 1000 + rank, dev)
+    # outputs of one rank live in one flat buffer so the multi-GPU gather is a
+    # single NCCL all-gather: [thetas 6n | crlbs 6n | logliks n | iterations n]
+    flat = torch.empty(14 * n, dtype=torch.float32, device=dev)
+    th, cr = flat[: 6 * n], flat[6 * n: 12 * n]
+    ll, it = flat[12 * n: 13 * n], flat[13 * n:].view(torch.int32)
+    gathered = torch.empty(14 * n * world, dtype=torch.float32, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step():
+        _lib.check(lib.pb_mle_fit_dev(n, BOX, spots.data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
+                                      cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
+                                      stream.cuda_stream))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, flat)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        k0[i].record()
+        _lib.check(lib.pb_mle_fit_dev(n, BOX, spots.data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
+                                      cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
+                                      stream.cuda_stream))
+        k1[i].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, flat)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
+    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_kernel = t.tolist()
+    mean_it = float(it.float().mean().item())
+    value = n * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end through the host-buffer C ABI (pinned host arrays) ----
+    e2e = None
+    if not args.no_e2e:
+        ne = n
+        hs = _lib.PinnedArray((ne, BOX, BOX), np.float32)
+        hth = _lib.PinnedArray((ne, 6), np.float32)
+        hcr = _lib.PinnedArray((ne, 6), np.float32)
+        hll = _lib.PinnedArray((ne,), np.float32)
+        hit = _lib.PinnedArray((ne,), np.int32)
+        torch.from_numpy(hs.array).copy_(spots.cpu())
+
+        def e2e_step():
+            _lib.check(lib.pb_mle_fit(ne, BOX, _lib.ptr(hs.array), EPS, MAX_IT, 1,
+                                      _lib.ptr(hth.array), _lib.ptr(hcr.array),
+                                      _lib.ptr(hll.array), _lib.ptr(hit.array), None, None))
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        el = tt.item()
+        # result sanity: e2e output equals the device-resident run
+        same = bool(np.array_equal(hit.array, it.cpu().numpy()))
+        e2e = {"value": ne * world * args.steps / el, "unit": "fits/s",
+               "h2d_bytes_per_step": ne * BOX * BOX * 4, "d2h_bytes_per_step": ne * 56,
+               "matches_device_run": same}
+        for h in (hs, hth, hcr, hll, hit):
+            h.free()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ach = BYTES_PER_SPOT * n / (ms_kernel * 1e-3) / 1e9
+        line = {
+            "metric": "MLE spot-fits/sec (7x7 ROI)", "value": value, "unit": "fits/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 math / f32 state", "data": "synthetic",
+            "config": {"workload": "configs[1]: 10M synthetic 7x7 spots/GPU, gaussmle sigmaxy "
+                                   "eps=1e-3 max_it=100", "box": BOX, "method": METHOD,
+                       "spots_per_gpu": n, "mean_iterations": mean_it,
+                       "l2": "input 1.96 GB per step >> 126 MB L2 (no flush needed)",
+                       "parallelism": f"spots sharded by index over {world} GPU(s)"
+                                      + ("; one NCCL all-gather of the packed outputs per step"
+                                         if world > 1 else "")},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": ms_kernel,
+                         "note": "algorithmic 252 B/spot; the fit is FP64-issue bound, not HBM bound "
+                                 "(SURVEY.md 8d) -- see DESIGN.md for the instruction roofline"},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            r, d, el = cpu_oracle_rate(args.cpu_seconds, threads)
+            line["cpu_baseline"] = {
+                "value": r, "unit": "fits/s", "cores": threads, "kind": "port",
+                "sample": f"{d} spots in {el:.1f} s (same distribution), oracle C port of "
+                          "picasso.gaussmle._mlefit_sigmaxy, bit-identical to the numba reference"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

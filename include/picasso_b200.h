@@ -1,0 +1,83 @@
+/*
+ * picasso_b200.h -- C ABI of libpicasso_b200.so: the B200 (sm_100a) implementation
+ * of picasso's single-molecule localization hot path.
+ *
+ * Conventions (the in-repo precedent for a native backend is Gpufit's ctypes
+ * binding, reference picasso/ext/pygpufit/gpufit.py:37-76, 199-366):
+ *   - every function returns an int status, 0 == PB_OK; on failure
+ *     pb_last_error() returns a thread-local message (cf. gpufit_get_last_error);
+ *   - the caller allocates every input and output as C-contiguous arrays and
+ *     passes raw pointers + sizes; the library never keeps a pointer after the
+ *     call returns;
+ *   - plain `foo()` entry points take HOST pointers (pageable or pinned) and
+ *     do the host<->device copies themselves, chunked and overlapped with the
+ *     kernels; `foo_dev()` entry points take DEVICE pointers on the current
+ *     CUDA device and are asynchronous on `stream` (a cudaStream_t passed as
+ *     void*; NULL = default stream);
+ *   - the library uses whichever device is current (cudaSetDevice / the
+ *     caller's torch.cuda.set_device); one process per GPU.
+ *
+ * Each entry point names the reference interface it replaces (file:line in
+ * jungmannlab/picasso @ 96e0da51).
+ */
+#ifndef PICASSO_B200_H
+#define PICASSO_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK 0
+#define PB_ERR_INVALID 1
+#define PB_ERR_CUDA 2
+#define PB_ERR_NOGPU 3
+#define PB_ERR_CAPACITY 4
+#define PB_ERR_CUFFT 5
+
+/* status flag bits written per spot by pb_mle_fit* (status array, nullable) */
+#define PB_MLE_FLAG_DEGENERATE_INIT 1 /* reference would raise ZeroDivisionError */
+#define PB_MLE_FLAG_PINV_FALLBACK 2   /* Fisher matrix singular: eigen pseudo-inverse used */
+#define PB_MLE_FLAG_NONFINITE 4       /* a CRLB entry is inf/nan */
+
+/* ---- library / device management ------------------------------------- */
+const char* pb_last_error(void);          /* cf. gpufit_get_last_error, gpufit.py:361-366 */
+const char* pb_version(void);
+int pb_device_count(void);                /* number of sm_100 devices visible (cf. gpufit cuda_available) */
+int pb_set_device(int device);            /* cudaSetDevice for the calling thread */
+int pb_synchronize(void);                 /* cudaDeviceSynchronize on the current device */
+/* pinned host memory for callers that want full PCIe speed (optional) */
+int pb_host_alloc(void** ptr, size_t bytes);
+int pb_host_free(void* ptr);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+long long pb_launch_count(void);
+
+/* ---- MLE Gaussian fit --------------------------------------------------
+ * Replaces picasso.gaussmle.gaussmle / gaussmle_async and the numba kernels
+ * _mlefit_sigmaxy / _mlefit_sigma (+ _crlb)      picasso/gaussmle.py:409-954.
+ *   spots      (n, box, box) float32, photons
+ *   eps        convergence criterion (Python float -> double)
+ *   max_it     maximum Newton iterations (0 => theta = start values)
+ *   method     0 = "sigma", 1 = "sigmaxy"; anything else -> PB_ERR_INVALID
+ *              with message "Method not available." (gaussmle.py:465)
+ *   thetas     (n, 6) float32  [x, y, photons, bg, sx, sy]
+ *   crlbs      (n, 6) float32
+ *   logliks    (n,)   float32
+ *   iterations (n,)   int32
+ *   status     (n,)   int32 flag bits, may be NULL
+ *   progress   nullable; the host variant stores the number of spots finished
+ *              so far (the reference's `current[0]`, gaussmle.py:386-406)
+ * box: odd, 5..21.
+ */
+int pb_mle_fit(size_t n, int box, const float* spots, double eps, int max_it, int method,
+               float* thetas, float* crlbs, float* logliks, int* iterations, int* status,
+               volatile long long* progress);
+int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double eps, int max_it, int method,
+                   float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
+                   int* d_status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICASSO_B200_H */

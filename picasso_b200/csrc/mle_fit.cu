@@ -1,0 +1,687 @@
+// picasso_b200/csrc/mle_fit.cu
+//
+// Per-spot 2-D Gaussian maximum-likelihood fit (Smith et al. 2010, integrated
+// pixel model, Poisson likelihood, per-parameter Newton steps, Fisher/CRLB) --
+// the B200 replacement for picasso.gaussmle._mlefit_sigmaxy / _mlefit_sigma
+// (reference picasso/gaussmle.py:533-954).
+//
+// Mapping (see DESIGN.md "MLE kernel"):
+//   * a cooperative group of G lanes owns one spot (G = 8 for box <= 7, 16 for
+//     box <= 15, 32 above) -> 32/G spots per warp in flight; all control flow
+//     is warp-uniform (converged groups are predicated off).
+//   * the model is separable: lane g evaluates the erf/exp terms of pixel
+//     EDGE g on both axes (box+1 edges per axis) -- 2 erf + 2 exp per lane per
+//     Newton iteration instead of the reference's 4 erf + 16 exp per PIXEL.
+//   * lane j then walks pixel row j (box pixels), accumulating the 2*n_par
+//     Newton sums in f64; sums are combined through shared memory and lane l
+//     applies the clamped Newton update for parameter l in float32 exactly as
+//     the reference does (theta is float32 state between iterations).
+//   * ROIs are staged into shared memory 4 spots at a time per warp with 1-D
+//     bulk async copies (TMA engine, mbarrier completion), double buffered.
+//   * CRLB: Fisher matrix in f64, diagonal of the inverse via a scaled
+//     Cholesky; singular / ill-conditioned matrices fall back to a Jacobi
+//     eigen pseudo-inverse with numpy's rcond=1e-15 (np.linalg.pinv semantics).
+//
+// No tensor cores: 2*n_par sums over box^2 pixels is not a dense contraction.
+#include <atomic>
+
+#include "pb_common.cuh"
+
+extern std::atomic<long long> g_pb_launches;
+
+namespace {
+
+constexpr double kInvSqrt2Pi = 0.3989422804014326779;   // 1/sqrt(2*pi)
+constexpr double kInvSqrt2 = 0.70710678118654757;        // gaussmle.py:276
+constexpr double kInvSqrtPi = 0.5641895835477562869;     // 1/sqrt(pi)
+constexpr int kTileSpots = 4;      // spots per TMA tile (per warp): 16*box^2 bytes
+constexpr int kWarpsPerBlock = 4;
+constexpr int kRedStride = 23;     // doubles per lane in the reduction scratch (22 + pad)
+
+struct MleArgs {
+    const float* spots;   // (n, box, box) f32, device
+    long long n;
+    double eps;
+    int max_it;
+    float* thetas;        // (n, 6)
+    float* crlbs;         // (n, 6)
+    float* logliks;       // (n,)
+    int* iterations;      // (n,)
+    int* status;          // (n,) nullable
+};
+
+template <int BOX, int G>
+struct MleSmem {
+    static constexpr int S = 32 / G;
+    static constexpr int PIX = BOX * BOX;
+    static constexpr int kRoiBytes = 2 * kTileSpots * PIX * 4;          // 2 stages
+    static constexpr int kFxBytes = S * 5 * BOX * 8;
+    static constexpr int kRedBytes = 32 * kRedStride * 8;
+    static constexpr int kSumBytes = S * 24 * 8;
+    static constexpr int kBarBytes = 16;
+    static constexpr int kPerWarp =
+        ((kRoiBytes + kFxBytes + kRedBytes + kSumBytes + kBarBytes + 127) / 128) * 128;
+    static constexpr int kTotal = kPerWarp * kWarpsPerBlock;
+};
+
+// ---- Jacobi eigen pseudo-inverse diagonal (rare fallback; np.linalg.pinv) --
+template <int NP>
+__device__ __noinline__ void pinv_diag_jacobi(const double* Msym /*NP*NP*/, double* diag) {
+    double A[NP * NP], V[NP * NP];
+    bool finite = true;
+    for (int i = 0; i < NP * NP; i++) {
+        A[i] = Msym[i];
+        finite = finite && isfinite(A[i]);
+    }
+    if (!finite) {
+        for (int i = 0; i < NP; i++) diag[i] = nan("");
+        return;
+    }
+    for (int i = 0; i < NP; i++)
+        for (int j = 0; j < NP; j++) V[i * NP + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0, dsum = 0.0;
+        for (int i = 0; i < NP; i++)
+            for (int j = 0; j < NP; j++) {
+                double v = A[i * NP + j] * A[i * NP + j];
+                if (i != j) off += v; else dsum += v;
+            }
+        if (off <= 1e-60 || off <= 1e-34 * dsum) break;
+        for (int p = 0; p < NP - 1; p++)
+            for (int q = p + 1; q < NP; q++) {
+                double apq = A[p * NP + q];
+                if (apq == 0.0) continue;
+                double th = (A[q * NP + q] - A[p * NP + p]) / (2.0 * apq);
+                double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                if (!isfinite(th)) t = 0.0;
+                double c = rsqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < NP; k++) {
+                    double akp = A[k * NP + p], akq = A[k * NP + q];
+                    A[k * NP + p] = c * akp - s * akq;
+                    A[k * NP + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < NP; k++) {
+                    double apk = A[p * NP + k], aqk = A[q * NP + k];
+                    A[p * NP + k] = c * apk - s * aqk;
+                    A[q * NP + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < NP; k++) {
+                    double vkp = V[k * NP + p], vkq = V[k * NP + q];
+                    V[k * NP + p] = c * vkp - s * vkq;
+                    V[k * NP + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double smax = 0.0;
+    for (int i = 0; i < NP; i++) smax = fmax(smax, fabs(A[i * NP + i]));
+    double cutoff = 1e-15 * smax;
+    for (int i = 0; i < NP; i++) {
+        double acc = 0.0;
+        for (int k = 0; k < NP; k++) {
+            double lam = A[k * NP + k];
+            if (fabs(lam) > cutoff) acc += V[i * NP + k] * V[i * NP + k] / lam;
+        }
+        diag[i] = acc;
+    }
+}
+
+// Diagonal of inv(M) for a symmetric positive-definite NP x NP matrix given as
+// its packed upper triangle m[idx(k,l)], k<=l (row-major packed).  Returns
+// false when the (diagonally scaled) Cholesky meets a non-positive / tiny
+// pivot -> caller falls back to the pseudo-inverse.
+template <int NP>
+__device__ __forceinline__ bool inv_diag_cholesky(const double* m, double* diag) {
+    auto idx = [](int k, int l) { return k * NP - (k * (k - 1)) / 2 + (l - k); };
+    double d[NP];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        double mii = m[idx(i, i)];
+        ok = ok && (mii > 0.0) && isfinite(mii);
+        d[i] = rsqrt(mii);
+    }
+    if (!ok) return false;
+    // scaled matrix C = D M D has unit diagonal; C = L L^T
+    double L[NP][NP];
+    double rl[NP];   // 1 / L[j][j]
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        double s = 1.0;
+#pragma unroll
+        for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+        ok = ok && (s > 1e-12);
+        rl[j] = rsqrt(s);
+        L[j][j] = s * rl[j];
+#pragma unroll
+        for (int i = j + 1; i < NP; i++) {
+            double c = m[idx(j, i)] * d[i] * d[j];
+#pragma unroll
+            for (int k = 0; k < j; k++) c -= L[i][k] * L[j][k];
+            L[i][j] = c * rl[j];
+        }
+    }
+    if (!ok) return false;
+    // X = inv(L) column by column; diag(inv(C))_j = sum_i X_ij^2
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        double X[NP];
+        double acc = 0.0;
+#pragma unroll
+        for (int i = j; i < NP; i++) {
+            double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = j; k < i; k++) s -= L[i][k] * X[k];
+            X[i] = s * rl[i];
+            acc += X[i] * X[i];
+        }
+        diag[j] = acc * d[j] * d[j];
+    }
+    return true;
+}
+
+template <int BOX, int G, int METHOD>   // METHOD 1 = sigmaxy (6 par), 0 = sigma (5 par)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+mle_fit_kernel(const MleArgs a) {
+    using SM = MleSmem<BOX, G>;
+    constexpr int S = SM::S;
+    constexpr int PIX = SM::PIX;
+    constexpr int NP = METHOD == 1 ? 6 : 5;
+    constexpr int NSUB = kTileSpots / S;
+    constexpr int NFISH = NP * (NP + 1) / 2;
+    static_assert(BOX + 1 <= G, "group too small for box");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int g = lane % G;         // lane within the spot group
+    const int grp = lane / G;       // group within the warp
+    unsigned char* wbase = smem_raw + warp * SM::kPerWarp;
+    float* roi = reinterpret_cast<float*>(wbase);                                 // [2][4*PIX]
+    double* fx = reinterpret_cast<double*>(wbase + SM::kRoiBytes) + grp * 5 * BOX;  // [5][BOX]
+    double* red = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kFxBytes);  // [32][23]
+    double* sums = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kFxBytes +
+                                             SM::kRedBytes) + grp * 24;          // [24]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + SM::kRoiBytes + SM::kFxBytes +
+                                                 SM::kRedBytes + SM::kSumBytes);  // [2]
+
+    const long long n = a.n;
+    const long long ntiles = (n + kTileSpots - 1) / kTileSpots;
+    const long long wstride = (long long)gridDim.x * kWarpsPerBlock;
+    long long tile = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(a.spots) & 15) == 0);
+    constexpr unsigned kTileBytes = kTileSpots * PIX * 4;
+
+    if (lane == 0) {
+        pb_mbar_init(&bars[0], 1);
+        pb_mbar_init(&bars[1], 1);
+        pb_mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto issue = [&](long long t, int stage) {
+        // full tiles via the TMA engine; the ragged tail tile by plain loads
+        const long long first = t * kTileSpots;
+        const bool full = tma_ok && (first + kTileSpots <= n);
+        float* dst = roi + stage * kTileSpots * PIX;
+        if (full) {
+            if (lane == 0) {
+                pb_fence_proxy_async();
+                pb_mbar_expect_tx(&bars[stage], kTileBytes);
+                pb_bulk_g2s(dst, a.spots + first * PIX, kTileBytes, &bars[stage]);
+            }
+        } else {
+            const long long avail = (n - first < kTileSpots ? n - first : kTileSpots) * PIX;
+            for (int i = lane; i < kTileSpots * PIX; i += 32)
+                dst[i] = i < avail ? a.spots[first * PIX + i] : 0.0f;
+        }
+        return full;
+    };
+
+    unsigned phase0 = 0, phase1 = 0;
+    bool cur_tma = false;
+    if (tile < ntiles) cur_tma = issue(tile, 0);
+    int stage = 0;
+
+    for (; tile < ntiles; tile += wstride, stage ^= 1) {
+        // prefetch the next tile into the other stage (it was fully consumed
+        // before the __syncwarp at the end of the previous trip)
+        bool next_tma = false;
+        if (tile + wstride < ntiles) next_tma = issue(tile + wstride, stage ^ 1);
+        if (cur_tma) {
+            if (stage == 0) { pb_mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+            else            { pb_mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+        }
+        __syncwarp();
+        const float* tile_roi = roi + stage * kTileSpots * PIX;
+
+#pragma unroll 1
+        for (int sub = 0; sub < NSUB; sub++) {
+            const int local = sub * S + grp;
+            const long long spot_idx = tile * kTileSpots + local;
+            const bool valid = spot_idx < n;
+            const float* sp = tile_roi + local * PIX;
+            int st_flags = 0;
+
+            // ---------------- initial parameters (gaussmle.py:28-168) -----
+            float th[6];
+            {
+                double rs_ = 0.0, rxs = 0.0;
+                if (g < BOX) {
+#pragma unroll
+                    for (int i = 0; i < BOX; i++) {
+                        double v = (double)sp[g * BOX + i];
+                        rs_ += v;
+                        rxs += v * (double)i;
+                    }
+                }
+                double sum = pb_gsum<G>(rs_);
+                double ysum = pb_gsum<G>(rs_ * (double)g);
+                double xsum = pb_gsum<G>(rxs);
+                double xc, yc;
+                if (sum <= 0.0) { sum = 0.01; yc = (BOX - 1) / 2.0; xc = (BOX - 1) / 2.0; }
+                else { yc = ysum / sum; xc = xsum / sum; }
+                // 3x3 edge-truncated mean filter, minimum (gaussmle.py:61-91,135)
+                float fmin_ = INFINITY;
+                if (g < BOX) {
+                    const int k = g;
+                    const int min_m = k - 1 < 0 ? 0 : k - 1, max_m = k + 2 > BOX ? BOX : k + 2;
+#pragma unroll
+                    for (int l = 0; l < BOX; l++) {
+                        const int min_n = l - 1 < 0 ? 0 : l - 1, max_n = l + 2 > BOX ? BOX : l + 2;
+                        double ns = 0.0;
+                        for (int m = min_m; m < max_m; m++)
+                            for (int q = min_n; q < max_n; q++) ns += (double)sp[m * BOX + q];
+                        float f = (float)(ns / (double)((max_m - min_m) * (max_n - min_n)));
+                        fmin_ = fminf(fmin_, f);
+                    }
+                }
+                const float bg = pb_gmin<G>(fmin_);
+                double ph = sum - (double)(BOX * BOX) * (double)bg;
+                ph = ph > 1.0 ? ph : 1.0;
+                // initial sigmas from the centre row / column of (spot - bg)
+                constexpr int H = BOX / 2;
+                double sdy = 0.0, sy_ = 0.0;
+                if (g < BOX) {
+                    float vy = sp[g * BOX + H] - bg;
+                    sdy = (double)vy * (double)((g - H) * (g - H));
+                    sy_ = (double)vy;
+                }
+                sdy = pb_gsum<G>(sdy);
+                sy_ = pb_gsum<G>(sy_);
+                double sdx = 0.0, sx_ = 0.0;
+#pragma unroll
+                for (int i = 0; i < BOX; i++) {
+                    float vx = sp[H * BOX + i] - bg;
+                    sdx += (double)vx * (double)((i - H) * (i - H));
+                    sx_ += (double)vx;
+                }
+                double sy0, sx0;
+                // the reference raises ZeroDivisionError when a sum is 0; we
+                // emit its 0.01 fallback and set status bit 0
+                if (sy_ == 0.0) { sy0 = 0.01; st_flags |= 1; } else sy0 = sqrt(sdy / sy_);
+                if (sx_ == 0.0) { sx0 = 0.01; st_flags |= 1; } else sx0 = sqrt(sdx / sx_);
+                if (!isfinite(sy0) || sy0 == 0.0) sy0 = 0.01;
+                if (!isfinite(sx0) || sx0 == 0.0) sx0 = 0.01;
+                th[0] = (float)xc; th[1] = (float)yc; th[2] = (float)ph; th[3] = bg;
+                if constexpr (METHOD == 1) { th[4] = (float)sx0; th[5] = (float)sy0; }
+                else { th[4] = (float)((sx0 + sy0) / 2.0); th[5] = th[4]; }
+            }
+            // max_step (gaussmle.py:558-561 / 770-773)
+            float ms_mine;
+            {
+                const float ms0 = th[4];
+                const float ms2 = (float)(0.1 * (double)th[2]);
+                const float ms3 = (float)(0.1 * (double)th[3]);
+                const float ms4 = (float)(0.2 * (double)th[4]);
+                const float ms5 = (float)(0.2 * (double)th[5]);
+                ms_mine = g < 2 ? ms0 : g == 2 ? ms2 : g == 3 ? ms3 : g == 4 ? ms4 : ms5;
+            }
+
+            // ---- shared 1-D machinery -------------------------------------
+            double PSFy, cy1, cy2, gy1, gy2;   // y factors of row g (registers)
+            auto eval_factors = [&]() {
+                // reciprocals of sigma, f32(sigma^2), f32(sigma^3), f32(sigma^5)
+                // (float32 ** int stays float32 in the reference): one per lane
+                const int ax = (METHOD == 1) ? ((g >> 2) & 1) : 0;
+                const float sig = ax ? th[5] : th[4];
+                const float s2f = sig * sig;
+                const float s3f = sig * s2f;
+                const float s5f = sig * (s2f * s2f);
+                const int kk_ = g & 3;
+                const double v = kk_ == 0 ? (double)sig : kk_ == 1 ? (double)s2f
+                                 : kk_ == 2 ? (double)s3f : (double)s5f;
+                const double r = 1.0 / v;
+                const double rsx = pb_gshfl<G>(r, 0), r2x = pb_gshfl<G>(r, 1);
+                const double r3x = pb_gshfl<G>(r, 2), r5x = pb_gshfl<G>(r, 3);
+                double rsy, r2y, r3y, r5y;
+                if constexpr (METHOD == 1) {
+                    rsy = pb_gshfl<G>(r, 4); r2y = pb_gshfl<G>(r, 5);
+                    r3y = pb_gshfl<G>(r, 6); r5y = pb_gshfl<G>(r, 7);
+                } else { rsy = rsx; r2y = r2x; r3y = r3x; r5y = r5x; }
+                const double sxd = (double)th[4], syd = (double)th[5];
+                // edge g: minus edge of pixel g == plus edge of pixel g-1 (exact)
+                const double ex = ((double)g - (double)th[0]) - 0.5;
+                const double ey = ((double)g - (double)th[1]) - 0.5;
+                const double Ex = erf(ex * (kInvSqrt2 * rsx));
+                const double Ey = erf(ey * (kInvSqrt2 * rsy));
+                const double tx = ex * rsx, ty = ey * rsy;
+                const double qx = 0.5 * tx * tx, qy = 0.5 * ty * ty;
+                const double Ax = exp(-qx), Ay = exp(-qy);
+                // plus-edge values from the next lane
+                const double Exp_ = pb_gshfl_down1<G>(Ex), Eyp_ = pb_gshfl_down1<G>(Ey);
+                const double Axp = pb_gshfl_down1<G>(Ax), Ayp = pb_gshfl_down1<G>(Ay);
+                const double exp_ = ex + 1.0, eyp_ = ey + 1.0;
+                const double PSFx = 0.5 * (Exp_ - Ex);
+                PSFy = 0.5 * (Eyp_ - Ey);
+                const double cx1 = (Ax - Axp) * rsx * kInvSqrt2Pi;
+                cy1 = (Ay - Ayp) * rsy * kInvSqrt2Pi;
+                const double cx2 = (ex * Ax - exp_ * Axp) * r3x * kInvSqrt2Pi;
+                cy2 = (ey * Ay - eyp_ * Ayp) * r3y * kInvSqrt2Pi;
+                double gx1, gx2;
+                if constexpr (METHOD == 1) {
+                    // _G uses exp(-(a^2)/(2*f32(sigma^2))): correct Ax by the
+                    // f32 rounding of sigma^2 (gaussmle.py:306-316)
+                    const double rhox = fma(sxd * sxd, r2x, -1.0), rhoy = fma(syd * syd, r2y, -1.0);
+                    const double zx = -qx * rhox, zy = -qy * rhoy;
+                    const double AGx = fma(Ax, fma(0.5 * zx, zx, zx), Ax);
+                    const double AGy = fma(Ay, fma(0.5 * zy, zy, zy), Ay);
+                    const double AGxp = pb_gshfl_down1<G>(AGx), AGyp = pb_gshfl_down1<G>(AGy);
+                    const double w1x = ex * AGx - exp_ * AGxp, w1y = ey * AGy - eyp_ * AGyp;
+                    const double w3x = ex * (ex * ex) * AGx - exp_ * (exp_ * exp_) * AGxp;
+                    const double w3y = ey * (ey * ey) * AGy - eyp_ * (eyp_ * eyp_) * AGyp;
+                    gx1 = w1x * r2x * kInvSqrt2Pi;
+                    gy1 = w1y * r2y * kInvSqrt2Pi;
+                    gx2 = (w3x * r5x - 2.0 * w1x * r3x) * kInvSqrt2Pi;
+                    gy2 = (w3y * r5y - 2.0 * w1y * r3y) * kInvSqrt2Pi;
+                } else {
+                    // isotropic sigma (gaussmle.py:339-383): dPSF/dsigma, d2PSF/dsigma2
+                    const double am = ex * (rsx * kInvSqrt2), ap = exp_ * (rsx * kInvSqrt2);
+                    const double bm = ey * (rsx * kInvSqrt2), bp = eyp_ * (rsx * kInvSqrt2);
+                    const double Fx = am * Ax - ap * Axp, Fy = bm * Ay - bp * Ayp;
+                    gx1 = Fx * rsx * kInvSqrtPi;      // dPSFxdt
+                    gy1 = Fy * rsx * kInvSqrtPi;
+                    const double dFx =
+                        (ap * Axp * (1.0 - 2.0 * ap * ap) - am * Ax * (1.0 - 2.0 * am * am)) * rsx;
+                    const double dFy =
+                        (bp * Ayp * (1.0 - 2.0 * bp * bp) - bm * Ay * (1.0 - 2.0 * bm * bm)) * rsx;
+                    const double rinvf = (double)(1.0f / th[4]);   // sigma ** (-1) is f32
+                    gx2 = kInvSqrtPi * (-Fx * r2x + rinvf * dFx);  // d2PSFxdt2
+                    gy2 = kInvSqrtPi * (-Fy * r2x + rinvf * dFy);
+                }
+                __syncwarp();   // previous readers of fx are done
+                if (g < BOX) {
+                    fx[0 * BOX + g] = PSFx; fx[1 * BOX + g] = cx1; fx[2 * BOX + g] = cx2;
+                    fx[3 * BOX + g] = gx1;  fx[4 * BOX + g] = gx2;
+                }
+                __syncwarp();
+            };
+
+            // ---------------- Newton iterations ---------------------------
+            int kk = 0;
+            bool done = !valid;
+            while (true) {
+                const bool active = !done && kk < a.max_it;
+                if (!__any_sync(0xffffffffu, active)) break;
+                eval_factors();
+                const double N = (double)th[2], bg = (double)th[3];
+                double num[6], den[6];
+#pragma unroll
+                for (int l = 0; l < 6; l++) num[l] = den[l] = 0.0;
+                if (g < BOX) {
+                    const float* rowp = sp + g * BOX;
+                    const double NPy = N * PSFy;
+#pragma unroll
+                    for (int i = 0; i < BOX; i++) {
+                        const double px = fx[0 * BOX + i], c1 = fx[1 * BOX + i], c2 = fx[2 * BOX + i];
+                        const double g1 = fx[3 * BOX + i], g2 = fx[4 * BOX + i];
+                        const double Npx = N * px;
+                        const double pp = px * PSFy;
+                        const double model = fma(Npx, PSFy, bg);
+                        const double data = (double)rowp[i];
+                        double cf = 0.0, df = 0.0;
+                        if (model > 10e-3) {
+                            const double inv = 1.0 / model;
+                            const double t = data * inv;
+                            cf = t - 1.0;
+                            df = t * inv;
+                        }
+                        cf = fmin(cf, 10e4);
+                        df = fmin(df, 10e4);
+                        const double d0 = NPy * c1, e0 = NPy * c2;
+                        const double d1 = Npx * cy1, e1 = Npx * cy2;
+                        num[0] = fma(cf, d0, num[0]); den[0] += fma(cf, e0, -df * d0 * d0);
+                        num[1] = fma(cf, d1, num[1]); den[1] += fma(cf, e1, -df * d1 * d1);
+                        num[2] = fma(cf, pp, num[2]); den[2] -= df * pp * pp;
+                        num[3] += cf;                  den[3] -= df;
+                        if constexpr (METHOD == 1) {
+                            const double d4 = NPy * g1, e4 = NPy * g2;
+                            const double d5 = Npx * gy1, e5 = Npx * gy2;
+                            num[4] = fma(cf, d4, num[4]); den[4] += fma(cf, e4, -df * d4 * d4);
+                            num[5] = fma(cf, d5, num[5]); den[5] += fma(cf, e5, -df * d5 * d5);
+                        } else {
+                            // dudt = N*(PSFy*dPx + PSFx*dPy); the reference's
+                            // d2udt2 has photons on the first term only (:380-382)
+                            const double d4 = N * (PSFy * g1 + px * gy1);
+                            const double e4 = NPy * g2 + 2.0 * g1 * gy1 + px * gy2;
+                            num[4] = fma(cf, d4, num[4]); den[4] += fma(cf, e4, -df * d4 * d4);
+                        }
+                    }
+                }
+                // combine over the group's lanes through shared memory
+                double* myred = red + lane * kRedStride;
+#pragma unroll
+                for (int l = 0; l < NP; l++) { myred[l] = num[l]; myred[6 + l] = den[l]; }
+                __syncwarp();
+                float th_new = 0.0f;
+                if (g < NP) {
+                    double sn = 0.0, sd = 0.0;
+                    const double* gr = red + (grp * G) * kRedStride;
+#pragma unroll
+                    for (int q = 0; q < BOX; q++) {
+                        sn += gr[q * kRedStride + g];
+                        sd += gr[q * kRedStride + 6 + g];
+                    }
+                    // clamped per-parameter Newton step in float32
+                    // (gaussmle.py:648-670, 860-884)
+                    const float nu = (float)sn, de = (float)sd;
+                    float thl = g == 0 ? th[0] : g == 1 ? th[1] : g == 2 ? th[2] : g == 3 ? th[3]
+                                : g == 4 ? th[4] : th[5];
+                    float upd;
+                    if (de == 0.0f) {
+                        if constexpr (METHOD == 1) {
+                            const float sg = nu > 0.f ? 1.f : (nu < 0.f ? -1.f : nu);
+                            upd = sg * ms_mine;
+                        } else {
+                            const float pr = nu * ms_mine;
+                            upd = pr > 0.f ? 1.f : (pr < 0.f ? -1.f : pr);
+                        }
+                    } else {
+                        upd = fminf(fmaxf(nu / de, -ms_mine), ms_mine);
+                    }
+                    thl -= upd;
+                    if (g == 2) thl = fmaxf(thl, 1.0f);
+                    if (g >= 3) thl = fmaxf(thl, 0.01f);
+                    if (METHOD == 0 && g == 4) thl = fminf(thl, (float)BOX);
+                    th_new = thl;
+                }
+                float tn[6];
+#pragma unroll
+                for (int l = 0; l < NP; l++) tn[l] = pb_gshfl<G>(th_new, l);
+                if (METHOD == 0) tn[5] = tn[4];
+                if (active) {
+                    kk++;
+                    bool conv = ((double)fabsf(th[0] - tn[0]) < a.eps) &&
+                                ((double)fabsf(th[1] - tn[1]) < a.eps);
+                    if (METHOD == 1)
+                        conv = conv && ((double)fabsf(th[4] - tn[4]) < a.eps) &&
+                               ((double)fabsf(th[5] - tn[5]) < a.eps);
+#pragma unroll
+                    for (int l = 0; l < 6; l++) th[l] = tn[l];
+                    if (conv) done = true;
+                }
+            }
+
+            // ---------------- CRLB + log-likelihood -----------------------
+            eval_factors();
+            {
+                const double N = (double)th[2], bg = (double)th[3];
+                double F[NFISH];
+                double ll = 0.0;
+#pragma unroll
+                for (int q = 0; q < NFISH; q++) F[q] = 0.0;
+                if (g < BOX) {
+                    const float* rowp = sp + g * BOX;
+                    const double NPy = N * PSFy;
+#pragma unroll
+                    for (int i = 0; i < BOX; i++) {
+                        const double px = fx[0 * BOX + i], c1 = fx[1 * BOX + i];
+                        const double g1 = fx[3 * BOX + i];
+                        const double Npx = N * px;
+                        const double model = fma(Npx, PSFy, bg);
+                        double du[NP];
+                        du[0] = NPy * c1;
+                        du[1] = Npx * cy1;
+                        du[2] = px * PSFy;
+                        du[3] = 1.0;
+                        if constexpr (METHOD == 1) { du[4] = NPy * g1; du[5] = Npx * gy1; }
+                        else du[4] = N * (PSFy * g1 + px * gy1);
+                        const double inv = 1.0 / model;
+                        int q = 0;
+#pragma unroll
+                        for (int k = 0; k < NP; k++) {
+                            const double dk = du[k] * inv;
+#pragma unroll
+                            for (int l = k; l < NP; l++) { F[q] = fma(du[l], dk, F[q]); q++; }
+                        }
+                        const float dataf = rowp[i];
+                        if (model > 0.0) {
+                            if (dataf > 0.0f)
+                                ll += (double)dataf * log(model) - model -
+                                      (double)(dataf * logf(dataf)) + (double)dataf;
+                            else
+                                ll -= model;
+                        }
+                    }
+                }
+                double* myred = red + lane * kRedStride;
+#pragma unroll
+                for (int q = 0; q < NFISH; q++) myred[q] = F[q];
+                myred[NFISH] = ll;
+                __syncwarp();
+                const double* gr = red + (grp * G) * kRedStride;
+                for (int q = g; q <= NFISH; q += G) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int r = 0; r < BOX; r++) s += gr[r * kRedStride + q];
+                    sums[q] = s;
+                }
+                __syncwarp();
+                double m[NFISH];
+#pragma unroll
+                for (int q = 0; q < NFISH; q++) m[q] = sums[q];
+                const double llsum = sums[NFISH];
+                double dg[NP];
+                bool ok = inv_diag_cholesky<NP>(m, dg);
+                if (!ok) {
+                    st_flags |= 2;
+                    double Mfull[NP * NP];
+                    int q = 0;
+                    for (int k = 0; k < NP; k++)
+                        for (int l = k; l < NP; l++) {
+                            Mfull[k * NP + l] = m[q];
+                            Mfull[l * NP + k] = m[q];
+                            q++;
+                        }
+                    pinv_diag_jacobi<NP>(Mfull, dg);
+                }
+                __syncwarp();
+                float cr = 0.f, tv = 0.f;
+#pragma unroll
+                for (int l = 0; l < NP; l++)
+                    if (g == l) { cr = (float)dg[l]; tv = th[l]; }
+                if (METHOD == 0 && g == 5) { cr = (float)dg[4]; tv = th[4]; }
+                const unsigned badmask = __ballot_sync(0xffffffffu, g < 6 && !isfinite(cr));
+                const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G));
+                if (badmask & gmask) st_flags |= 4;
+                if (valid) {
+                    if (g < 6) {
+                        a.thetas[spot_idx * 6 + g] = tv;
+                        a.crlbs[spot_idx * 6 + g] = cr;
+                    }
+                    if (g == 6) a.logliks[spot_idx] = (float)llsum;
+                    if (g == 7) a.iterations[spot_idx] = kk;
+                    if (a.status != nullptr && g == 0) a.status[spot_idx] = st_flags;
+                }
+            }
+        }   // sub
+        __syncwarp();   // everyone is done reading this stage before it is refilled
+        cur_tma = next_tma;
+    }
+}
+
+template <int BOX, int G, int METHOD>
+int launch_mle(const MleArgs& a, cudaStream_t stream) {
+    using SM = MleSmem<BOX, G>;
+    auto kern = mle_fit_kernel<BOX, G, METHOD>;
+    int blocks_per_sm = 0, num_sms = 0, dev = 0;
+    PB_CUDA_CHECK(cudaGetDevice(&dev));
+    PB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SM::kTotal));
+    PB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern,
+                                                                kWarpsPerBlock * 32, SM::kTotal));
+    if (blocks_per_sm < 1) {
+        pb_set_error("mle kernel does not fit on an SM (box=%d)", BOX);
+        return PB_ERR_CUDA;
+    }
+    const long long ntiles = (a.n + kTileSpots - 1) / kTileSpots;
+    long long want = (ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    long long cap = (long long)num_sms * blocks_per_sm;   // persistent: one wave
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, kWarpsPerBlock * 32, SM::kTotal, stream>>>(a);
+    g_pb_launches++;
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+template <int METHOD>
+int dispatch_box(int box, const MleArgs& a, cudaStream_t stream) {
+    switch (box) {
+        case 5:  return launch_mle<5, 8, METHOD>(a, stream);
+        case 7:  return launch_mle<7, 8, METHOD>(a, stream);
+        case 9:  return launch_mle<9, 16, METHOD>(a, stream);
+        case 11: return launch_mle<11, 16, METHOD>(a, stream);
+        case 13: return launch_mle<13, 16, METHOD>(a, stream);
+        case 15: return launch_mle<15, 16, METHOD>(a, stream);
+        case 17: return launch_mle<17, 32, METHOD>(a, stream);
+        case 19: return launch_mle<19, 32, METHOD>(a, stream);
+        case 21: return launch_mle<21, 32, METHOD>(a, stream);
+        default:
+            pb_set_error("unsupported box size %d (supported: odd 5..21)", box);
+            return PB_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+// Device-pointer entry point, asynchronous on `stream`.  Declared in
+// include/picasso_b200.h.
+extern "C" int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double eps, int max_it,
+                              int method, float* d_thetas, float* d_crlbs, float* d_logliks,
+                              int* d_iterations, int* d_status, void* stream) {
+    if (method != 0 && method != 1) {
+        pb_set_error("Method not available.");   // gaussmle.py:465
+        return PB_ERR_INVALID;
+    }
+    if (n == 0) return PB_OK;
+    if (!d_spots || !d_thetas || !d_crlbs || !d_logliks || !d_iterations) {
+        pb_set_error("pb_mle_fit_dev: null device pointer");
+        return PB_ERR_INVALID;
+    }
+    if (max_it < 0) max_it = 0;
+    MleArgs a{d_spots, (long long)n, eps, max_it, d_thetas, d_crlbs, d_logliks, d_iterations,
+              d_status};
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return method == 1 ? dispatch_box<1>(box, a, s) : dispatch_box<0>(box, a, s);
+}

@@ -1,0 +1,56 @@
+"""Deterministic synthetic inputs for the BASELINE.json configurations
+(SURVEY.md section 8d).  Used by tests/ and bench.py; not part of the hot path.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def _erf(x):
+    # vectorised erf without scipy dependency at import time
+    from scipy.special import erf
+
+    return erf(x)
+
+
+def synthetic_spots(n: int, box: int = 7, seed=0, return_truth: bool = False):
+    """Config 1/2 spots: integrated-pixel Gaussian + Poisson noise, float32.
+
+    x0, y0 ~ U(c-0.5, c+0.5), sigma_x, sigma_y ~ U(0.9, 1.3), photons ~
+    U(500, 5000), bg ~ U(5, 30); c = box // 2.
+    """
+    rng = np.random.default_rng(seed)
+    c = box // 2
+    x0 = rng.uniform(c - 0.5, c + 0.5, n)
+    y0 = rng.uniform(c - 0.5, c + 0.5, n)
+    sx = rng.uniform(0.9, 1.3, n)
+    sy = rng.uniform(0.9, 1.3, n)
+    ph = rng.uniform(500, 5000, n)
+    bg = rng.uniform(5, 30, n)
+    i = np.arange(box)[None, :]
+
+    def dE(mu, s):
+        a = (i - mu[:, None] + 0.5) / (math.sqrt(2) * s[:, None])
+        b = (i - mu[:, None] - 0.5) / (math.sqrt(2) * s[:, None])
+        return 0.5 * (_erf(a) - _erf(b))
+
+    ex, ey = dE(x0, sx), dE(y0, sy)
+    mu = ph[:, None, None] * ey[:, :, None] * ex[:, None, :] + bg[:, None, None]
+    spots = rng.poisson(mu).astype(np.float32)
+    if return_truth:
+        return spots, np.stack([x0, y0, ph, bg, sx, sy], 1)
+    return spots
+
+
+def synthetic_spots_chunked(n: int, box: int = 7, chunk: int = 100_000, seed: int = 0, out=None):
+    """Config 2: n spots generated in chunks with seeds SeedSequence(seed).spawn(k)."""
+    nchunks = (n + chunk - 1) // chunk
+    seeds = np.random.SeedSequence(seed).spawn(nchunks)
+    if out is None:
+        out = np.empty((n, box, box), np.float32)
+    for k in range(nchunks):
+        lo, hi = k * chunk, min(n, (k + 1) * chunk)
+        out[lo:hi] = synthetic_spots(hi - lo, box, seeds[k])
+    return out
