@@ -31,10 +31,18 @@ def test_mle_matches_oracle(box, method, oracle):
     assert r["same_it"] >= 0.99, r["same_it"]
     assert r["rms"][[0, 1, 4, 5]].max() <= 1e-4, r["rms"]      # px
     assert r["rel"][[2, 3]].max() <= 1e-4, r["rel"]            # photons, bg (relative)
-    crl = np.abs(r["cr"] - r["ocr"]) / np.abs(r["ocr"])
-    assert np.nanmax(crl) <= 1e-3, np.nanmax(crl)
-    assert np.sqrt(np.nanmean(crl ** 2)) <= 1e-5
-    assert np.abs(r["ll"] - r["oll"]).max() <= 2e-3 * max(1.0, np.abs(r["oll"]).max())
+    # spots whose iteration count agrees followed the same trajectory: their
+    # results must agree to float32 rounding; the <1 % that stopped one
+    # iteration apart differ by the size of that last Newton step
+    same = r["it"] == r["oit"]
+    dth = np.abs(r["th"][same] - r["oth"][same])
+    assert (dth[:, [0, 1, 4, 5]] <= 2e-5).all(), dth[:, [0, 1, 4, 5]].max()
+    crl = np.abs(r["cr"][same] - r["ocr"][same]) / np.abs(r["ocr"][same])
+    assert np.nanmax(crl) <= 1e-4, np.nanmax(crl)
+    crl_all = np.abs(r["cr"] - r["ocr"]) / np.abs(r["ocr"])
+    assert np.sqrt(np.nanmean(crl_all.astype(np.float64) ** 2)) <= 1e-4
+    dll = np.abs(r["ll"][same] - r["oll"][same])
+    assert (dll <= 1e-3 + 2e-6 * np.abs(r["oll"][same])).all(), dll.max()
 
 
 def test_mle_outputs_and_errors(oracle):
