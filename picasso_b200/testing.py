@@ -54,3 +54,32 @@ def synthetic_spots_chunked(n: int, box: int = 7, chunk: int = 100_000, seed: in
         lo, hi = k * chunk, min(n, (k + 1) * chunk)
         out[lo:hi] = synthetic_spots(hi - lo, box, seeds[k])
     return out
+
+
+def synthetic_movie(frames: int, Y: int, X: int, emitters_per_frame: int = 60, seed: int = 1,
+                    sigma: float = 1.1, amplitude: float = 2000.0, baseline: int = 100,
+                    bg: float = 20.0, margin: int = 8, return_truth: bool = False):
+    """Config 3 movie (SURVEY.md 8d): uint16 frames = baseline + Poisson(bg + emitters);
+    emitters are point-sampled Gaussians with peak `amplitude`, width `sigma`, at uniform
+    positions at least `margin` px from the border."""
+    rng = np.random.default_rng(seed)
+    movie = np.empty((frames, Y, X), np.uint16)
+    truth = []
+    yy = np.arange(Y, dtype=np.float64)[:, None]
+    xx = np.arange(X, dtype=np.float64)[None, :]
+    r = int(math.ceil(5 * sigma))
+    for f in range(frames):
+        mu = np.full((Y, X), bg, np.float64)
+        ex = rng.uniform(margin, X - margin, emitters_per_frame)
+        ey = rng.uniform(margin, Y - margin, emitters_per_frame)
+        for x0, y0 in zip(ex, ey):
+            y_lo, y_hi = max(0, int(y0) - r), min(Y, int(y0) + r + 1)
+            x_lo, x_hi = max(0, int(x0) - r), min(X, int(x0) + r + 1)
+            gy = np.exp(-0.5 * ((yy[y_lo:y_hi] - y0) / sigma) ** 2)
+            gx = np.exp(-0.5 * ((xx[:, x_lo:x_hi] - x0) / sigma) ** 2)
+            mu[y_lo:y_hi, x_lo:x_hi] += amplitude * gy * gx
+        movie[f] = np.minimum(baseline + rng.poisson(mu), 65535).astype(np.uint16)
+        truth.append(np.stack([np.full_like(ex, f), ex, ey], 1))
+    if return_truth:
+        return movie, np.concatenate(truth)
+    return movie

@@ -88,7 +88,85 @@ def gen_mle(ref):
     save("mle_float_spots.npz", **out)
 
 
-GENERATORS = {"mle": gen_mle}
+def gen_identify(ref):
+    """identify / get_spots golden vectors (reference localize.py:97-337, 917-1145)."""
+    from picasso_b200 import testing
+
+    loc = ref["localize"]
+    out = {}
+    rng = np.random.default_rng(7)
+    # 1) tie-heavy small-integer frames: pins the first-in-row-major argmax rule
+    cases = []
+    for k, box in enumerate((3, 5, 7, 9, 11, 13)):
+        Y, X = 40 + 3 * k, 52 - 2 * k
+        fr = rng.integers(0, 2 * box * box, (Y, X)).astype(np.float32)
+        y, x = loc._local_maxima(fr, box)
+        out[f"ties_b{box}_frame"] = fr
+        out[f"ties_b{box}_y"] = y
+        out[f"ties_b{box}_x"] = x
+        cases.append(len(y))
+    # 2) net-gradient wrap-around: bright last row / column, candidates at i == box_half
+    for box in (5, 7, 9):
+        Y, X = 30, 34
+        fr = rng.integers(0, 50, (Y, X)).astype(np.float32)
+        fr[-1, :] += 3000
+        fr[:, -1] += 2000
+        h = box // 2
+        fr[h, h] = 5000; fr[h, 17] = 4000; fr[15, h] = 4500; fr[12, 20] = 6000
+        y, x, ng = loc.identify_in_image(fr, -1e30, box)
+        out[f"wrap_b{box}_frame"] = fr
+        out[f"wrap_b{box}_y"] = y; out[f"wrap_b{box}_x"] = x; out[f"wrap_b{box}_ng"] = ng
+    # 3) realistic movie: serial identify, roi, frame bounds, get_spots
+    movie = testing.synthetic_movie(12, 64, 72, emitters_per_frame=10, seed=5)
+    out["movie"] = movie
+    for box, mng in ((7, 5000), (9, 8000), (5, 3000)):
+        ids = loc._identify_serial(movie, mng, box, None, None, None)
+        tag = f"mov_b{box}"
+        out[f"{tag}_frame"] = ids["frame"].to_numpy(); out[f"{tag}_x"] = ids["x"].to_numpy()
+        out[f"{tag}_y"] = ids["y"].to_numpy(); out[f"{tag}_ng"] = ids["net_gradient"].to_numpy()
+        cam = {"Baseline": 100, "Sensitivity": 0.45, "Gain": 2, "Qe": 0.9}
+        out[f"{tag}_spots"] = loc.get_spots(movie, ids, box, cam)
+    roi = ((10, 12), (50, 61))
+    ids = loc._identify_serial(movie, 5000, 7, roi, (3, 8), None)
+    out["roi_frame"] = ids["frame"].to_numpy(); out["roi_x"] = ids["x"].to_numpy()
+    out["roi_y"] = ids["y"].to_numpy(); out["roi_ng"] = ids["net_gradient"].to_numpy()
+    out["roi"] = np.array(roi); out["roi_frame_bounds"] = np.array([3, 8])
+    save("identify.npz", **out)
+    print("tie cases maxima counts:", cases)
+
+
+def gen_testdata(ref):
+    """Known answers on the reference's bundled test movie (tests/data/testdata.raw,
+    100x32x32 uint16; SURVEY.md 8c 'verified oracle outputs')."""
+    loc, gm, glq, rnd = ref["localize"], ref["gaussmle"], ref["gausslq"], ref["render"]
+    import pandas as pd
+
+    movie = np.fromfile(os.path.join(ref_import.REFERENCE_ROOT, "tests", "data", "testdata.raw"),
+                        dtype="<u2").reshape(100, 32, 32)
+    ids = loc._identify_serial(movie, 5000, 7, None, None, None)
+    cam = {"Baseline": 0, "Sensitivity": 1, "Gain": 1}
+    spots = loc.get_spots(movie, ids, 7, cam)
+    th, cr, ll, it = gm.gaussmle(spots, 0.001, 100, "sigmaxy")
+    ths, crs, lls, its = gm.gaussmle(spots, 0.001, 100, "sigma")
+    lq = glq.fit_spots(spots)
+    locs = gm.locs_from_fits(ids, th, cr, ll, it, 7)
+    info = [{"Height": 32, "Width": 32, "Frames": 100, "Pixelsize": 130}]
+    out = dict(movie=movie, ids_frame=ids["frame"].to_numpy(), ids_x=ids["x"].to_numpy(),
+               ids_y=ids["y"].to_numpy(), ids_ng=ids["net_gradient"].to_numpy(), spots=spots,
+               mle_thetas=th, mle_crlbs=cr, mle_logliks=ll, mle_iterations=it,
+               mles_thetas=ths, mles_crlbs=crs, mles_logliks=lls, mles_iterations=its,
+               lq_thetas=lq)
+    for c in locs.columns:
+        out[f"locs_{c}"] = locs[c].to_numpy()
+    for bm in (None, "gaussian", "gaussian_iso"):
+        n, img = rnd.render(locs, info, oversampling=20, blur_method=bm)
+        out[f"render_{bm}_n"] = np.array(n); out[f"render_{bm}_image"] = img
+    save("testdata.npz", **out)
+    print("testdata: n ids", len(ids), "sum ng", float(ids["net_gradient"].sum()),
+          "mean theta", th.mean(0))
+
+
+GENERATORS = {"mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata}
 
 
 def main():
