@@ -77,6 +77,63 @@ int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double eps, int max_
                    float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
                    int* d_status, void* stream);
 
+/* ---- spot identification ------------------------------------------------
+ * Replaces localize.identify_in_image / identify_in_frame / identify_by_frame_number
+ * and the frame loops _identify_serial / identify_async
+ * (picasso/localize.py:97-337, 340-421, 482-636).
+ *   movie        (n_frames, Y, X) uint16 (dtype 0) or float32 (dtype 1)
+ *   frame_offset number of movie[0] in the full movie (added to emitted frames)
+ *   box          odd, 3..15;  min_ng: keep spots with net_gradient > min_ng
+ *   roi          nullable int[4] = {y_start, x_start, y_end, x_end}: the frame is
+ *                sliced first (python slice semantics), coordinates are offset back
+ *   frame,x,y    int64 outputs, ng float32; capacity = their length
+ *   n_found      number of spots found; if it exceeds capacity the call returns
+ *                PB_ERR_CAPACITY and the caller retries with a larger buffer
+ * The host variant returns the spots sorted by (frame, y, x) -- the order of the
+ * serial reference; the _dev variant appends in arbitrary order and only
+ * advances *d_counter (a device uint64 the caller zeroes).
+ * Frame-bounds filtering (localize.py:395-409) is done by the caller by
+ * choosing which frames to pass. */
+#define PB_DTYPE_U16 0
+#define PB_DTYPE_F32 1
+int pb_identify(const void* movie, int dtype, size_t n_frames, int Y, int X,
+                long long frame_offset, int box, double min_ng, const int* roi,
+                long long* frame, long long* x, long long* y, float* ng, size_t capacity,
+                size_t* n_found);
+int pb_identify_dev(const void* d_movie, int dtype, size_t n_frames, int Y, int X,
+                    long long frame_offset, int box, double min_ng, const int* roi,
+                    long long* d_frame, long long* d_x, long long* d_y, float* d_ng,
+                    size_t capacity, unsigned long long* d_counter, void* stream);
+
+/* ---- ROI extraction + photon conversion ------------------------------------
+ * Replaces localize.get_spots = _cut_spots(_numba/_framebyframe) + _to_photons
+ * (picasso/localize.py:917-1145): spots[i] = (f32(movie[frame_i, y_i-r:y_i+r+1,
+ * x_i-r:x_i+r+1]) - baseline) * sensitivity / gain, float32 arithmetic.
+ * `movie` holds frames [frame_offset, frame_offset + n_frames); spots of other
+ * frames are left untouched (callers stream a memmapped movie chunk by chunk). */
+int pb_get_spots(const void* movie, int dtype, size_t n_frames, int Y, int X,
+                 long long frame_offset, size_t n, const long long* frame, const long long* x,
+                 const long long* y, int box, float baseline, float sensitivity, float gain,
+                 float* spots);
+int pb_get_spots_dev(const void* d_movie, int dtype, size_t n_frames, int Y, int X,
+                     long long frame_offset, size_t n, const long long* d_frame,
+                     const long long* d_x, const long long* d_y, int box, float baseline,
+                     float sensitivity, float gain, float* d_spots, void* stream);
+
+/* ---- least-squares Gaussian fit --------------------------------------------
+ * Replaces picasso.gausslq.fit_spot / fit_spots / fit_spots_parallel
+ * (picasso/gausslq.py:206-343: scipy.optimize.leastsq == MINPACK lmdif with
+ * ftol = xtol = 1e-2 on a float32-rounded point-sampled Gaussian) and stands in
+ * for the vendored Gpufit DLL call gpufit_constrained (ext/pygpufit/gpufit.py:40-61,
+ * gausslq.py:346-395).
+ *   spots  (n, box, box) float32;  box odd, 5..15
+ *   thetas (n, 6) float32 [x, y, photons, bg, sx, sy], x/y relative to the box centre
+ *   infos  (n,) int32 MINPACK info codes (1-4 converged), nullable
+ *   nfevs  (n,) int32 residual evaluations used, nullable */
+int pb_lq_fit(size_t n, int box, const float* spots, float* thetas, int* infos, int* nfevs);
+int pb_lq_fit_dev(size_t n, int box, const float* d_spots, float* d_thetas, int* d_infos,
+                  int* d_nfevs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,457 @@
+// picasso_b200/csrc/identify.cu
+//
+// Spot identification and ROI extraction on B200 -- replaces
+//   localize._local_maxima + _net_gradient + identify_in_image/identify_in_frame
+//       (reference picasso/localize.py:97-337)  -> pb_identify*
+//   localize._cut_spots_numba + _to_photons (get_spots)
+//       (reference picasso/localize.py:917-931, 1101-1145) -> pb_get_spots*
+//
+// identify kernel (fused local-max + net-gradient filter), one CTA per
+// TY x TX output tile of one frame:
+//   * the tile plus a halo is staged in shared memory with 16-byte vector
+//     loads (8 uint16 / 4 float per load) when the row pitch allows it;
+//   * thread j walks DOWN column j keeping the row-window maxima of the last
+//     2h+1 rows in registers (separable form of the reference's b x b argmax:
+//     centre > every window pixel before it in row-major order and >= every
+//     one after it -- np.argmax returns the first maximum);
+//   * a thread that finds a maximum evaluates the net gradient in float32 in
+//     the reference's row-major order with unfused IEEE ops, including the
+//     reference's negative-index wrap-around at the top/left scan border, and
+//     appends (frame, y, x, ng) if ng > minimum_ng.
+// HBM-bound by design: each pixel is read once (+ halo re-reads through L2).
+#include <algorithm>
+#include <atomic>
+#include <numeric>
+#include <vector>
+
+#include "pb_common.cuh"
+#include "../../include/picasso_b200.h"
+
+extern std::atomic<long long> g_pb_launches;
+
+namespace {
+
+constexpr int kTY = 32;     // output rows per tile
+constexpr int kTX = 128;    // output columns per tile == threads per CTA
+constexpr int kHP = 8;      // column halo in shared memory (>= h+1, keeps 16 B alignment)
+
+struct IdArgs {
+    const void* movie;      // frames [n_frames][Y][X]
+    long long n_frames;
+    int Y, X;               // full frame shape (row pitch X)
+    int y0, x0, Ys, Xs;     // ROI window (image = frame[y0:y0+Ys, x0:x0+Xs])
+    long long frame_offset; // added to the emitted frame number
+    float min_ng;           // compared as double below
+    double min_ng_d;
+    long long* out_frame;
+    long long* out_x;
+    long long* out_y;
+    float* out_ng;
+    unsigned long long capacity;
+    unsigned long long* counter;   // total found (may exceed capacity)
+};
+
+template <typename T> struct PixTraits;
+template <> struct PixTraits<unsigned short> {
+    using Vec = uint4;              // 8 pixels
+    static constexpr int kPerVec = 8;
+    __device__ static float to_f32(unsigned short v) { return (float)v; }
+};
+template <> struct PixTraits<float> {
+    using Vec = float4;             // 4 pixels
+    static constexpr int kPerVec = 4;
+    __device__ static float to_f32(float v) { return v; }
+};
+
+template <typename T>
+__device__ __forceinline__ T pmax(T a, T b) { return a > b ? a : b; }
+
+template <typename T, int H>
+__global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
+    constexpr int BOX = 2 * H + 1;
+    constexpr int ROWS = kTY + 2 * H + 2;   // window halo H + gradient halo 1
+    constexpr int COLS = kTX + 2 * kHP;
+    static_assert(H + 1 <= kHP, "halo too small");
+    __shared__ __align__(16) T tile[ROWS][COLS];
+    __shared__ float ux[BOX * BOX], uy[BOX * BOX];
+
+    const int tid = threadIdx.x;
+    const long long f = blockIdx.z;
+    const int ty0 = blockIdx.y * kTY;            // first output row (image coords)
+    const int tx0 = blockIdx.x * kTX;            // first output column (image coords)
+    const T* frame = static_cast<const T*>(a.movie) + (size_t)f * a.Y * a.X;
+    // image(r, c) = frame[(y0 + r) * X + (x0 + c)], valid for 0<=r<Ys, 0<=c<Xs
+
+    // unit vectors towards the centre (localize.py:279-286), float32 IEEE ops
+    for (int q = tid; q < BOX * BOX; q += kTX) {
+        const float vx = (float)(H - q % BOX), vy = (float)(H - q / BOX);
+        const float un = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+        ux[q] = __fdiv_rn(vx, un);
+        uy[q] = __fdiv_rn(vy, un);
+    }
+
+    // ---- stage the tile: rows ty0-H-1 .. ty0+kTY+H, cols tx0-kHP .. tx0+kTX+kHP-1
+    {
+        using V = typename PixTraits<T>::Vec;
+        constexpr int PV = PixTraits<T>::kPerVec;
+        const bool vec_ok = ((a.X % PV) == 0) && ((a.x0 % PV) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(a.movie) & 15) == 0);
+        constexpr int VPR = COLS / PV;   // vectors per tile row
+        for (int idx = tid; idx < ROWS * VPR; idx += kTX) {
+            const int tr = idx / VPR, tv = idx % VPR;
+            const int r = ty0 - H - 1 + tr;
+            const int c = tx0 - kHP + tv * PV;
+            T* dst = &tile[tr][tv * PV];
+            if (r >= 0 && r < a.Ys && c >= 0 && c + PV <= a.Xs && vec_ok) {
+                *reinterpret_cast<V*>(dst) =
+                    __ldg(reinterpret_cast<const V*>(frame + (size_t)(a.y0 + r) * a.X + a.x0 + c));
+            } else {
+#pragma unroll
+                for (int k = 0; k < PV; k++) {
+                    const int cc = c + k;
+                    dst[k] = (r >= 0 && r < a.Ys && cc >= 0 && cc < a.Xs)
+                                 ? frame[(size_t)(a.y0 + r) * a.X + a.x0 + cc]
+                                 : T(0);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int j = tx0 + tid;                 // image column of this thread
+    const int tc = kHP + tid;                // tile column
+    // scan range of the reference: i in [H, Ys-H-1), j in [H, Xs-H-1)
+    const bool col_ok = (j >= H) && (j < a.Xs - H - 1);
+
+    // rolling state: row-window maxima of the last 2H+1 rows; centre/left/right
+    // of the last H+1 rows
+    T rm[2 * H + 1], cc[H + 1], ll[H + 1], rr[H + 1];
+    unsigned candmask = 0;   // bit u set: (ty0 + u, j) is a local maximum
+#pragma unroll
+    for (int k = 0; k < 2 * H + 1; k++) rm[k] = T(0);
+#pragma unroll
+    for (int k = 0; k < H + 1; k++) { cc[k] = T(0); ll[k] = T(0); rr[k] = T(0); }
+
+#pragma unroll
+    for (int t = 0; t < kTY + 2 * H; t++) {
+        // tile row t+1 <-> image row ty0 - H + t
+        const T* row = &tile[t + 1][tc];
+        T L = row[-H], R = row[1];
+#pragma unroll
+        for (int k = 1; k < H; k++) { L = pmax(L, row[-H + k]); R = pmax(R, row[1 + k]); }
+        const T Cv = row[0];
+        const T RM = pmax(pmax(L, R), Cv);
+#pragma unroll
+        for (int k = 0; k < 2 * H; k++) rm[k] = rm[k + 1];
+        rm[2 * H] = RM;
+#pragma unroll
+        for (int k = 0; k < H; k++) { cc[k] = cc[k + 1]; ll[k] = ll[k + 1]; rr[k] = rr[k + 1]; }
+        cc[H] = Cv; ll[H] = L; rr[H] = R;
+        if (t >= 2 * H) {
+            const int u = t - 2 * H;             // output row within the tile
+            const int i = ty0 + u;               // image row of the window centre
+            // window rows are rm[0..2H]; centre row values are cc[0], ll[0], rr[0]
+            T above = rm[0], below = rm[H + 1];
+#pragma unroll
+            for (int k = 1; k < H; k++) { above = pmax(above, rm[k]); below = pmax(below, rm[H + 1 + k]); }
+            const T c0 = cc[0];
+            const bool is_max = col_ok && (i >= H) && (i < a.Ys - H - 1) && (c0 > above) &&
+                                (c0 > ll[0]) && (c0 >= rr[0]) && (c0 >= below);
+            if (is_max) candmask |= (1u << u);
+        }
+    }
+
+    // ---- net gradient for the (rare) maxima (localize.py:202-244): float32,
+    // row-major accumulation, unfused IEEE ops, negative-index wrap-around
+    while (candmask) {
+        const int u = __ffs(candmask) - 1;
+        candmask &= candmask - 1;
+        const int i = ty0 + u;
+        float acc = 0.0f;
+        const int tr_c = u + H + 1;      // tile row of the centre
+        for (int kk = -H; kk <= H; kk++) {
+            for (int mm = -H; mm <= H; mm++) {
+                if (kk == 0 && mm == 0) continue;
+                const int k = i + kk, m = j + mm;
+                float up, lf;
+                const float dn = PixTraits<T>::to_f32(tile[tr_c + kk + 1][tc + mm]);
+                const float rt = PixTraits<T>::to_f32(tile[tr_c + kk][tc + mm + 1]);
+                if (k - 1 >= 0) up = PixTraits<T>::to_f32(tile[tr_c + kk - 1][tc + mm]);
+                else  // numba negative index: frame[-1] is the LAST image row
+                    up = PixTraits<T>::to_f32(frame[(size_t)(a.y0 + a.Ys - 1) * a.X + a.x0 + m]);
+                if (m - 1 >= 0) lf = PixTraits<T>::to_f32(tile[tr_c + kk][tc + mm - 1]);
+                else
+                    lf = PixTraits<T>::to_f32(frame[(size_t)(a.y0 + k) * a.X + a.x0 + a.Xs - 1]);
+                const float gy = __fsub_rn(dn, up);
+                const float gx = __fsub_rn(rt, lf);
+                const int q = (kk + H) * BOX + (mm + H);
+                const float tsum = __fadd_rn(__fmul_rn(gy, uy[q]), __fmul_rn(gx, ux[q]));
+                acc = __fadd_rn(acc, tsum);
+            }
+        }
+        if ((double)acc > a.min_ng_d) {
+            const unsigned long long slot = atomicAdd(a.counter, 1ull);
+            if (slot < a.capacity) {
+                a.out_frame[slot] = f + a.frame_offset;
+                a.out_y[slot] = i + a.y0;
+                a.out_x[slot] = j + a.x0;
+                a.out_ng[slot] = acc;
+            }
+        }
+    }
+}
+
+template <typename T>
+int launch_identify(const IdArgs& a, int box, cudaStream_t stream) {
+    if (a.Ys <= 0 || a.Xs <= 0 || a.n_frames <= 0) return PB_OK;
+    dim3 grid((a.Xs + kTX - 1) / kTX, (a.Ys + kTY - 1) / kTY, 1);
+    // gridDim.z is limited to 65535: loop over frame batches
+    const long long zmax = 32768;
+    for (long long f0 = 0; f0 < a.n_frames; f0 += zmax) {
+        IdArgs b = a;
+        const long long nf = std::min(zmax, a.n_frames - f0);
+        size_t fsz = (size_t)a.Y * a.X * sizeof(T);
+        b.movie = static_cast<const char*>(a.movie) + (size_t)f0 * fsz;
+        b.n_frames = nf;
+        b.frame_offset = a.frame_offset + f0;
+        grid.z = (unsigned)nf;
+        switch (box / 2) {
+            case 1: identify_kernel<T, 1><<<grid, kTX, 0, stream>>>(b); break;
+            case 2: identify_kernel<T, 2><<<grid, kTX, 0, stream>>>(b); break;
+            case 3: identify_kernel<T, 3><<<grid, kTX, 0, stream>>>(b); break;
+            case 4: identify_kernel<T, 4><<<grid, kTX, 0, stream>>>(b); break;
+            case 5: identify_kernel<T, 5><<<grid, kTX, 0, stream>>>(b); break;
+            case 6: identify_kernel<T, 6><<<grid, kTX, 0, stream>>>(b); break;
+            case 7: identify_kernel<T, 7><<<grid, kTX, 0, stream>>>(b); break;
+            default:
+                pb_set_error("unsupported box size %d for identify (odd 3..15)", box);
+                return PB_ERR_INVALID;
+        }
+        g_pb_launches++;
+        PB_CUDA_CHECK(cudaGetLastError());
+    }
+    return PB_OK;
+}
+
+// ---- ROI gather + photon conversion ----------------------------------------
+struct CutArgs {
+    const void* movie;
+    long long n_frames;        // frames present in `movie`
+    long long frame_offset;    // movie[0] is frame number frame_offset
+    int Y, X, box;
+    const long long* frame;
+    const long long* x;
+    const long long* y;
+    long long n;
+    float baseline, sensitivity, gain;
+    float* spots;
+};
+
+template <typename T>
+__global__ void cut_spots_kernel(const CutArgs a) {
+    const int pix = a.box * a.box;
+    const long long total = a.n * pix;
+    const int r = a.box / 2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long id = idx / pix;
+        const int p = (int)(idx - id * pix);
+        const long long fr = a.frame[id] - a.frame_offset;
+        if (fr < 0 || fr >= a.n_frames) continue;     // spot belongs to another chunk
+        const int yy = (int)a.y[id] - r + p / a.box;
+        const int xx = (int)a.x[id] - r + p % a.box;
+        const T* frame = static_cast<const T*>(a.movie) + (size_t)fr * a.Y * a.X;
+        // out-of-frame windows cannot come from identify(); clamp defensively
+        const int yc = min(max(yy, 0), a.Y - 1), xc = min(max(xx, 0), a.X - 1);
+        const float s = PixTraits<T>::to_f32(frame[(size_t)yc * a.X + xc]);
+        // (spots - baseline) * sensitivity / gain in float32 (localize.py:1106-1112)
+        a.spots[idx] = __fdiv_rn(__fmul_rn(__fsub_rn(s, a.baseline), a.sensitivity), a.gain);
+    }
+}
+
+}  // namespace
+
+extern "C" int pb_identify_dev(const void* d_movie, int dtype, size_t n_frames, int Y, int X,
+                               long long frame_offset, int box, double min_ng, const int* roi,
+                               long long* d_frame, long long* d_x, long long* d_y, float* d_ng,
+                               size_t capacity, unsigned long long* d_counter, void* stream) {
+    if (box < 3 || box > 15 || (box & 1) == 0) {
+        pb_set_error("unsupported box size %d for identify (odd 3..15)", box);
+        return PB_ERR_INVALID;
+    }
+    if (dtype != PB_DTYPE_U16 && dtype != PB_DTYPE_F32) {
+        pb_set_error("unsupported movie dtype %d (0 = uint16, 1 = float32)", dtype);
+        return PB_ERR_INVALID;
+    }
+    IdArgs a{};
+    a.movie = d_movie; a.n_frames = (long long)n_frames; a.Y = Y; a.X = X;
+    a.y0 = 0; a.x0 = 0; a.Ys = Y; a.Xs = X;
+    if (roi) {   // ((y0, x0), (y1, x1)) with python slice clamping
+        int y0 = roi[0], x0 = roi[1], y1 = roi[2], x1 = roi[3];
+        if (y0 < 0) y0 += Y; if (x0 < 0) x0 += X; if (y1 < 0) y1 += Y; if (x1 < 0) x1 += X;
+        y0 = std::max(0, std::min(y0, Y)); x0 = std::max(0, std::min(x0, X));
+        y1 = std::max(y0, std::min(y1, Y)); x1 = std::max(x0, std::min(x1, X));
+        a.y0 = y0; a.x0 = x0; a.Ys = y1 - y0; a.Xs = x1 - x0;
+    }
+    a.frame_offset = frame_offset;
+    a.min_ng_d = min_ng; a.min_ng = (float)min_ng;
+    a.out_frame = d_frame; a.out_x = d_x; a.out_y = d_y; a.out_ng = d_ng;
+    a.capacity = capacity; a.counter = d_counter;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return dtype == PB_DTYPE_U16 ? launch_identify<unsigned short>(a, box, s)
+                                 : launch_identify<float>(a, box, s);
+}
+
+extern "C" int pb_get_spots_dev(const void* d_movie, int dtype, size_t n_frames, int Y, int X,
+                                long long frame_offset, size_t n, const long long* d_frame,
+                                const long long* d_x, const long long* d_y, int box, float baseline,
+                                float sensitivity, float gain, float* d_spots, void* stream) {
+    if (box < 1 || (box & 1) == 0) { pb_set_error("box must be odd"); return PB_ERR_INVALID; }
+    if (dtype != PB_DTYPE_U16 && dtype != PB_DTYPE_F32) {
+        pb_set_error("unsupported movie dtype %d", dtype);
+        return PB_ERR_INVALID;
+    }
+    if (n == 0) return PB_OK;
+    CutArgs a{d_movie, (long long)n_frames, frame_offset, Y, X, box, d_frame, d_x, d_y,
+              (long long)n, baseline, sensitivity, gain, d_spots};
+    const long long total = (long long)n * box * box;
+    int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == PB_DTYPE_U16) cut_spots_kernel<unsigned short><<<grid, 256, 0, s>>>(a);
+    else cut_spots_kernel<float><<<grid, 256, 0, s>>>(a);
+    g_pb_launches++;
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+// ---- host-buffer entry points ------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        PB_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
+        return PB_OK;
+    }
+};
+inline size_t dtype_size(int dtype) { return dtype == PB_DTYPE_U16 ? 2 : 4; }
+}  // namespace
+
+// Identify over a host movie chunk; results sorted by (frame, y, x) like the
+// serial reference (localize.py:604-636).  If more than `capacity` spots are
+// found, *n_found holds the required capacity and PB_ERR_CAPACITY is returned.
+extern "C" int pb_identify(const void* movie, int dtype, size_t n_frames, int Y, int X,
+                           long long frame_offset, int box, double min_ng, const int* roi,
+                           long long* frame, long long* x, long long* y, float* ng,
+                           size_t capacity, size_t* n_found) {
+    if (!n_found) { pb_set_error("pb_identify: n_found is null"); return PB_ERR_INVALID; }
+    *n_found = 0;
+    if (n_frames == 0) return PB_OK;
+    if (!movie) { pb_set_error("pb_identify: null movie"); return PB_ERR_INVALID; }
+    const size_t fsz = (size_t)Y * X * dtype_size(dtype);
+    // frame chunks of ~128 MB, double buffered H2D
+    size_t chunk = std::max<size_t>(1, (128u << 20) / fsz);
+    chunk = std::min(chunk, n_frames);
+    DevBuf mv[2], dfr, dx, dy, dng, dcnt;
+    int rc;
+    for (int s = 0; s < 2; s++) if ((rc = mv[s].alloc(chunk * fsz))) return rc;
+    const size_t cap = std::max<size_t>(capacity, 1);
+    if ((rc = dfr.alloc(cap * 8)) || (rc = dx.alloc(cap * 8)) || (rc = dy.alloc(cap * 8)) ||
+        (rc = dng.alloc(cap * 4)) || (rc = dcnt.alloc(8)))
+        return rc;
+    cudaStream_t st[2];
+    cudaEvent_t ev[2];
+    for (int s = 0; s < 2; s++) {
+        PB_CUDA_CHECK(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+        PB_CUDA_CHECK(cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming));
+    }
+    PB_CUDA_CHECK(cudaMemsetAsync(dcnt.p, 0, 8, st[0]));
+    PB_CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    size_t c = 0;
+    rc = PB_OK;
+    for (size_t f0 = 0; f0 < n_frames && rc == PB_OK; f0 += chunk, c++) {
+        const int s = (int)(c & 1);
+        const size_t nf = std::min(chunk, n_frames - f0);
+        if (c >= 2) cudaEventSynchronize(ev[s]);
+        cudaMemcpyAsync(mv[s].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz,
+                        cudaMemcpyHostToDevice, st[s]);
+        rc = pb_identify_dev(mv[s].p, dtype, nf, Y, X, frame_offset + (long long)f0, box, min_ng,
+                             roi, static_cast<long long*>(dfr.p), static_cast<long long*>(dx.p),
+                             static_cast<long long*>(dy.p), static_cast<float*>(dng.p), capacity,
+                             static_cast<unsigned long long*>(dcnt.p), st[s]);
+        cudaEventRecord(ev[s], st[s]);
+    }
+    for (int s = 0; s < 2; s++) cudaStreamSynchronize(st[s]);
+    unsigned long long found = 0;
+    cudaError_t e = cudaMemcpy(&found, dcnt.p, 8, cudaMemcpyDeviceToHost);
+    for (int s = 0; s < 2; s++) { cudaStreamDestroy(st[s]); cudaEventDestroy(ev[s]); }
+    if (rc != PB_OK) return rc;
+    if (e != cudaSuccess) { pb_set_error("pb_identify: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    *n_found = (size_t)found;
+    if (found > capacity) {
+        pb_set_error("pb_identify: found %llu spots, capacity %zu", found, capacity);
+        return PB_ERR_CAPACITY;
+    }
+    if (found == 0) return PB_OK;
+    std::vector<long long> hf(found), hx(found), hy(found);
+    std::vector<float> hn(found);
+    PB_CUDA_CHECK(cudaMemcpy(hf.data(), dfr.p, found * 8, cudaMemcpyDeviceToHost));
+    PB_CUDA_CHECK(cudaMemcpy(hx.data(), dx.p, found * 8, cudaMemcpyDeviceToHost));
+    PB_CUDA_CHECK(cudaMemcpy(hy.data(), dy.p, found * 8, cudaMemcpyDeviceToHost));
+    PB_CUDA_CHECK(cudaMemcpy(hn.data(), dng.p, found * 4, cudaMemcpyDeviceToHost));
+    std::vector<size_t> order(found);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](size_t p, size_t q) {
+        if (hf[p] != hf[q]) return hf[p] < hf[q];
+        if (hy[p] != hy[q]) return hy[p] < hy[q];
+        return hx[p] < hx[q];
+    });
+    for (size_t k = 0; k < found; k++) {
+        frame[k] = hf[order[k]]; x[k] = hx[order[k]]; y[k] = hy[order[k]]; ng[k] = hn[order[k]];
+    }
+    return PB_OK;
+}
+
+// get_spots over a host movie chunk: spots whose frame lies in
+// [frame_offset, frame_offset + n_frames) are written, others left untouched.
+extern "C" int pb_get_spots(const void* movie, int dtype, size_t n_frames, int Y, int X,
+                            long long frame_offset, size_t n, const long long* frame,
+                            const long long* x, const long long* y, int box, float baseline,
+                            float sensitivity, float gain, float* spots) {
+    if (n == 0 || n_frames == 0) return PB_OK;
+    if (!movie || !frame || !x || !y || !spots) { pb_set_error("pb_get_spots: null pointer"); return PB_ERR_INVALID; }
+    const size_t pix = (size_t)box * box;
+    // only the spots that fall into this chunk are gathered (ids are normally frame-sorted)
+    std::vector<size_t> sel;
+    sel.reserve(n);
+    for (size_t k = 0; k < n; k++)
+        if (frame[k] >= frame_offset && frame[k] < frame_offset + (long long)n_frames) sel.push_back(k);
+    if (sel.empty()) return PB_OK;
+    const size_t m = sel.size();
+    std::vector<long long> hf(m), hx(m), hy(m);
+    for (size_t k = 0; k < m; k++) { hf[k] = frame[sel[k]]; hx[k] = x[sel[k]]; hy[k] = y[sel[k]]; }
+    const size_t fsz = (size_t)Y * X * dtype_size(dtype);
+    DevBuf mv, dfr, dx, dy, dsp;
+    int rc;
+    // upload only the frame range that is actually referenced
+    long long fmin = hf[0], fmax = hf[0];
+    for (size_t k = 1; k < m; k++) { fmin = std::min(fmin, hf[k]); fmax = std::max(fmax, hf[k]); }
+    const size_t nf = (size_t)(fmax - fmin + 1);
+    if ((rc = mv.alloc(nf * fsz)) || (rc = dfr.alloc(m * 8)) || (rc = dx.alloc(m * 8)) ||
+        (rc = dy.alloc(m * 8)) || (rc = dsp.alloc(m * pix * 4)))
+        return rc;
+    PB_CUDA_CHECK(cudaMemcpy(mv.p, static_cast<const char*>(movie) + (size_t)(fmin - frame_offset) * fsz,
+                             nf * fsz, cudaMemcpyHostToDevice));
+    PB_CUDA_CHECK(cudaMemcpy(dfr.p, hf.data(), m * 8, cudaMemcpyHostToDevice));
+    PB_CUDA_CHECK(cudaMemcpy(dx.p, hx.data(), m * 8, cudaMemcpyHostToDevice));
+    PB_CUDA_CHECK(cudaMemcpy(dy.p, hy.data(), m * 8, cudaMemcpyHostToDevice));
+    rc = pb_get_spots_dev(mv.p, dtype, nf, Y, X, fmin, m, static_cast<long long*>(dfr.p),
+                          static_cast<long long*>(dx.p), static_cast<long long*>(dy.p), box,
+                          baseline, sensitivity, gain, static_cast<float*>(dsp.p), nullptr);
+    if (rc != PB_OK) return rc;
+    std::vector<float> hs(m * pix);
+    PB_CUDA_CHECK(cudaMemcpy(hs.data(), dsp.p, m * pix * 4, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < m; k++)
+        memcpy(spots + sel[k] * pix, hs.data() + k * pix, pix * 4);
+    return PB_OK;
+}

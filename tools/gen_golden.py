@@ -165,8 +165,29 @@ def gen_testdata(ref):
     print("testdata: n ids", len(ids), "sum ng", float(ids["net_gradient"].sum()),
           "mean theta", th.mean(0))
 
+def gen_lq(ref):
+    """gausslq.fit_spots golden vectors (scipy.optimize.leastsq / MINPACK lmdif path,
+    reference gausslq.py:206-289)."""
+    from picasso_b200 import testing
 
-GENERATORS = {"mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata}
+    glq = ref["gausslq"]
+    out = {}
+    for box, n in ((7, 3000), (5, 300), (9, 300), (11, 300), (13, 300)):
+        spots = testing.synthetic_spots(n, box, seed=200 + box)
+        out[f"b{box}_spots_u16"] = spots.astype(np.uint16)
+        out[f"b{box}_thetas"] = glq.fit_spots(spots)
+    # noiseless point-sampled float spots (tests/conftest.py:121-154 regime)
+    g = np.load(os.path.join(GOLD, "mle_float_spots.npz"))
+    out["float_spots"] = g["spots"]
+    out["float_thetas"] = glq.fit_spots(g["spots"])
+    # photon-converted movie ROIs (non-integer, negative values possible)
+    idg = np.load(os.path.join(GOLD, "identify.npz"))
+    out["movie_spots"] = idg["mov_b7_spots"]
+    out["movie_thetas"] = glq.fit_spots(idg["mov_b7_spots"])
+    save("lq.npz", **out)
+
+
+GENERATORS = {"mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq}
 
 
 def main():
