@@ -134,6 +134,32 @@ int pb_lq_fit(size_t n, int box, const float* spots, float* thetas, int* infos, 
 int pb_lq_fit_dev(size_t n, int box, const float* d_spots, float* d_thetas, int* d_infos,
                   int* d_nfevs, void* stream);
 
+/* ---- rendering ----------------------------------------------------------------
+ * Replaces the unrotated paths of picasso.render.render (picasso/render.py:37-174):
+ * _render_hist (:798-853, mode 0), _render_gaussian (:1020-1112, mode 1) and
+ * _render_gaussian_iso (:1148-1216, mode 2) with _render_setup (:177-232),
+ * _fill (:451-467) and _draw_gaussian_loc/_fill_gaussian (:494-575).
+ *   x, y, lpx, lpy  float32[n] localisation coordinates / precisions (camera px);
+ *                   lpx/lpy are ignored (may be NULL) for mode 0
+ *   oversampling    display pixels per camera pixel
+ *   viewport        (y_min, x_min) .. (y_max, x_max), strict inequalities
+ *   image           float32 [n_pixel_y][n_pixel_x], zeroed by the call;
+ *                   n_pixel = ceil(oversampling * (max - min)) is computed by the caller
+ *   n_in_view       number of localisations inside the viewport (the reference's `n`)
+ * The _dev variant takes an optional workspace (pb_render_workspace_bytes) enabling
+ * the tile-binned shared-memory path; without it the direct-atomics path is used.
+ * Unknown mode -> PB_ERR_INVALID, message "blur_method not understood." (render.py:174). */
+size_t pb_render_workspace_bytes(size_t n, int n_pixel_y, int n_pixel_x);
+int pb_render(size_t n, const float* x, const float* y, const float* lpx, const float* lpy,
+              double oversampling, double y_min, double x_min, double y_max, double x_max,
+              double min_blur_width, int mode, float* image, int n_pixel_y, int n_pixel_x,
+              long long* n_in_view);
+int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
+                  const float* d_lpy, double oversampling, double y_min, double x_min, double y_max,
+                  double x_max, double min_blur_width, int mode, float* d_image, int n_pixel_y,
+                  int n_pixel_x, unsigned long long* d_count, void* d_workspace,
+                  size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

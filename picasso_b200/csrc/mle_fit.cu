@@ -38,6 +38,17 @@ constexpr int kTileSpots = 4;      // spots per TMA tile (per warp): 16*box^2 by
 constexpr int kWarpsPerBlock = 4;
 constexpr int kRedStride = 23;     // doubles per lane in the reduction scratch (22 + pad)
 
+// tuning knobs (tools/tune_mle.py builds variants with -D overrides)
+#ifndef PB_MLE_MINB
+#define PB_MLE_MINB 3          // min resident CTAs per SM requested from ptxas
+#endif
+#ifndef PB_MLE_PIX_UNROLL
+#define PB_MLE_PIX_UNROLL 32   // unroll factor of the per-row pixel loops
+#endif
+#define PB_STR2(x) #x
+#define PB_STR(x) PB_STR2(x)
+#define PB_PIX_UNROLL _Pragma(PB_STR(unroll PB_MLE_PIX_UNROLL))
+
 struct MleArgs {
     const float* spots;   // (n, box, box) f32, device
     long long n;
@@ -180,7 +191,7 @@ __device__ __forceinline__ bool inv_diag_cholesky(const double* m, double* diag)
 }
 
 template <int BOX, int G, int METHOD>   // METHOD 1 = sigmaxy (6 par), 0 = sigma (5 par)
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PB_MLE_MINB)
 mle_fit_kernel(const MleArgs a) {
     using SM = MleSmem<BOX, G>;
     constexpr int S = SM::S;
@@ -430,7 +441,7 @@ mle_fit_kernel(const MleArgs a) {
                 if (g < BOX) {
                     const float* rowp = sp + g * BOX;
                     const double NPy = N * PSFy;
-#pragma unroll
+                    PB_PIX_UNROLL
                     for (int i = 0; i < BOX; i++) {
                         const double px = fx[0 * BOX + i], c1 = fx[1 * BOX + i], c2 = fx[2 * BOX + i];
                         const double g1 = fx[3 * BOX + i], g2 = fx[4 * BOX + i];
@@ -532,7 +543,7 @@ mle_fit_kernel(const MleArgs a) {
                 if (g < BOX) {
                     const float* rowp = sp + g * BOX;
                     const double NPy = N * PSFy;
-#pragma unroll
+                    PB_PIX_UNROLL
                     for (int i = 0; i < BOX; i++) {
                         const double px = fx[0 * BOX + i], c1 = fx[1 * BOX + i];
                         const double g1 = fx[3 * BOX + i];

@@ -1,0 +1,371 @@
+// picasso_b200/csrc/render.cu
+//
+// Super-resolution rendering on B200 -- replaces the unrotated paths of
+// picasso.render.render: _render_setup + _fill (_render_hist) and
+// _draw_gaussian_loc/_fill_gaussian (_render_gaussian, _render_gaussian_iso)
+// (reference picasso/render.py:177-232, 451-575, 798-853, 1020-1216).
+//
+// Per-localisation values follow the reference exactly: strict viewport test,
+// coordinates promoted to f64, float32 sigma = f32(oversampling) * max(lp,
+// f32(min_blur_width)), window = np.int32 truncations of (c -/+ 3 sigma), 1-D
+// kernels evaluated in f64 and rounded to f32, pixel value = gy[i] * gx[j] in
+// f32.  Only the accumulation ORDER differs (atomics vs the reference's serial
+// loop), so images agree to float32 summation rounding; the histogram (integer
+// counts) is exact.
+//
+// Kernels:
+//   render_hist_kernel     one thread per localisation, RED.ADD of 1.0f
+//   render_splat_kernel    8 lanes per localisation: lane j owns window columns
+//                          j, j+8, ...; a row's 8 consecutive pixels share one or
+//                          two 32 B sectors, so the L2 atomic unit sees coalesced
+//                          reductions.  Used for small batches.
+//   render_tiled_kernel    localisations are binned by 64x64-pixel tile
+//                          (counting sort on the device); one CTA accumulates its
+//                          tile in shared memory with shared-memory atomics and
+//                          flushes it once with coalesced reductions; window parts
+//                          that cross the tile edge go straight to global atomics.
+#include <algorithm>
+#include <atomic>
+
+#include "pb_common.cuh"
+#include "../../include/picasso_b200.h"
+
+extern std::atomic<long long> g_pb_launches;
+
+namespace {
+
+struct RenderArgs {
+    const float* x;
+    const float* y;
+    const float* lpx;
+    const float* lpy;
+    long long n;
+    double os, y_min, x_min, y_max, x_max;
+    float osf, mbw;
+    int mode;              // 0 hist, 1 gaussian, 2 gaussian_iso
+    float* image;
+    int npy, npx;
+    unsigned long long* count;   // localisations in view
+};
+
+struct Splat {            // everything _draw_gaussian_loc derives for one localisation
+    double x_, y_, inv_2sx2, inv_2sy2, norm;
+    int i_min, i_max, j_min, j_max;
+    bool in_view;
+};
+
+__device__ __forceinline__ Splat make_splat(const RenderArgs& a, long long k) {
+    Splat s;
+    const double xv = (double)a.x[k], yv = (double)a.y[k];
+    s.in_view = (xv > a.x_min) && (yv > a.y_min) && (xv < a.x_max) && (yv < a.y_max);
+    s.x_ = a.os * (xv - a.x_min);
+    s.y_ = a.os * (yv - a.y_min);
+    s.i_min = s.i_max = s.j_min = s.j_max = 0;
+    s.inv_2sx2 = s.inv_2sy2 = s.norm = 0.0;
+    if (!s.in_view || a.mode == 0) return s;
+    const float bw = __fmul_rn(a.osf, fmaxf(a.lpx[k], a.mbw));
+    const float bh = __fmul_rn(a.osf, fmaxf(a.lpy[k], a.mbw));
+    float sx, sy;
+    if (a.mode == 2) { sy = __fdiv_rn(__fadd_rn(bh, bw), 2.0f); sx = sy; }
+    else { sx = bw; sy = bh; }
+    const double moy = 3.0 * (double)sy, mox = 3.0 * (double)sx;
+    s.i_min = max((int)(s.y_ - moy), 0);
+    s.i_max = min((int)(s.y_ + moy + 1.0), a.npy);
+    s.j_min = max((int)(s.x_ - mox), 0);
+    s.j_max = min((int)(s.x_ + mox) + 1, a.npx);
+    s.inv_2sx2 = 1.0 / (2.0 * (double)sx * (double)sx);
+    s.inv_2sy2 = 1.0 / (2.0 * (double)sy * (double)sy);
+    s.norm = 1.0 / (2.0 * 3.141592653589793 * (double)sx * (double)sy);
+    return s;
+}
+
+__device__ __forceinline__ float splat_gx(const Splat& s, int j) {
+    const double dx = (double)j + 0.5 - s.x_;
+    return (float)exp(-dx * dx * s.inv_2sx2);
+}
+__device__ __forceinline__ float splat_gy(const Splat& s, int i) {
+    const double dy = (double)i + 0.5 - s.y_;
+    return (float)(s.norm * exp(-dy * dy * s.inv_2sy2));
+}
+
+__global__ void render_hist_kernel(const RenderArgs a) {
+    unsigned long long local = 0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const Splat s = make_splat(a, k);
+        if (s.in_view) {
+            local++;
+            const int i = (int)s.x_, j = (int)s.y_;      // x.astype(int32): truncation
+            if (j >= 0 && j < a.npy && i >= 0 && i < a.npx)
+                atomicAdd(a.image + (size_t)j * a.npx + i, 1.0f);
+        }
+    }
+    // block-aggregated count
+    __shared__ unsigned long long blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&blk, local);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk) atomicAdd(a.count, blk);
+}
+
+constexpr int kLanes = 8;     // lanes per localisation in the direct splat kernel
+
+__global__ void render_splat_kernel(const RenderArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane & (kLanes - 1);
+    const long long groups = ((long long)gridDim.x * blockDim.x) / kLanes;
+    const long long gid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kLanes;
+    unsigned long long local = 0;
+    const long long nround = (a.n + groups - 1) / groups;
+    for (long long r = 0; r < nround; r++) {
+        const long long k = r * groups + gid;
+        Splat s;
+        s.in_view = false;
+        if (k < a.n) s = make_splat(a, k);
+        if (s.in_view && g == 0) local++;
+        if (!s.in_view) continue;
+        const int nx = s.j_max - s.j_min, ny = s.i_max - s.i_min;
+        if (nx <= 0 || ny <= 0) continue;
+        for (int j0 = 0; j0 < nx; j0 += kLanes) {
+            const int j = s.j_min + j0 + g;
+            const bool jok = (j0 + g) < nx;
+            const float gx = jok ? splat_gx(s, j) : 0.0f;
+            for (int i = s.i_min; i < s.i_max; i++) {
+                const float gy = splat_gy(s, i);
+                if (jok) atomicAdd(a.image + (size_t)i * a.npx + j, __fmul_rn(gy, gx));
+            }
+        }
+    }
+    __shared__ unsigned long long blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(&blk, local);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk) atomicAdd(a.count, blk);
+}
+
+// ---- tiled path ---------------------------------------------------------------
+constexpr int kTile = 64;                 // tile edge in image pixels (16 KB of smem)
+
+// pass 1: tile id per localisation (-1 = not in view) + histogram of tile sizes
+__global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restrict__ tile_of,
+                                  unsigned int* __restrict__ tile_count) {
+    unsigned long long local = 0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const double xv = (double)a.x[k], yv = (double)a.y[k];
+        const bool in_view = (xv > a.x_min) && (yv > a.y_min) && (xv < a.x_max) && (yv < a.y_max);
+        int t = -1;
+        if (in_view) {
+            local++;
+            int px = (int)(a.os * (xv - a.x_min)), py = (int)(a.os * (yv - a.y_min));
+            px = min(max(px, 0), a.npx - 1);
+            py = min(max(py, 0), a.npy - 1);
+            t = (py / kTile) * tiles_x + (px / kTile);
+            atomicAdd(tile_count + t, 1u);
+        }
+        tile_of[k] = t;
+    }
+    __shared__ unsigned long long blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&blk, local);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk) atomicAdd(a.count, blk);
+}
+
+// pass 2: exclusive scan of the tile histogram (single CTA, tiles <= a few 100k)
+__global__ void render_scan_kernel(const unsigned int* __restrict__ count,
+                                   unsigned int* __restrict__ start,
+                                   unsigned int* __restrict__ cursor, int ntiles) {
+    __shared__ unsigned int part[1024];
+    const int t = threadIdx.x;
+    const int per = (ntiles + 1023) / 1024;
+    unsigned int s = 0;
+    for (int q = 0; q < per; q++) {
+        const int idx = t * per + q;
+        if (idx < ntiles) s += count[idx];
+    }
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned int v = (t >= o) ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned int run = (t == 0) ? 0 : part[t - 1];
+    for (int q = 0; q < per; q++) {
+        const int idx = t * per + q;
+        if (idx < ntiles) {
+            start[idx] = run;
+            cursor[idx] = run;
+            run += count[idx];
+        }
+    }
+    if (t == 1023) start[ntiles] = part[1023];
+}
+
+// pass 3: scatter localisation indices into tile order
+__global__ void render_scatter_kernel(long long n, const int* __restrict__ tile_of,
+                                      unsigned int* __restrict__ cursor,
+                                      unsigned int* __restrict__ order) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int t = tile_of[k];
+        if (t >= 0) order[atomicAdd(cursor + t, 1u)] = (unsigned int)k;
+    }
+}
+
+// pass 4: one CTA per tile, shared-memory accumulation
+__global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, int tiles_x,
+                                                           const unsigned int* __restrict__ start,
+                                                           const unsigned int* __restrict__ order) {
+    __shared__ float acc[kTile * kTile];
+    const int tile = blockIdx.x;
+    const unsigned int first = start[tile], last = start[tile + 1];
+    if (first == last) return;
+    const int ty0 = (tile / tiles_x) * kTile, tx0 = (tile % tiles_x) * kTile;
+    for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) acc[q] = 0.0f;
+    __syncthreads();
+    const int g = threadIdx.x & (kLanes - 1);
+    const unsigned int grp = threadIdx.x / kLanes, ngrp = blockDim.x / kLanes;
+    for (unsigned int q = first + grp; q < last; q += ngrp) {
+        const Splat s = make_splat(a, (long long)order[q]);
+        const int nx = s.j_max - s.j_min, ny = s.i_max - s.i_min;
+        if (nx <= 0 || ny <= 0) continue;
+        for (int j0 = 0; j0 < nx; j0 += kLanes) {
+            const int j = s.j_min + j0 + g;
+            const bool jok = (j0 + g) < nx;
+            const float gx = jok ? splat_gx(s, j) : 0.0f;
+            const bool jin = (j >= tx0) && (j < tx0 + kTile);
+            for (int i = s.i_min; i < s.i_max; i++) {
+                const float v = __fmul_rn(splat_gy(s, i), gx);
+                if (!jok) continue;
+                if (jin && i >= ty0 && i < ty0 + kTile)
+                    atomicAdd(&acc[(i - ty0) * kTile + (j - tx0)], v);
+                else
+                    atomicAdd(a.image + (size_t)i * a.npx + j, v);
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) {
+        const int i = ty0 + q / kTile, j = tx0 + q % kTile;
+        const float v = acc[q];
+        if (v != 0.0f && i < a.npy && j < a.npx) atomicAdd(a.image + (size_t)i * a.npx + j, v);
+    }
+}
+
+}  // namespace
+
+// Workspace (bytes) pb_render_dev needs for the tiled path; 0 => use the direct path.
+extern "C" size_t pb_render_workspace_bytes(size_t n, int n_pixel_y, int n_pixel_x) {
+    const size_t tiles = (size_t)((n_pixel_y + kTile - 1) / kTile) * ((n_pixel_x + kTile - 1) / kTile);
+    return n * 8 + (tiles + 1) * 12 + 256;
+}
+
+extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
+                             const float* d_lpy, double oversampling, double y_min, double x_min,
+                             double y_max, double x_max, double min_blur_width, int mode,
+                             float* d_image, int n_pixel_y, int n_pixel_x,
+                             unsigned long long* d_count, void* d_workspace,
+                             size_t workspace_bytes, void* stream) {
+    if (mode < 0 || mode > 2) { pb_set_error("blur_method not understood."); return PB_ERR_INVALID; }
+    if (n_pixel_y <= 0 || n_pixel_x <= 0) return PB_OK;
+    if (!d_image || !d_count) { pb_set_error("pb_render_dev: null pointer"); return PB_ERR_INVALID; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    PB_CUDA_CHECK(cudaMemsetAsync(d_image, 0, sizeof(float) * (size_t)n_pixel_y * n_pixel_x, s));
+    PB_CUDA_CHECK(cudaMemsetAsync(d_count, 0, 8, s));
+    if (n == 0) return PB_OK;
+    RenderArgs a{d_x, d_y, d_lpx, d_lpy, (long long)n, oversampling, y_min, x_min, y_max, x_max,
+                 (float)oversampling, (float)min_blur_width, mode, d_image, n_pixel_y, n_pixel_x,
+                 d_count};
+    const int threads = 256;
+    if (mode == 0) {
+        int grid = (int)std::min<long long>(((long long)n + threads - 1) / threads, 148 * 16);
+        render_hist_kernel<<<grid, threads, 0, s>>>(a);
+        g_pb_launches++;
+        PB_CUDA_CHECK(cudaGetLastError());
+        return PB_OK;
+    }
+    const int tiles_x = (n_pixel_x + kTile - 1) / kTile, tiles_y = (n_pixel_y + kTile - 1) / kTile;
+    const long long ntiles = (long long)tiles_x * tiles_y;
+    const size_t need = pb_render_workspace_bytes(n, n_pixel_y, n_pixel_x);
+    const bool tiled = d_workspace && workspace_bytes >= need && n >= 65536 && n < 0xffffffffull &&
+                       ntiles >= 64;
+    if (!tiled) {
+        long long want = ((long long)n * kLanes + threads - 1) / threads;
+        int grid = (int)std::min<long long>(want, 148 * 16);
+        render_splat_kernel<<<grid, threads, 0, s>>>(a);
+        g_pb_launches++;
+        PB_CUDA_CHECK(cudaGetLastError());
+        return PB_OK;
+    }
+    // workspace layout: tile_of[n] i32 | order[n] u32 | count[T] | start[T+1] | cursor[T]
+    char* w = static_cast<char*>(d_workspace);
+    int* tile_of = reinterpret_cast<int*>(w);
+    unsigned int* order = reinterpret_cast<unsigned int*>(w + n * 4);
+    unsigned int* tcount = reinterpret_cast<unsigned int*>(w + n * 8);
+    unsigned int* tstart = tcount + ntiles;
+    unsigned int* tcursor = tstart + ntiles + 1;
+    PB_CUDA_CHECK(cudaMemsetAsync(tcount, 0, ntiles * 4, s));
+    int grid = (int)std::min<long long>(((long long)n + threads - 1) / threads, 148 * 16);
+    render_bin_kernel<<<grid, threads, 0, s>>>(a, tiles_x, tile_of, tcount);
+    render_scan_kernel<<<1, 1024, 0, s>>>(tcount, tstart, tcursor, (int)ntiles);
+    render_scatter_kernel<<<grid, threads, 0, s>>>((long long)n, tile_of, tcursor, order);
+    render_tiled_kernel<<<(unsigned)ntiles, 256, 0, s>>>(a, tiles_x, tstart, order);
+    g_pb_launches += 4;
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+// Host-buffer variant: H2D of (x, y, lpx, lpy), render, D2H of the image.
+extern "C" int pb_render(size_t n, const float* x, const float* y, const float* lpx,
+                         const float* lpy, double oversampling, double y_min, double x_min,
+                         double y_max, double x_max, double min_blur_width, int mode, float* image,
+                         int n_pixel_y, int n_pixel_x, long long* n_in_view) {
+    if (mode < 0 || mode > 2) { pb_set_error("blur_method not understood."); return PB_ERR_INVALID; }
+    if (n_in_view) *n_in_view = 0;
+    const size_t npix = (size_t)std::max(n_pixel_y, 0) * std::max(n_pixel_x, 0);
+    if (npix == 0) return PB_OK;
+    if (!image || (n && (!x || !y)) || (n && mode && (!lpx || !lpy))) {
+        pb_set_error("pb_render: null pointer");
+        return PB_ERR_INVALID;
+    }
+    float *dx = nullptr, *dy = nullptr, *dlx = nullptr, *dly = nullptr, *dimg = nullptr;
+    unsigned long long* dcnt = nullptr;
+    void* dws = nullptr;
+    const size_t nb = std::max<size_t>(n, 1) * 4;
+    const size_t wsb = pb_render_workspace_bytes(n, n_pixel_y, n_pixel_x);
+    int rc = PB_OK;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t err) { if (err != cudaSuccess && e == cudaSuccess) e = err; return err == cudaSuccess; };
+    ok(cudaMalloc(&dx, nb)); ok(cudaMalloc(&dy, nb));
+    if (mode) { ok(cudaMalloc(&dlx, nb)); ok(cudaMalloc(&dly, nb)); ok(cudaMalloc(&dws, wsb)); }
+    ok(cudaMalloc(&dimg, npix * 4)); ok(cudaMalloc(&dcnt, 8));
+    if (e == cudaSuccess && n) {
+        ok(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+        ok(cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice));
+        if (mode) {
+            ok(cudaMemcpy(dlx, lpx, n * 4, cudaMemcpyHostToDevice));
+            ok(cudaMemcpy(dly, lpy, n * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    if (e == cudaSuccess)
+        rc = pb_render_dev(n, dx, dy, dlx, dly, oversampling, y_min, x_min, y_max, x_max,
+                           min_blur_width, mode, dimg, n_pixel_y, n_pixel_x, dcnt, dws, wsb, nullptr);
+    unsigned long long cnt = 0;
+    if (e == cudaSuccess && rc == PB_OK) {
+        ok(cudaMemcpy(image, dimg, npix * 4, cudaMemcpyDeviceToHost));
+        ok(cudaMemcpy(&cnt, dcnt, 8, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(dx); cudaFree(dy); cudaFree(dlx); cudaFree(dly); cudaFree(dimg); cudaFree(dcnt); cudaFree(dws);
+    if (e != cudaSuccess) { pb_set_error("pb_render: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    if (n_in_view) *n_in_view = (long long)cnt;
+    return rc;
+}

@@ -1,0 +1,44 @@
+"""The few ``picasso.lib`` helpers the hot path needs (reference picasso/lib.py):
+``get_from_metadata`` :878-920 and ``minimize_shifts`` :2034-2078.  Host-side numpy;
+no GUI code."""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+
+def get_from_metadata(info, key: Any, default=None, *, raise_error: bool = False):
+    """Search the metadata (dict, or list of dicts from last to first) for ``key``
+    (reference lib.py:878-920; a falsy value counts as missing in the list form)."""
+    if isinstance(info, dict):
+        if raise_error and key not in info:
+            raise KeyError(f"Key '{key}' not found in metadata.")
+        return info.get(key, default)
+    if isinstance(info, list):
+        for entry in reversed(info):
+            value = entry.get(key)
+            if value:
+                return value
+        if raise_error:
+            raise KeyError(f"Key '{key}' not found in metadata.")
+        return default
+    raise ValueError("info must be a dict or a list of dicts.")
+
+
+def minimize_shifts(shifts_x, shifts_y, shifts_z=None):
+    """Least-squares chain of pairwise shifts (RCC; reference lib.py:2034-2078):
+    solve ``A d = r`` with ``A[pair(i, j), i:j] = 1`` by pseudo-inverse and return the
+    cumulative shifts (leading 0) as ``(shift_y, shift_x[, shift_z])``."""
+    n = shifts_x.shape[0]
+    pairs = [(i, j) for i in range(n - 1) for j in range(i + 1, n)]
+    stacks = [shifts_y, shifts_x] + ([shifts_z] if shifts_z is not None else [])
+    rij = np.zeros((len(pairs), len(stacks)))
+    A = np.zeros((len(pairs), n - 1))
+    for row, (i, j) in enumerate(pairs):
+        for col, sh in enumerate(stacks):
+            rij[row, col] = sh[i, j]
+        A[row, i:j] = 1
+    Dj = np.dot(np.linalg.pinv(A), rij)
+    out = tuple(np.insert(np.cumsum(Dj[:, c]), 0, 0) for c in range(len(stacks)))
+    return out

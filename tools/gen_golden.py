@@ -186,8 +186,38 @@ def gen_lq(ref):
     out["movie_thetas"] = glq.fit_spots(idg["mov_b7_spots"])
     save("lq.npz", **out)
 
+def gen_render(ref):
+    """render.render golden images (reference render.py:37-174, 177-232, 451-575,
+    798-853, 1020-1216), unrotated None / gaussian / gaussian_iso."""
+    import pandas as pd
 
-GENERATORS = {"mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq}
+    rnd = ref["render"]
+    rng = np.random.default_rng(11)
+    n = 4000
+    locs = pd.DataFrame({
+        "frame": rng.integers(0, 100, n).astype(np.uint32),
+        "x": rng.uniform(-1, 33, n).astype(np.float32),      # some outside the FOV
+        "y": rng.uniform(-1, 25, n).astype(np.float32),
+        "lpx": rng.uniform(0.02, 0.4, n).astype(np.float32),
+        "lpy": rng.uniform(0.02, 0.4, n).astype(np.float32),
+    })
+    info = [{"Height": 24, "Width": 32, "Frames": 100, "Pixelsize": 130}]
+    out = {c: locs[c].to_numpy() for c in locs.columns}
+    cases = {
+        "full_os8": dict(oversampling=8),
+        "view_os5": dict(oversampling=5, viewport=((4.5, 3.25), (20.125, 30.75))),
+        "os1_mbw1": dict(oversampling=1, min_blur_width=1),       # what postprocess.segment uses
+        "os2p5_mbw": dict(oversampling=2.5, min_blur_width=0.1),
+    }
+    for tag, kw in cases.items():
+        for bm in (None, "gaussian", "gaussian_iso"):
+            k, img = rnd.render(locs, info, blur_method=bm, **kw)
+            out[f"{tag}_{bm}_n"] = np.array(k)
+            out[f"{tag}_{bm}_image"] = img
+    save("render.npz", **out)
+
+
+GENERATORS = {"mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render}
 
 
 def main():
