@@ -160,6 +160,26 @@ int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_l
                   int n_pixel_x, unsigned long long* d_count, void* d_workspace,
                   size_t workspace_bytes, void* stream);
 
+/* ---- RCC cross-correlation ----------------------------------------------------
+ * Replaces the FFT work of picasso.imageprocess.xcorr / get_image_shift / rcc
+ * (picasso/imageprocess.py:27-217) inside postprocess.undrift
+ * (picasso/postprocess.py:2903-2961): for every pair i<j,
+ *   window = crop(fftshift(real(ifft2(fft2(seg_i) * conj(fft2(seg_j))))) / sqrt(Y*X))
+ * with the crop rows [Y0, Y0+H) and columns [X0, X0+W) (the reference's centre crop,
+ * imageprocess.py:88-101; Y0 = X0 = 0, H = Y, W = X gives the whole correlation).
+ *   segments (n_seg, Y, X) float32;  windows (n_seg*(n_seg-1)/2, H, W) float32 in the
+ *   reference's pair order (i outer, j inner);  sums (n_seg) float64 = np.sum(seg)
+ *   (the reference returns (0,0) for pairs with a zero-sum image, :83-84).
+ * The arg-max / 5x5 peak fit / minimize_shifts stay on the host. */
+int pb_rcc_windows(int n_seg, int Y, int X, const float* segments, int Y0, int X0, int H, int W,
+                   float* windows, double* sums);
+/* building blocks with device pointers (multi-GPU callers shard pairs across ranks) */
+int pb_rcc_spectra_dev(int n_seg, int Y, int X, const float* d_segments, void* d_spectra,
+                       double* d_sums, void* stream);
+int pb_rcc_windows_dev(int n_pairs, const int* d_pair_i, const int* d_pair_j, int Y, int X,
+                       const void* d_spectra, int Y0, int X0, int H, int W, float* d_windows,
+                       int batch, void* d_workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,224 @@
+// picasso_b200/csrc/rcc.cu
+//
+// Redundant cross-correlation (RCC) drift estimation on B200 -- replaces the FFT
+// part of picasso.imageprocess.xcorr / get_image_shift / rcc
+// (reference picasso/imageprocess.py:27-217) used by postprocess.undrift
+// (picasso/postprocess.py:2903-2961).
+//
+// The reference recomputes fft2(A), fft2(B) and one ifft2 for EVERY pair in
+// float64 on the CPU (3 FFTs x n(n-1)/2 pairs).  Here:
+//   * one batched cuFFT R2C per SEGMENT (half-spectra kept resident in HBM),
+//   * per pair: a fused conj-multiply kernel -> batched cuFFT C2R -> a crop
+//     kernel that applies fftshift + the 1/(N*sqrt(N)) normalisation and copies
+//     only the central `roi` window (the reference crops it after the fact,
+//     imageprocess.py:88-101) -- 4 KB per pair go back to the host,
+//   * the arg-max + 5x5 peak fit stay on the host (picasso_b200/imageprocess.py).
+// float32 transforms: the peak is fitted from a 5x5 window of O(1)-relative
+// values; cuFFT's 1e-6 relative error moves the fitted shift by << 1e-3 px.
+// HBM-bound (cuFFT passes over 2*Y*X*4 B per pair).
+#include <algorithm>
+#include <atomic>
+#include <cufft.h>
+#include <vector>
+
+#include "pb_common.cuh"
+#include "../../include/picasso_b200.h"
+
+extern std::atomic<long long> g_pb_launches;
+
+namespace {
+
+#define PB_CUFFT_CHECK(expr)                                                       \
+    do {                                                                           \
+        cufftResult _r = (expr);                                                   \
+        if (_r != CUFFT_SUCCESS) {                                                 \
+            pb_set_error("%s failed: cufft error %d (%s:%d)", #expr, (int)_r, __FILE__, __LINE__); \
+            return PB_ERR_CUFFT;                                                   \
+        }                                                                          \
+    } while (0)
+
+// P[b] = F[i_b] * conj(F[j_b]) over the half spectrum (imageprocess.py:45-47)
+__global__ void rcc_conj_mul_kernel(const float2* __restrict__ spectra, size_t spec_elems,
+                                    const int* __restrict__ pi, const int* __restrict__ pj,
+                                    int npairs, float2* __restrict__ out) {
+    const size_t total = (size_t)npairs * spec_elems;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / spec_elems);
+        const size_t k = idx - (size_t)b * spec_elems;
+        const float2 a = __ldg(spectra + (size_t)pi[b] * spec_elems + k);
+        const float2 c = __ldg(spectra + (size_t)pj[b] * spec_elems + k);
+        // a * conj(c)
+        out[idx] = make_float2(fmaf(a.x, c.x, a.y * c.y), fmaf(a.y, c.x, -a.x * c.y));
+    }
+}
+
+// crop[b][r][c] = corr[b][(r + Y0 - Y/2) mod Y][(c + X0 - X/2) mod X] * scale
+// (np.fft.fftshift rolls by N//2; scale = 1/(Y*X) from ifft2 and 1/sqrt(Y*X))
+__global__ void rcc_crop_kernel(const float* __restrict__ corr, int Y, int X, int npairs, int Y0,
+                                int X0, int H, int W, double scale, float* __restrict__ out) {
+    const size_t total = (size_t)npairs * H * W;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % W);
+        const int r = (int)((idx / W) % H);
+        const int b = (int)(idx / ((size_t)W * H));
+        int sr = (r + Y0 - Y / 2) % Y; if (sr < 0) sr += Y;
+        int sc = (c + X0 - X / 2) % X; if (sc < 0) sc += X;
+        out[idx] = (float)((double)corr[((size_t)b * Y + sr) * X + sc] * scale);
+    }
+}
+
+// per-image sum in f64 (the reference tests np.sum(image) == 0, imageprocess.py:83)
+__global__ void rcc_sum_kernel(const float* __restrict__ img, size_t elems, double* out) {
+    const float* p = img + (size_t)blockIdx.y * elems;
+    double s = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < elems;
+         i += (size_t)gridDim.x * blockDim.x)
+        s += (double)p[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, s);
+    }
+}
+
+struct CufftPlan {
+    cufftHandle h = 0;
+    bool ok = false;
+    ~CufftPlan() { if (ok) cufftDestroy(h); }
+};
+
+}  // namespace
+
+// Forward transforms of all segments: d_spectra[s] = rfft2(d_segments[s]) (unnormalised),
+// plus per-segment sums.  d_spectra holds n_seg * Y * (X/2+1) float2.
+extern "C" int pb_rcc_spectra_dev(int n_seg, int Y, int X, const float* d_segments,
+                                  void* d_spectra, double* d_sums, void* stream) {
+    if (n_seg <= 0) return PB_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    CufftPlan plan;
+    int dims[2] = {Y, X};
+    PB_CUFFT_CHECK(cufftPlanMany(&plan.h, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, n_seg));
+    plan.ok = true;
+    PB_CUFFT_CHECK(cufftSetStream(plan.h, s));
+    PB_CUFFT_CHECK(cufftExecR2C(plan.h, const_cast<float*>(d_segments),
+                                static_cast<cufftComplex*>(d_spectra)));
+    g_pb_launches++;
+    if (d_sums) {
+        PB_CUDA_CHECK(cudaMemsetAsync(d_sums, 0, sizeof(double) * n_seg, s));
+        dim3 grid(64, n_seg);
+        rcc_sum_kernel<<<grid, 256, 0, s>>>(d_segments, (size_t)Y * X, d_sums);
+        g_pb_launches++;
+    }
+    PB_CUDA_CHECK(cudaGetLastError());
+    PB_CUDA_CHECK(cudaStreamSynchronize(s));   // plan is destroyed on return
+    return PB_OK;
+}
+
+// Correlation windows for a list of pairs: d_windows[p] = crop of
+// fftshift(irfft2(F_i * conj(F_j))) / sqrt(Y*X), H x W window starting at (Y0, X0).
+// Pairs are processed in batches of `batch` (workspace: batch * (spec + Y*X) floats).
+extern "C" int pb_rcc_windows_dev(int n_pairs, const int* d_pair_i, const int* d_pair_j, int Y,
+                                  int X, const void* d_spectra, int Y0, int X0, int H, int W,
+                                  float* d_windows, int batch, void* d_workspace,
+                                  size_t workspace_bytes, void* stream) {
+    if (n_pairs <= 0) return PB_OK;
+    if (batch < 1) batch = 1;
+    const size_t spec = (size_t)Y * (X / 2 + 1);
+    const size_t need = (size_t)batch * (spec * 8 + (size_t)Y * X * 4);
+    if (!d_workspace || workspace_bytes < need) {
+        pb_set_error("pb_rcc_windows_dev: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return PB_ERR_INVALID;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    float2* prod = static_cast<float2*>(d_workspace);
+    float* corr = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + (size_t)batch * spec * 8);
+    CufftPlan plan, tail;
+    int dims[2] = {Y, X};
+    PB_CUFFT_CHECK(cufftPlanMany(&plan.h, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, batch));
+    plan.ok = true;
+    PB_CUFFT_CHECK(cufftSetStream(plan.h, s));
+    const double scale = 1.0 / ((double)Y * X) / sqrt((double)Y * X);
+    for (int p0 = 0; p0 < n_pairs; p0 += batch) {
+        const int nb = std::min(batch, n_pairs - p0);
+        cufftHandle h = plan.h;
+        if (nb != batch) {
+            PB_CUFFT_CHECK(cufftPlanMany(&tail.h, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, nb));
+            tail.ok = true;
+            PB_CUFFT_CHECK(cufftSetStream(tail.h, s));
+            h = tail.h;
+        }
+        const size_t total = (size_t)nb * spec;
+        int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+        rcc_conj_mul_kernel<<<grid, 256, 0, s>>>(static_cast<const float2*>(d_spectra), spec,
+                                                 d_pair_i + p0, d_pair_j + p0, nb, prod);
+        PB_CUFFT_CHECK(cufftExecC2R(h, reinterpret_cast<cufftComplex*>(prod), corr));
+        const size_t wt = (size_t)nb * H * W;
+        int g2 = (int)std::min<size_t>((wt + 255) / 256, 148 * 32);
+        rcc_crop_kernel<<<g2, 256, 0, s>>>(corr, Y, X, nb, Y0, X0, H, W, scale,
+                                           d_windows + (size_t)p0 * H * W);
+        g_pb_launches += 3;
+    }
+    PB_CUDA_CHECK(cudaGetLastError());
+    PB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return PB_OK;
+}
+
+// Host-buffer variant for all i<j pairs of `segments` (n_seg, Y, X) float32:
+// windows (n_pairs, H, W) float32 in the reference's pair order (i outer, j inner),
+// sums (n_seg) float64.
+extern "C" int pb_rcc_windows(int n_seg, int Y, int X, const float* segments, int Y0, int X0,
+                              int H, int W, float* windows, double* sums) {
+    if (n_seg < 1) return PB_OK;
+    if (!segments || !sums || (n_seg > 1 && !windows)) { pb_set_error("pb_rcc_windows: null pointer"); return PB_ERR_INVALID; }
+    if (Y < 1 || X < 1 || H < 1 || W < 1 || Y0 < 0 || X0 < 0 || Y0 + H > Y || X0 + W > X) {
+        pb_set_error("pb_rcc_windows: bad window");
+        return PB_ERR_INVALID;
+    }
+    const size_t img = (size_t)Y * X, spec = (size_t)Y * (X / 2 + 1);
+    const int n_pairs = n_seg * (n_seg - 1) / 2;
+    // batch sized for ~1 GB of workspace
+    int batch = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)1 << 30) / (spec * 8 + img * 4)));
+    batch = std::max(1, std::min(batch, std::max(n_pairs, 1)));
+    float *dseg = nullptr, *dwin = nullptr;
+    void *dspec = nullptr, *dws = nullptr;
+    double* dsum = nullptr;
+    int *dpi = nullptr, *dpj = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t err) { if (err != cudaSuccess && e == cudaSuccess) e = err; };
+    const size_t wsb = (size_t)batch * (spec * 8 + img * 4);
+    ok(cudaMalloc(&dseg, n_seg * img * 4));
+    ok(cudaMalloc(&dspec, n_seg * spec * 8));
+    ok(cudaMalloc(&dsum, n_seg * 8));
+    ok(cudaMalloc(&dws, wsb));
+    ok(cudaMalloc(&dwin, std::max<size_t>(1, (size_t)n_pairs * H * W * 4)));
+    ok(cudaMalloc(&dpi, std::max(1, n_pairs) * 4));
+    ok(cudaMalloc(&dpj, std::max(1, n_pairs) * 4));
+    int rc = PB_OK;
+    if (e == cudaSuccess) {
+        std::vector<int> pi, pj;
+        for (int i = 0; i < n_seg - 1; i++)
+            for (int j = i + 1; j < n_seg; j++) { pi.push_back(i); pj.push_back(j); }
+        ok(cudaMemcpy(dseg, segments, n_seg * img * 4, cudaMemcpyHostToDevice));
+        if (n_pairs) {
+            ok(cudaMemcpy(dpi, pi.data(), n_pairs * 4, cudaMemcpyHostToDevice));
+            ok(cudaMemcpy(dpj, pj.data(), n_pairs * 4, cudaMemcpyHostToDevice));
+        }
+        if (e == cudaSuccess) rc = pb_rcc_spectra_dev(n_seg, Y, X, dseg, dspec, dsum, nullptr);
+        if (e == cudaSuccess && rc == PB_OK && n_pairs)
+            rc = pb_rcc_windows_dev(n_pairs, dpi, dpj, Y, X, dspec, Y0, X0, H, W, dwin, batch, dws,
+                                    wsb, nullptr);
+        if (e == cudaSuccess && rc == PB_OK) {
+            ok(cudaMemcpy(sums, dsum, n_seg * 8, cudaMemcpyDeviceToHost));
+            if (n_pairs) ok(cudaMemcpy(windows, dwin, (size_t)n_pairs * H * W * 4, cudaMemcpyDeviceToHost));
+        }
+    }
+    cudaFree(dseg); cudaFree(dspec); cudaFree(dsum); cudaFree(dws); cudaFree(dwin); cudaFree(dpi); cudaFree(dpj);
+    if (e != cudaSuccess) { pb_set_error("pb_rcc_windows: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    return rc;
+}

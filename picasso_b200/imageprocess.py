@@ -1,0 +1,147 @@
+"""FFT cross-correlation and RCC on B200.
+
+Drop-in for the hot-path part of ``picasso.imageprocess`` (reference
+picasso/imageprocess.py): ``xcorr`` :27, ``get_image_shift`` :53, ``rcc`` :160.  The
+transforms run in cuFFT (one forward transform per segment, one inverse per pair,
+csrc/rcc.cu); the 5-parameter peak fit of the 5x5 window stays on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable
+
+import numpy as np
+
+from . import _lib, lib
+
+
+def _declare(l):
+    if getattr(l, "_rcc_declared", False):
+        return
+    vp, i32 = C.c_void_p, C.c_int
+    l.pb_rcc_windows.argtypes = [i32, i32, i32, vp, i32, i32, i32, i32, vp, vp]
+    l.pb_rcc_windows.restype = i32
+    l._rcc_declared = True
+
+
+def _crop_geometry(Y, X, roi):
+    """Rows/cols kept by the reference's centre crop (imageprocess.py:88-101)."""
+    Y_ = X_ = 0
+    if roi is not None:
+        Y_ = int((Y - roi) / 2)
+        X_ = int((X - roi) / 2)
+        if Y_ <= 0:
+            Y_ = 0
+        if X_ <= 0:
+            X_ = 0
+    return Y_, X_, Y - 2 * Y_, X - 2 * X_
+
+
+def _windows(segments, roi):
+    """Cropped, fftshift-ed, normalised correlation windows of all i<j pairs."""
+    l = _lib.load()
+    _declare(l)
+    _lib.require_gpu()
+    seg = np.ascontiguousarray(segments, dtype=np.float32)
+    n_seg, Y, X = seg.shape
+    Y_, X_, H, W = _crop_geometry(Y, X, roi)
+    n_pairs = n_seg * (n_seg - 1) // 2
+    win = np.zeros((n_pairs, H, W), dtype=np.float32)
+    sums = np.zeros(n_seg, dtype=np.float64)
+    _lib.check(l.pb_rcc_windows(n_seg, Y, X, _lib.ptr(seg), Y_, X_, H, W, _lib.ptr(win),
+                                _lib.ptr(sums)))
+    return win, sums, (Y_, X_)
+
+
+def xcorr(imageA, imageB):
+    """Cross-correlation of two images (reference imageprocess.py:27-50):
+    ``fftshift(real(ifft2(fft2(A) * conj(fft2(B))))) / sqrt(A.size)``."""
+    stack = np.stack([np.asarray(imageA), np.asarray(imageB)])
+    win, _, _ = _windows(stack, None)
+    return win[0].astype(np.float64)
+
+
+def _gauss_peak_fit(window):
+    """Fit ``a * exp(-0.5 * ((x - xc)^2 + (y - yc)^2) / s^2) + b`` to a square window
+    centred on the brightest pixel, start ``[max, 0, 0, 1, min]``, bounds a, s, b >= 0
+    -- the model, start values and bounds of the reference's ``curve_fit`` call
+    (imageprocess.py:119-135).  Returns (xc, yc)."""
+    from scipy.optimize import curve_fit
+
+    k = window.shape[0] // 2
+    y, x = np.mgrid[-k:k + 1, -k:k + 1]
+
+    def model(coords, a, xc, yc, s, b):
+        xx, yy = coords
+        return (a * np.exp(-0.5 * ((xx - xc) ** 2 + (yy - yc) ** 2) / s ** 2) + b).ravel()
+
+    p0 = [window.max(), 0, 0, 1, window.min()]
+    bounds = ([0, -np.inf, -np.inf, 0, 0], [np.inf] * 5)
+    popt, _ = curve_fit(model, (x, y), window.ravel(), p0=p0, bounds=bounds)
+    return popt[1], popt[2]
+
+
+def _shift_from_window(XCorr, Y, X, Y_, X_, box):
+    """arg-max, fit-window cut-out and peak fit (reference imageprocess.py:103-157)."""
+    fit_X = int(box / 2)
+    y_max_, x_max_ = np.unravel_index(XCorr.argmax(), XCorr.shape)
+    FitROI = XCorr[y_max_ - fit_X: y_max_ + fit_X + 1, x_max_ - fit_X: x_max_ + fit_X + 1]
+    dims = FitROI.shape
+    if 0 in dims or dims[0] != dims[1]:
+        xc, yc = 0, 0
+    else:
+        xc, yc = _gauss_peak_fit(FitROI)
+        xc += X_ + x_max_
+        yc += Y_ + y_max_
+        xc -= np.floor(X / 2)
+        yc -= np.floor(Y / 2)
+    return -yc, -xc
+
+
+def get_image_shift(imageA, imageB, box: int, roi: int | None = None, display: bool = False):
+    """Shift from ``imageA`` to ``imageB`` (reference imageprocess.py:53-157);
+    ``(0, 0)`` if either image sums to zero or the fit window touches the crop edge."""
+    imageA = np.asarray(imageA)
+    imageB = np.asarray(imageB)
+    if (np.sum(imageA) == 0) or (np.sum(imageB) == 0):
+        return 0, 0
+    win, _, (Y_, X_) = _windows(np.stack([imageA, imageB]), roi)
+    Y, X = imageA.shape
+    return _shift_from_window(win[0].astype(np.float64), Y, X, Y_, X_, box)
+
+
+def rcc(segments, max_shift: float | None = None, callback: Callable[[int], None] | None = None):
+    """Redundant cross-correlation over all segment pairs (reference
+    imageprocess.py:160-217); returns ``lib.minimize_shifts(shifts_x, shifts_y)`` =
+    ``(shift_y, shift_x)`` per segment.  ``callback`` is called with 0..n_pairs."""
+    segments = np.asarray(segments)
+    n_segments = len(segments)
+    shifts_x = np.zeros((n_segments, n_segments))
+    shifts_y = np.zeros((n_segments, n_segments))
+    if callback is not None:
+        callback(0)
+    bar = None
+    n_pairs = int(n_segments * (n_segments - 1) / 2)
+    if callback is None:
+        from tqdm import tqdm
+
+        bar = tqdm(total=n_pairs, desc="Correlating image pairs", unit="pairs")
+    if n_pairs:
+        win, sums, (Y_, X_) = _windows(segments, max_shift)
+        _, Y, X = segments.shape
+        flag = 0
+        for i in range(n_segments - 1):
+            for j in range(i + 1, n_segments):
+                if sums[i] == 0 or sums[j] == 0:
+                    sy, sx = 0, 0
+                else:
+                    sy, sx = _shift_from_window(win[flag].astype(np.float64), Y, X, Y_, X_, 5)
+                shifts_y[i, j], shifts_x[i, j] = sy, sx
+                flag += 1
+                if bar is not None:
+                    bar.update()
+                else:
+                    callback(flag)
+    if bar is not None:
+        bar.close()
+    return lib.minimize_shifts(shifts_x, shifts_y)

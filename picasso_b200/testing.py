@@ -83,3 +83,31 @@ def synthetic_movie(frames: int, Y: int, X: int, emitters_per_frame: int = 60, s
     if return_truth:
         return movie, np.concatenate(truth)
     return movie
+
+
+def synthetic_drift_locs(n_frames: int, Y: int, X: int, n_clusters: int = 40,
+                         locs_per_frame: float = 5.0, seed: int = 3, jitter: float = 0.05,
+                         lp: float = 0.05, amp_x: float = 1.0, amp_y: float = 0.7):
+    """Config 5 style localizations: clusters with an analytic drift
+    x += amp_x * sin(2 pi t / (n_frames / 2)), y += amp_y * (t / n_frames - 0.5)."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    n = int(n_frames * locs_per_frame)
+    frame = np.sort(rng.integers(0, n_frames, n)).astype(np.uint32)
+    cx = rng.uniform(6, X - 6, n_clusters)
+    cy = rng.uniform(6, Y - 6, n_clusters)
+    which = rng.integers(0, n_clusters, n)
+    t = frame.astype(np.float64)
+    dx = amp_x * np.sin(2 * np.pi * t / (n_frames / 2.0))
+    dy = amp_y * (t / n_frames - 0.5)
+    x = cx[which] + dx + rng.normal(0, jitter, n)
+    y = cy[which] + dy + rng.normal(0, jitter, n)
+    locs = pd.DataFrame({
+        "frame": frame, "x": x.astype(np.float32), "y": y.astype(np.float32),
+        "lpx": np.full(n, lp, np.float32), "lpy": np.full(n, lp, np.float32),
+    })
+    info = [{"Height": Y, "Width": X, "Frames": n_frames, "Pixelsize": 130}]
+    drift = np.stack([amp_x * np.sin(2 * np.pi * np.arange(n_frames) / (n_frames / 2.0)),
+                      amp_y * (np.arange(n_frames) / n_frames - 0.5)], 1)
+    return locs, info, drift

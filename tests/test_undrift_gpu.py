@@ -1,0 +1,114 @@
+"""GPU parity: cuFFT RCC + CUDA segment rendering vs the real reference (golden) and the
+numpy oracle.  Tolerance: per-pair shifts, segment shifts and the per-frame drift within
+1e-3 px (the reference's own tests allow 0.5 px)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from picasso_b200 import imageprocess, lib, postprocess, testing
+
+pytestmark = [pytest.mark.gpu, pytest.mark.filterwarnings("ignore::DeprecationWarning")]
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "undrift.npz"))
+
+
+@pytest.fixture(scope="module")
+def problem(gold):
+    locs = pd.DataFrame({k: gold[k] for k in ("frame", "x", "y", "lpx", "lpy")})
+    H, W, F = (int(v) for v in gold["info_hwf"])
+    return locs, [{"Height": H, "Width": W, "Frames": F, "Pixelsize": 130}]
+
+
+def test_n_segments_bankers_rounding():
+    assert postprocess.n_segments([{"Frames": 250}], 100) == 2      # 2.5 -> 2
+    assert postprocess.n_segments([{"Frames": 350}], 100) == 4      # 3.5 -> 4
+    assert postprocess.n_segments([{"Frames": 1000}], 100) == 10
+
+
+def test_segment_golden(gold, problem):
+    locs, info = problem
+    seen = []
+    bounds, segs = postprocess.segment(locs, info, 100, {"blur_method": "gaussian",
+                                                         "min_blur_width": 1}, seen.append)
+    assert seen == list(range(9))
+    assert bounds.dtype == np.uint32 and segs.dtype == np.float64
+    np.testing.assert_array_equal(bounds, gold["bounds"])
+    ref = gold["segments"]
+    np.testing.assert_allclose(segs, ref, rtol=1e-4, atol=1e-6 * ref.max())
+    # mass == locs minus the dropped last frame (reference test_undrift.py:305-312)
+    kept = (locs["frame"] < bounds[-1]).sum()
+    assert kept < len(locs)
+
+
+def test_xcorr_and_shifts_golden(gold):
+    segs = gold["segments"].astype(np.float64)
+    xc = imageprocess.xcorr(segs[0], segs[1])
+    ref = gold["xcorr_0_1"]
+    assert xc.shape == ref.shape
+    np.testing.assert_allclose(xc, ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+    assert np.unravel_index(xc.argmax(), xc.shape) == np.unravel_index(ref.argmax(), ref.shape)
+    for (i, j) in ((0, 1), (0, 7), (3, 4)):
+        sy, sx = imageprocess.get_image_shift(segs[i], segs[j], 5, 32)
+        assert abs(sy - gold["pair_shift_y"][i, j]) < 1e-3 and abs(sx - gold["pair_shift_x"][i, j]) < 1e-3
+    sy, sx = imageprocess.get_image_shift(segs[0], segs[3], 5, None)
+    np.testing.assert_allclose([sy, sx], gold["shift_noroi_0_3"], atol=1e-3)
+    assert imageprocess.get_image_shift(np.zeros((16, 16)), segs[0][:16, :16], 5) == (0, 0)
+
+
+def test_rcc_golden(gold):
+    segs = gold["segments"].astype(np.float64)
+    seen = []
+    shift_y, shift_x = imageprocess.rcc(segs, 32, seen.append)
+    assert seen == list(range(29))
+    np.testing.assert_allclose(shift_y, gold["rcc_shift_y"], atol=1e-3)
+    np.testing.assert_allclose(shift_x, gold["rcc_shift_x"], atol=1e-3)
+
+
+def test_undrift_golden_and_ground_truth(gold, problem):
+    locs, info = problem
+    drift, und = postprocess.undrift(locs, info, 100, display=False,
+                                     segmentation_callback=lambda i: None,
+                                     rcc_callback=lambda i: None)
+    assert list(drift.columns) == ["x", "y"] and len(drift) == info[0]["Frames"]
+    np.testing.assert_allclose(drift["x"].to_numpy(), gold["drift_x"], atol=1e-3)
+    np.testing.assert_allclose(drift["y"].to_numpy(), gold["drift_y"], atol=1e-3)
+    np.testing.assert_allclose(und["x"].to_numpy(), gold["undrifted_x"], atol=1e-3)
+    np.testing.assert_allclose(und["y"].to_numpy(), gold["undrifted_y"], atol=1e-3)
+    assert und is not locs and not np.array_equal(und["x"].to_numpy(), locs["x"].to_numpy())
+
+
+def test_undrift_recovers_injected_drift():
+    """Reference test_undrift.py:333-340: RCC recovers the injected drift within 0.5 px
+    after de-meaning."""
+    locs, info, truth = testing.synthetic_drift_locs(2000, 96, 96, n_clusters=60,
+                                                     locs_per_frame=8, seed=5)
+    drift, _ = postprocess.undrift(locs, info, 200, display=False,
+                                   segmentation_callback=lambda i: None,
+                                   rcc_callback=lambda i: None)
+    for k, col in enumerate(("x", "y")):
+        est = drift[col].to_numpy() - drift[col].mean()
+        tru = truth[:, k] - truth[:, k].mean()
+        assert np.abs(est - tru).max() < 0.5
+
+
+def test_apply_drift_and_minimize_shifts():
+    locs = pd.DataFrame({"frame": np.uint32([0, 1, 2]), "x": np.float32([1, 1, 1]),
+                         "y": np.float32([2, 2, 2])})
+    info = [{"Frames": 3}]
+    out = postprocess.apply_drift(locs.copy(), info, drift=np.array([[0.1, 0.2], [0.2, 0.4], [0.3, 0.6]]))
+    np.testing.assert_allclose(out["x"], [0.9, 0.8, 0.7], atol=1e-6)
+    np.testing.assert_allclose(out["y"], [1.8, 1.6, 1.4], atol=1e-6)
+    with pytest.raises(ValueError):
+        postprocess.apply_drift(locs.copy(), info, drift=np.zeros((2, 2)))
+    true = np.array([0.0, 0.5, -0.25, 1.0])
+    sx = np.zeros((4, 4)); sy = np.zeros((4, 4))
+    for i in range(3):
+        for j in range(i + 1, 4):
+            sx[i, j] = true[j] - true[i]
+    y, x = lib.minimize_shifts(sx, sy)
+    np.testing.assert_allclose(x, true, atol=1e-9)

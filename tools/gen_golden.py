@@ -216,8 +216,39 @@ def gen_render(ref):
             out[f"{tag}_{bm}_image"] = img
     save("render.npz", **out)
 
+def gen_undrift(ref):
+    """RCC undrift golden vectors (reference postprocess.py:2824-2961,
+    imageprocess.py:27-217, lib.py:2034-2078)."""
+    from picasso_b200 import testing
 
-GENERATORS = {"mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render}
+    post, imp = ref["postprocess"], ref["imageprocess"]
+    locs, info, _ = testing.synthetic_drift_locs(800, 64, 72, n_clusters=30, locs_per_frame=6,
+                                                 seed=3)
+    out = {c: locs[c].to_numpy() for c in locs.columns}
+    out["info_hwf"] = np.array([64, 72, 800])
+    bounds, segments = post.segment(locs, info, 100,
+                                    {"blur_method": "gaussian", "min_blur_width": 1}, lambda i: None)
+    out["bounds"] = bounds
+    out["segments"] = segments.astype(np.float32)     # values are float32 renders
+    assert (segments == segments.astype(np.float32)).all()
+    n = len(segments)
+    sy = np.zeros((n, n)); sx = np.zeros((n, n))
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            sy[i, j], sx[i, j] = imp.get_image_shift(segments[i], segments[j], 5, 32)
+    out["pair_shift_y"] = sy; out["pair_shift_x"] = sx
+    shift_y, shift_x = imp.rcc(segments, 32, lambda i: None)
+    out["rcc_shift_y"] = shift_y; out["rcc_shift_x"] = shift_x
+    out["xcorr_0_1"] = imp.xcorr(segments[0], segments[1])
+    out["shift_noroi_0_3"] = np.array(imp.get_image_shift(segments[0], segments[3], 5, None))
+    drift, und = post.undrift(locs, info, 100, display=False, segmentation_callback=lambda i: None,
+                              rcc_callback=lambda i: None)
+    out["drift_x"] = drift["x"].to_numpy(); out["drift_y"] = drift["y"].to_numpy()
+    out["undrifted_x"] = und["x"].to_numpy(); out["undrifted_y"] = und["y"].to_numpy()
+    save("undrift.npz", **out)
+
+
+GENERATORS = {"mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift}
 
 
 def main():
