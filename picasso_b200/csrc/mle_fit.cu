@@ -40,10 +40,10 @@ constexpr int kRedStride = 23;     // doubles per lane in the reduction scratch 
 
 // tuning knobs (tools/tune_mle.py builds variants with -D overrides)
 #ifndef PB_MLE_MINB
-#define PB_MLE_MINB 3          // min resident CTAs per SM requested from ptxas
+#define PB_MLE_MINB 4          // min resident CTAs per SM requested from ptxas
 #endif
 #ifndef PB_MLE_PIX_UNROLL
-#define PB_MLE_PIX_UNROLL 32   // unroll factor of the per-row pixel loops
+#define PB_MLE_PIX_UNROLL 1   // unroll factor of the per-row pixel loops
 #endif
 #define PB_STR2(x) #x
 #define PB_STR(x) PB_STR2(x)
@@ -61,19 +61,34 @@ struct MleArgs {
     int* status;          // (n,) nullable
 };
 
+constexpr int kNFx = 13;          // per-column x-factors kept in shared memory
+
 template <int BOX, int G>
 struct MleSmem {
     static constexpr int S = 32 / G;
     static constexpr int PIX = BOX * BOX;
-    static constexpr int kRoiBytes = 2 * kTileSpots * PIX * 4;          // 2 stages
-    static constexpr int kFxBytes = S * 5 * BOX * 8;
+    static constexpr int kRoiBytes = 2 * kTileSpots * PIX * 4;          // 2 TMA stages (f32)
+    static constexpr int kDataBytes = ((S * PIX * 8 + 15) / 16) * 16;    // current spots as f64
+    static constexpr int kFxBytes = S * kNFx * BOX * 8;
     static constexpr int kRedBytes = 32 * kRedStride * 8;
     static constexpr int kSumBytes = S * 24 * 8;
     static constexpr int kBarBytes = 16;
     static constexpr int kPerWarp =
-        ((kRoiBytes + kFxBytes + kRedBytes + kSumBytes + kBarBytes + 127) / 128) * 128;
+        ((kRoiBytes + kDataBytes + kFxBytes + kRedBytes + kSumBytes + kBarBytes + 127) / 128) * 128;
     static constexpr int kTotal = kPerWarp * kWarpsPerBlock;
 };
+
+// 1/x for x in the normal range: MUFU seed (rcp.approx.ftz.f64) refined by one cubic
+// and one quadratic Newton step (seed error e -> e^6), i.e. full double precision
+// without the slow-path branch that '/' carries for denormals and infinities.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    r = fma(r, fma(e, e, e), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
 
 // ---- Jacobi eigen pseudo-inverse diagonal (rare fallback; np.linalg.pinv) --
 template <int NP>
@@ -200,6 +215,8 @@ mle_fit_kernel(const MleArgs a) {
     constexpr int NSUB = kTileSpots / S;
     constexpr int NFISH = NP * (NP + 1) / 2;
     static_assert(BOX + 1 <= G, "group too small for box");
+    // shared-memory x-factor slots (per column i)
+    enum { F_NPX = 0, F_PX, F_C1, F_C2, F_G1, F_G2, F_PX2, F_C1SQ, F_G1SQ, F_G1PX, F_C1PX, F_C1G1 };
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
@@ -207,13 +224,16 @@ mle_fit_kernel(const MleArgs a) {
     const int g = lane % G;         // lane within the spot group
     const int grp = lane / G;       // group within the warp
     unsigned char* wbase = smem_raw + warp * SM::kPerWarp;
-    float* roi = reinterpret_cast<float*>(wbase);                                 // [2][4*PIX]
-    double* fx = reinterpret_cast<double*>(wbase + SM::kRoiBytes) + grp * 5 * BOX;  // [5][BOX]
-    double* red = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kFxBytes);  // [32][23]
-    double* sums = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kFxBytes +
-                                             SM::kRedBytes) + grp * 24;          // [24]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + SM::kRoiBytes + SM::kFxBytes +
-                                                 SM::kRedBytes + SM::kSumBytes);  // [2]
+    float* roi = reinterpret_cast<float*>(wbase);                                   // [2][4*PIX]
+    double* dspot = reinterpret_cast<double*>(wbase + SM::kRoiBytes) + grp * PIX;    // [PIX] f64
+    double* fx = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kDataBytes) +
+                 grp * kNFx * BOX;                                                  // [13][BOX]
+    double* red = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kDataBytes +
+                                            SM::kFxBytes);                          // [32][23]
+    double* sums = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kDataBytes +
+                                             SM::kFxBytes + SM::kRedBytes) + grp * 24;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + SM::kRoiBytes + SM::kDataBytes +
+                                                 SM::kFxBytes + SM::kRedBytes + SM::kSumBytes);
 
     const long long n = a.n;
     const long long ntiles = (n + kTileSpots - 1) / kTileSpots;
@@ -273,12 +293,16 @@ mle_fit_kernel(const MleArgs a) {
             const float* sp = tile_roi + local * PIX;
             int st_flags = 0;
 
+            // the ROI as float64 (converted once; every iteration re-reads it)
+            __syncwarp();
+            for (int q = g; q < PIX; q += G) dspot[q] = (double)sp[q];
+
             // ---------------- initial parameters (gaussmle.py:28-168) -----
             float th[6];
             {
                 double rs_ = 0.0, rxs = 0.0;
                 if (g < BOX) {
-#pragma unroll
+#pragma unroll 1
                     for (int i = 0; i < BOX; i++) {
                         double v = (double)sp[g * BOX + i];
                         rs_ += v;
@@ -296,7 +320,7 @@ mle_fit_kernel(const MleArgs a) {
                 if (g < BOX) {
                     const int k = g;
                     const int min_m = k - 1 < 0 ? 0 : k - 1, max_m = k + 2 > BOX ? BOX : k + 2;
-#pragma unroll
+#pragma unroll 1
                     for (int l = 0; l < BOX; l++) {
                         const int min_n = l - 1 < 0 ? 0 : l - 1, max_n = l + 2 > BOX ? BOX : l + 2;
                         double ns = 0.0;
@@ -311,21 +335,16 @@ mle_fit_kernel(const MleArgs a) {
                 ph = ph > 1.0 ? ph : 1.0;
                 // initial sigmas from the centre row / column of (spot - bg)
                 constexpr int H = BOX / 2;
-                double sdy = 0.0, sy_ = 0.0;
+                double sdy = 0.0, sy_ = 0.0, sdx = 0.0, sx_ = 0.0;
                 if (g < BOX) {
-                    float vy = sp[g * BOX + H] - bg;
-                    sdy = (double)vy * (double)((g - H) * (g - H));
-                    sy_ = (double)vy;
+                    const float vy = sp[g * BOX + H] - bg;
+                    const float vx = sp[H * BOX + g] - bg;
+                    const double d2 = (double)((g - H) * (g - H));
+                    sdy = (double)vy * d2; sy_ = (double)vy;
+                    sdx = (double)vx * d2; sx_ = (double)vx;
                 }
-                sdy = pb_gsum<G>(sdy);
-                sy_ = pb_gsum<G>(sy_);
-                double sdx = 0.0, sx_ = 0.0;
-#pragma unroll
-                for (int i = 0; i < BOX; i++) {
-                    float vx = sp[H * BOX + i] - bg;
-                    sdx += (double)vx * (double)((i - H) * (i - H));
-                    sx_ += (double)vx;
-                }
+                sdy = pb_gsum<G>(sdy); sy_ = pb_gsum<G>(sy_);
+                sdx = pb_gsum<G>(sdx); sx_ = pb_gsum<G>(sx_);
                 double sy0, sx0;
                 // the reference raises ZeroDivisionError when a sum is 0; we
                 // emit its 0.01 fallback and set status bit 0
@@ -348,241 +367,276 @@ mle_fit_kernel(const MleArgs a) {
                 ms_mine = g < 2 ? ms0 : g == 2 ? ms2 : g == 3 ? ms3 : g == 4 ? ms4 : ms5;
             }
 
-            // ---- shared 1-D machinery -------------------------------------
-            double PSFy, cy1, cy2, gy1, gy2;   // y factors of row g (registers)
-            auto eval_factors = [&]() {
-                // reciprocals of sigma, f32(sigma^2), f32(sigma^3), f32(sigma^5)
-                // (float32 ** int stays float32 in the reference): one per lane
-                const int ax = (METHOD == 1) ? ((g >> 2) & 1) : 0;
-                const float sig = ax ? th[5] : th[4];
-                const float s2f = sig * sig;
-                const float s3f = sig * s2f;
-                const float s5f = sig * (s2f * s2f);
-                const int kk_ = g & 3;
-                const double v = kk_ == 0 ? (double)sig : kk_ == 1 ? (double)s2f
-                                 : kk_ == 2 ? (double)s3f : (double)s5f;
-                const double r = 1.0 / v;
-                const double rsx = pb_gshfl<G>(r, 0), r2x = pb_gshfl<G>(r, 1);
-                const double r3x = pb_gshfl<G>(r, 2), r5x = pb_gshfl<G>(r, 3);
-                double rsy, r2y, r3y, r5y;
-                if constexpr (METHOD == 1) {
-                    rsy = pb_gshfl<G>(r, 4); r2y = pb_gshfl<G>(r, 5);
-                    r3y = pb_gshfl<G>(r, 6); r5y = pb_gshfl<G>(r, 7);
-                } else { rsy = rsx; r2y = r2x; r3y = r3x; r5y = r5x; }
-                const double sxd = (double)th[4], syd = (double)th[5];
-                // edge g: minus edge of pixel g == plus edge of pixel g-1 (exact)
-                const double ex = ((double)g - (double)th[0]) - 0.5;
-                const double ey = ((double)g - (double)th[1]) - 0.5;
-                const double Ex = erf(ex * (kInvSqrt2 * rsx));
-                const double Ey = erf(ey * (kInvSqrt2 * rsy));
-                const double tx = ex * rsx, ty = ey * rsy;
-                const double qx = 0.5 * tx * tx, qy = 0.5 * ty * ty;
-                const double Ax = exp(-qx), Ay = exp(-qy);
-                // plus-edge values from the next lane
-                const double Exp_ = pb_gshfl_down1<G>(Ex), Eyp_ = pb_gshfl_down1<G>(Ey);
-                const double Axp = pb_gshfl_down1<G>(Ax), Ayp = pb_gshfl_down1<G>(Ay);
-                const double exp_ = ex + 1.0, eyp_ = ey + 1.0;
-                const double PSFx = 0.5 * (Exp_ - Ex);
-                PSFy = 0.5 * (Eyp_ - Ey);
-                const double cx1 = (Ax - Axp) * rsx * kInvSqrt2Pi;
-                cy1 = (Ay - Ayp) * rsy * kInvSqrt2Pi;
-                const double cx2 = (ex * Ax - exp_ * Axp) * r3x * kInvSqrt2Pi;
-                cy2 = (ey * Ay - eyp_ * Ayp) * r3y * kInvSqrt2Pi;
-                double gx1, gx2;
-                if constexpr (METHOD == 1) {
-                    // _G uses exp(-(a^2)/(2*f32(sigma^2))): correct Ax by the
-                    // f32 rounding of sigma^2 (gaussmle.py:306-316)
-                    const double rhox = fma(sxd * sxd, r2x, -1.0), rhoy = fma(syd * syd, r2y, -1.0);
-                    const double zx = -qx * rhox, zy = -qy * rhoy;
-                    const double AGx = fma(Ax, fma(0.5 * zx, zx, zx), Ax);
-                    const double AGy = fma(Ay, fma(0.5 * zy, zy, zy), Ay);
-                    const double AGxp = pb_gshfl_down1<G>(AGx), AGyp = pb_gshfl_down1<G>(AGy);
-                    const double w1x = ex * AGx - exp_ * AGxp, w1y = ey * AGy - eyp_ * AGyp;
-                    const double w3x = ex * (ex * ex) * AGx - exp_ * (exp_ * exp_) * AGxp;
-                    const double w3y = ey * (ey * ey) * AGy - eyp_ * (eyp_ * eyp_) * AGyp;
-                    gx1 = w1x * r2x * kInvSqrt2Pi;
-                    gy1 = w1y * r2y * kInvSqrt2Pi;
-                    gx2 = (w3x * r5x - 2.0 * w1x * r3x) * kInvSqrt2Pi;
-                    gy2 = (w3y * r5y - 2.0 * w1y * r3y) * kInvSqrt2Pi;
-                } else {
-                    // isotropic sigma (gaussmle.py:339-383): dPSF/dsigma, d2PSF/dsigma2
-                    const double am = ex * (rsx * kInvSqrt2), ap = exp_ * (rsx * kInvSqrt2);
-                    const double bm = ey * (rsx * kInvSqrt2), bp = eyp_ * (rsx * kInvSqrt2);
-                    const double Fx = am * Ax - ap * Axp, Fy = bm * Ay - bp * Ayp;
-                    gx1 = Fx * rsx * kInvSqrtPi;      // dPSFxdt
-                    gy1 = Fy * rsx * kInvSqrtPi;
-                    const double dFx =
-                        (ap * Axp * (1.0 - 2.0 * ap * ap) - am * Ax * (1.0 - 2.0 * am * am)) * rsx;
-                    const double dFy =
-                        (bp * Ayp * (1.0 - 2.0 * bp * bp) - bm * Ay * (1.0 - 2.0 * bm * bm)) * rsx;
-                    const double rinvf = (double)(1.0f / th[4]);   // sigma ** (-1) is f32
-                    gx2 = kInvSqrtPi * (-Fx * r2x + rinvf * dFx);  // d2PSFxdt2
-                    gy2 = kInvSqrtPi * (-Fy * r2x + rinvf * dFy);
-                }
-                __syncwarp();   // previous readers of fx are done
-                if (g < BOX) {
-                    fx[0 * BOX + g] = PSFx; fx[1 * BOX + g] = cx1; fx[2 * BOX + g] = cx2;
-                    fx[3 * BOX + g] = gx1;  fx[4 * BOX + g] = gx2;
-                }
-                __syncwarp();
-            };
-
-            // ---------------- Newton iterations ---------------------------
+            // ---- Newton iterations, then one more pass of the same loop body
+            //      in CRLB mode (one instance of the factor code: I-cache) ------
             int kk = 0;
             bool done = !valid;
+            bool crlb_phase = false;
+#pragma unroll 1
             while (true) {
                 const bool active = !done && kk < a.max_it;
-                if (!__any_sync(0xffffffffu, active)) break;
-                eval_factors();
-                const double N = (double)th[2], bg = (double)th[3];
-                double num[6], den[6];
-#pragma unroll
-                for (int l = 0; l < 6; l++) num[l] = den[l] = 0.0;
-                if (g < BOX) {
-                    const float* rowp = sp + g * BOX;
-                    const double NPy = N * PSFy;
-                    PB_PIX_UNROLL
-                    for (int i = 0; i < BOX; i++) {
-                        const double px = fx[0 * BOX + i], c1 = fx[1 * BOX + i], c2 = fx[2 * BOX + i];
-                        const double g1 = fx[3 * BOX + i], g2 = fx[4 * BOX + i];
-                        const double Npx = N * px;
-                        const double pp = px * PSFy;
-                        const double model = fma(Npx, PSFy, bg);
-                        const double data = (double)rowp[i];
-                        double cf = 0.0, df = 0.0;
-                        if (model > 10e-3) {
-                            const double inv = 1.0 / model;
-                            const double t = data * inv;
-                            cf = t - 1.0;
-                            df = t * inv;
-                        }
-                        cf = fmin(cf, 10e4);
-                        df = fmin(df, 10e4);
-                        const double d0 = NPy * c1, e0 = NPy * c2;
-                        const double d1 = Npx * cy1, e1 = Npx * cy2;
-                        num[0] = fma(cf, d0, num[0]); den[0] += fma(cf, e0, -df * d0 * d0);
-                        num[1] = fma(cf, d1, num[1]); den[1] += fma(cf, e1, -df * d1 * d1);
-                        num[2] = fma(cf, pp, num[2]); den[2] -= df * pp * pp;
-                        num[3] += cf;                  den[3] -= df;
-                        if constexpr (METHOD == 1) {
-                            const double d4 = NPy * g1, e4 = NPy * g2;
-                            const double d5 = Npx * gy1, e5 = Npx * gy2;
-                            num[4] = fma(cf, d4, num[4]); den[4] += fma(cf, e4, -df * d4 * d4);
-                            num[5] = fma(cf, d5, num[5]); den[5] += fma(cf, e5, -df * d5 * d5);
-                        } else {
-                            // dudt = N*(PSFy*dPx + PSFx*dPy); the reference's
-                            // d2udt2 has photons on the first term only (:380-382)
-                            const double d4 = N * (PSFy * g1 + px * gy1);
-                            const double e4 = NPy * g2 + 2.0 * g1 * gy1 + px * gy2;
-                            num[4] = fma(cf, d4, num[4]); den[4] += fma(cf, e4, -df * d4 * d4);
-                        }
-                    }
-                }
-                // combine over the group's lanes through shared memory
-                double* myred = red + lane * kRedStride;
-#pragma unroll
-                for (int l = 0; l < NP; l++) { myred[l] = num[l]; myred[6 + l] = den[l]; }
-                __syncwarp();
-                float th_new = 0.0f;
-                if (g < NP) {
-                    double sn = 0.0, sd = 0.0;
-                    const double* gr = red + (grp * G) * kRedStride;
-#pragma unroll
-                    for (int q = 0; q < BOX; q++) {
-                        sn += gr[q * kRedStride + g];
-                        sd += gr[q * kRedStride + 6 + g];
-                    }
-                    // clamped per-parameter Newton step in float32
-                    // (gaussmle.py:648-670, 860-884)
-                    const float nu = (float)sn, de = (float)sd;
-                    float thl = g == 0 ? th[0] : g == 1 ? th[1] : g == 2 ? th[2] : g == 3 ? th[3]
-                                : g == 4 ? th[4] : th[5];
-                    float upd;
-                    if (de == 0.0f) {
-                        if constexpr (METHOD == 1) {
-                            const float sg = nu > 0.f ? 1.f : (nu < 0.f ? -1.f : nu);
-                            upd = sg * ms_mine;
-                        } else {
-                            const float pr = nu * ms_mine;
-                            upd = pr > 0.f ? 1.f : (pr < 0.f ? -1.f : pr);
-                        }
-                    } else {
-                        upd = fminf(fmaxf(nu / de, -ms_mine), ms_mine);
-                    }
-                    thl -= upd;
-                    if (g == 2) thl = fmaxf(thl, 1.0f);
-                    if (g >= 3) thl = fmaxf(thl, 0.01f);
-                    if (METHOD == 0 && g == 4) thl = fminf(thl, (float)BOX);
-                    th_new = thl;
-                }
-                float tn[6];
-#pragma unroll
-                for (int l = 0; l < NP; l++) tn[l] = pb_gshfl<G>(th_new, l);
-                if (METHOD == 0) tn[5] = tn[4];
-                if (active) {
-                    kk++;
-                    bool conv = ((double)fabsf(th[0] - tn[0]) < a.eps) &&
-                                ((double)fabsf(th[1] - tn[1]) < a.eps);
-                    if (METHOD == 1)
-                        conv = conv && ((double)fabsf(th[4] - tn[4]) < a.eps) &&
-                               ((double)fabsf(th[5] - tn[5]) < a.eps);
-#pragma unroll
-                    for (int l = 0; l < 6; l++) th[l] = tn[l];
-                    if (conv) done = true;
-                }
-            }
+                if (!__any_sync(0xffffffffu, active)) crlb_phase = true;
 
-            // ---------------- CRLB + log-likelihood -----------------------
-            eval_factors();
-            {
+                // ===== 1-D factors: lane g evaluates pixel EDGE g on both axes =====
+                double PSFy, cy1, cy2, gy1, gy2;   // y factors of row g (registers)
+                {
+                    // reciprocals of sigma, f32(sigma^2), f32(sigma^3), f32(sigma^5)
+                    // (float32 ** int stays float32 in the reference): one per lane
+                    const int ax = (METHOD == 1) ? ((g >> 2) & 1) : 0;
+                    const float sig = ax ? th[5] : th[4];
+                    const float s2f = sig * sig;
+                    const float s3f = sig * s2f;
+                    const float s5f = sig * (s2f * s2f);
+                    const int kq = g & 3;
+                    const double v = kq == 0 ? (double)sig : kq == 1 ? (double)s2f
+                                     : kq == 2 ? (double)s3f : (double)s5f;
+                    const double r = 1.0 / v;
+                    const double rsx = pb_gshfl<G>(r, 0), r2x = pb_gshfl<G>(r, 1);
+                    const double r3x = pb_gshfl<G>(r, 2), r5x = pb_gshfl<G>(r, 3);
+                    double rsy, r2y, r3y, r5y;
+                    if constexpr (METHOD == 1) {
+                        rsy = pb_gshfl<G>(r, 4); r2y = pb_gshfl<G>(r, 5);
+                        r3y = pb_gshfl<G>(r, 6); r5y = pb_gshfl<G>(r, 7);
+                    } else { rsy = rsx; r2y = r2x; r3y = r3x; r5y = r5x; }
+                    const double sxd = (double)th[4], syd = (double)th[5];
+                    // edge g: minus edge of pixel g == plus edge of pixel g-1 (exact)
+                    const double ex = ((double)g - (double)th[0]) - 0.5;
+                    const double ey = ((double)g - (double)th[1]) - 0.5;
+                    const double Ex = erf(ex * (kInvSqrt2 * rsx));
+                    const double Ey = erf(ey * (kInvSqrt2 * rsy));
+                    const double tx = ex * rsx, ty = ey * rsy;
+                    const double qx = 0.5 * tx * tx, qy = 0.5 * ty * ty;
+                    const double Ax = exp(-qx), Ay = exp(-qy);
+                    // plus-edge values from the next lane
+                    const double Exp_ = pb_gshfl_down1<G>(Ex), Eyp_ = pb_gshfl_down1<G>(Ey);
+                    const double Axp = pb_gshfl_down1<G>(Ax), Ayp = pb_gshfl_down1<G>(Ay);
+                    const double exp_ = ex + 1.0, eyp_ = ey + 1.0;
+                    const double PSFx = 0.5 * (Exp_ - Ex);
+                    PSFy = 0.5 * (Eyp_ - Ey);
+                    const double cx1 = (Ax - Axp) * rsx * kInvSqrt2Pi;
+                    cy1 = (Ay - Ayp) * rsy * kInvSqrt2Pi;
+                    const double cx2 = (ex * Ax - exp_ * Axp) * r3x * kInvSqrt2Pi;
+                    cy2 = (ey * Ay - eyp_ * Ayp) * r3y * kInvSqrt2Pi;
+                    double gx1, gx2;
+                    if constexpr (METHOD == 1) {
+                        // _G uses exp(-(a^2)/(2*f32(sigma^2))): correct Ax by the
+                        // f32 rounding of sigma^2 (gaussmle.py:306-316)
+                        const double rhox = fma(sxd * sxd, r2x, -1.0), rhoy = fma(syd * syd, r2y, -1.0);
+                        const double zx = -qx * rhox, zy = -qy * rhoy;
+                        const double AGx = fma(Ax, fma(0.5 * zx, zx, zx), Ax);
+                        const double AGy = fma(Ay, fma(0.5 * zy, zy, zy), Ay);
+                        const double AGxp = pb_gshfl_down1<G>(AGx), AGyp = pb_gshfl_down1<G>(AGy);
+                        const double w1x = ex * AGx - exp_ * AGxp, w1y = ey * AGy - eyp_ * AGyp;
+                        const double w3x = ex * (ex * ex) * AGx - exp_ * (exp_ * exp_) * AGxp;
+                        const double w3y = ey * (ey * ey) * AGy - eyp_ * (eyp_ * eyp_) * AGyp;
+                        gx1 = w1x * r2x * kInvSqrt2Pi;
+                        gy1 = w1y * r2y * kInvSqrt2Pi;
+                        gx2 = (w3x * r5x - 2.0 * w1x * r3x) * kInvSqrt2Pi;
+                        gy2 = (w3y * r5y - 2.0 * w1y * r3y) * kInvSqrt2Pi;
+                    } else {
+                        // isotropic sigma (gaussmle.py:339-383): dPSF/dsigma, d2PSF/dsigma2
+                        const double am = ex * (rsx * kInvSqrt2), ap = exp_ * (rsx * kInvSqrt2);
+                        const double bm = ey * (rsx * kInvSqrt2), bp = eyp_ * (rsx * kInvSqrt2);
+                        const double Fx = am * Ax - ap * Axp, Fy = bm * Ay - bp * Ayp;
+                        gx1 = Fx * rsx * kInvSqrtPi;      // dPSFxdt
+                        gy1 = Fy * rsx * kInvSqrtPi;
+                        const double dFx =
+                            (ap * Axp * (1.0 - 2.0 * ap * ap) - am * Ax * (1.0 - 2.0 * am * am)) * rsx;
+                        const double dFy =
+                            (bp * Ayp * (1.0 - 2.0 * bp * bp) - bm * Ay * (1.0 - 2.0 * bm * bm)) * rsx;
+                        const double rinvf = (double)(1.0f / th[4]);   // sigma ** (-1) is f32
+                        gx2 = kInvSqrtPi * (-Fx * r2x + rinvf * dFx);  // d2PSFxdt2
+                        gy2 = kInvSqrtPi * (-Fy * r2x + rinvf * dFy);
+                    }
+                    __syncwarp();   // previous readers of fx are done
+                    if (g < BOX) {
+                        fx[F_NPX * BOX + g] = (double)th[2] * PSFx;
+                        fx[F_PX * BOX + g] = PSFx;
+                        fx[F_C1 * BOX + g] = cx1;
+                        fx[F_C2 * BOX + g] = cx2;
+                        fx[F_G1 * BOX + g] = gx1;
+                        fx[F_G2 * BOX + g] = gx2;
+                        fx[F_PX2 * BOX + g] = PSFx * PSFx;
+                        fx[F_C1SQ * BOX + g] = cx1 * cx1;
+                        fx[F_G1SQ * BOX + g] = gx1 * gx1;
+                        fx[F_G1PX * BOX + g] = gx1 * PSFx;
+                        fx[F_C1PX * BOX + g] = cx1 * PSFx;
+                        fx[F_C1G1 * BOX + g] = cx1 * gx1;
+                    }
+                    __syncwarp();
+                }
                 const double N = (double)th[2], bg = (double)th[3];
-                double F[NFISH];
-                double ll = 0.0;
-#pragma unroll
-                for (int q = 0; q < NFISH; q++) F[q] = 0.0;
-                if (g < BOX) {
-                    const float* rowp = sp + g * BOX;
-                    const double NPy = N * PSFy;
-                    PB_PIX_UNROLL
-                    for (int i = 0; i < BOX; i++) {
-                        const double px = fx[0 * BOX + i], c1 = fx[1 * BOX + i];
-                        const double g1 = fx[3 * BOX + i];
-                        const double Npx = N * px;
-                        const double model = fma(Npx, PSFy, bg);
-                        double du[NP];
-                        du[0] = NPy * c1;
-                        du[1] = Npx * cy1;
-                        du[2] = px * PSFy;
-                        du[3] = 1.0;
-                        if constexpr (METHOD == 1) { du[4] = NPy * g1; du[5] = Npx * gy1; }
-                        else du[4] = N * (PSFy * g1 + px * gy1);
-                        const double inv = 1.0 / model;
-                        int q = 0;
-#pragma unroll
-                        for (int k = 0; k < NP; k++) {
-                            const double dk = du[k] * inv;
-#pragma unroll
-                            for (int l = k; l < NP; l++) { F[q] = fma(du[l], dk, F[q]); q++; }
+                const double NPy = N * PSFy;
+                double* myred = red + lane * kRedStride;
+                const double* gr = red + (grp * G) * kRedStride;
+
+                if (!crlb_phase) {
+                    // ===== Newton sums.  Every derivative is (row factor) x (column
+                    // factor), so lane j accumulates column-weighted sums of cf and df
+                    // over its row and applies the row factors once per row. =====
+                    double c0 = 0, cpx = 0, cc1 = 0, cc2 = 0, cg1 = 0, cg2 = 0;
+                    double d0 = 0, dpx2 = 0, dc1 = 0, dg1 = 0, dgp = 0;
+                    if (g < BOX) {
+                        const double* drow = dspot + g * BOX;
+                        PB_PIX_UNROLL
+                        for (int i = 0; i < BOX; i++) {
+                            const double model = fma(fx[F_NPX * BOX + i], PSFy, bg);
+                            double cf = 0.0, df = 0.0;
+                            if (model > 10e-3) {
+                                const double inv = fast_rcp(model);
+                                const double t = drow[i] * inv;
+                                cf = fmin(t - 1.0, 10e4);
+                                df = fmin(t * inv, 10e4);
+                            }
+                            c0 += cf;
+                            cpx = fma(cf, fx[F_PX * BOX + i], cpx);
+                            cc1 = fma(cf, fx[F_C1 * BOX + i], cc1);
+                            cc2 = fma(cf, fx[F_C2 * BOX + i], cc2);
+                            cg1 = fma(cf, fx[F_G1 * BOX + i], cg1);
+                            cg2 = fma(cf, fx[F_G2 * BOX + i], cg2);
+                            d0 += df;
+                            dpx2 = fma(df, fx[F_PX2 * BOX + i], dpx2);
+                            dc1 = fma(df, fx[F_C1SQ * BOX + i], dc1);
+                            dg1 = fma(df, fx[F_G1SQ * BOX + i], dg1);
+                            if constexpr (METHOD == 0) dgp = fma(df, fx[F_G1PX * BOX + i], dgp);
                         }
-                        const float dataf = rowp[i];
+                    }
+                    const double Ncy1 = N * cy1, Ncy2 = N * cy2;
+                    myred[0] = NPy * cc1;            myred[6] = NPy * cc2 - NPy * NPy * dc1;
+                    myred[1] = Ncy1 * cpx;           myred[7] = Ncy2 * cpx - Ncy1 * Ncy1 * dpx2;
+                    myred[2] = PSFy * cpx;           myred[8] = -PSFy * PSFy * dpx2;
+                    myred[3] = c0;                   myred[9] = -d0;
+                    if constexpr (METHOD == 1) {
+                        const double Ngy1 = N * gy1, Ngy2 = N * gy2;
+                        myred[4] = NPy * cg1;        myred[10] = NPy * cg2 - NPy * NPy * dg1;
+                        myred[5] = Ngy1 * cpx;       myred[11] = Ngy2 * cpx - Ngy1 * Ngy1 * dpx2;
+                    } else {
+                        // dudt = N*(PSFy*dPx + PSFx*dPy); the reference's d2udt2 has
+                        // photons on the first term only (gaussmle.py:380-382)
+                        myred[4] = N * (PSFy * cg1 + gy1 * cpx);
+                        myred[10] = (NPy * cg2 + 2.0 * gy1 * cg1 + gy2 * cpx) -
+                                    N * N * (PSFy * PSFy * dg1 + 2.0 * PSFy * gy1 * dgp +
+                                             gy1 * gy1 * dpx2);
+                    }
+                    __syncwarp();
+                    float th_new = 0.0f;
+                    if (g < NP) {
+                        double sn = 0.0, sd = 0.0;
+#pragma unroll 1
+                        for (int q = 0; q < BOX; q++) {
+                            sn += gr[q * kRedStride + g];
+                            sd += gr[q * kRedStride + 6 + g];
+                        }
+                        // clamped per-parameter Newton step in float32
+                        // (gaussmle.py:648-670, 860-884)
+                        const float nu = (float)sn, de = (float)sd;
+                        float thl = g == 0 ? th[0] : g == 1 ? th[1] : g == 2 ? th[2] : g == 3 ? th[3]
+                                    : g == 4 ? th[4] : th[5];
+                        float upd;
+                        if (de == 0.0f) {
+                            if constexpr (METHOD == 1) {
+                                const float sg = nu > 0.f ? 1.f : (nu < 0.f ? -1.f : nu);
+                                upd = sg * ms_mine;
+                            } else {
+                                const float pr = nu * ms_mine;
+                                upd = pr > 0.f ? 1.f : (pr < 0.f ? -1.f : pr);
+                            }
+                        } else {
+                            upd = fminf(fmaxf(nu / de, -ms_mine), ms_mine);
+                        }
+                        thl -= upd;
+                        if (g == 2) thl = fmaxf(thl, 1.0f);
+                        if (g >= 3) thl = fmaxf(thl, 0.01f);
+                        if (METHOD == 0 && g == 4) thl = fminf(thl, (float)BOX);
+                        th_new = thl;
+                    }
+                    float tn[6];
+#pragma unroll
+                    for (int l = 0; l < NP; l++) tn[l] = pb_gshfl<G>(th_new, l);
+                    if (METHOD == 0) tn[5] = tn[4];
+                    if (active) {
+                        kk++;
+                        bool conv = ((double)fabsf(th[0] - tn[0]) < a.eps) &&
+                                    ((double)fabsf(th[1] - tn[1]) < a.eps);
+                        if (METHOD == 1)
+                            conv = conv && ((double)fabsf(th[4] - tn[4]) < a.eps) &&
+                                   ((double)fabsf(th[5] - tn[5]) < a.eps);
+#pragma unroll
+                        for (int l = 0; l < 6; l++) th[l] = tn[l];
+                        if (conv) done = true;
+                    }
+                    continue;
+                }
+
+                // ===== CRLB + log-likelihood (gaussmle.py:673-742, 887-954) =====
+                // column factors b in {c1, px, 1, g1}; acc[pair(b, b')] += bb'/model
+                double ac[10];
+#pragma unroll
+                for (int q = 0; q < 10; q++) ac[q] = 0.0;
+                double ll = 0.0;
+                if (g < BOX) {
+                    const double* drow = dspot + g * BOX;
+                    const float* frow = sp + g * BOX;
+#pragma unroll 1
+                    for (int i = 0; i < BOX; i++) {
+                        const double model = fma(fx[F_NPX * BOX + i], PSFy, bg);
+                        const double w = 1.0 / model;
+                        ac[0] = fma(w, fx[F_C1SQ * BOX + i], ac[0]);   // c1 c1
+                        ac[1] = fma(w, fx[F_C1PX * BOX + i], ac[1]);   // c1 px
+                        ac[2] = fma(w, fx[F_C1 * BOX + i], ac[2]);     // c1 1
+                        ac[3] = fma(w, fx[F_C1G1 * BOX + i], ac[3]);   // c1 g1
+                        ac[4] = fma(w, fx[F_PX2 * BOX + i], ac[4]);    // px px
+                        ac[5] = fma(w, fx[F_PX * BOX + i], ac[5]);     // px 1
+                        ac[6] = fma(w, fx[F_G1PX * BOX + i], ac[6]);   // px g1
+                        ac[7] += w;                                    // 1 1
+                        ac[8] = fma(w, fx[F_G1 * BOX + i], ac[8]);     // 1 g1
+                        ac[9] = fma(w, fx[F_G1SQ * BOX + i], ac[9]);   // g1 g1
+                        const float dataf = frow[i];
                         if (model > 0.0) {
                             if (dataf > 0.0f)
-                                ll += (double)dataf * log(model) - model -
-                                      (double)(dataf * logf(dataf)) + (double)dataf;
+                                ll += drow[i] * log(model) - model - (double)(dataf * logf(dataf)) +
+                                      drow[i];
                             else
                                 ll -= model;
                         }
                     }
                 }
-                double* myred = red + lane * kRedStride;
+                // pair index of column-factor kinds: 0 = c1, 1 = px, 2 = one, 3 = g1
+                auto pr = [&](int p, int q) -> double {
+                    const int lo = p < q ? p : q, hi = p < q ? q : p;
+                    return ac[lo * 4 - (lo * (lo - 1)) / 2 + (hi - lo)];
+                };
+                double F[NFISH];
+                if constexpr (METHOD == 1) {
+                    // dudt_k = arow[k] * b_{kind[k]}(i)
+                    const double arow[6] = {NPy, N * cy1, PSFy, 1.0, NPy, N * gy1};
+                    constexpr int kind[6] = {0, 1, 1, 2, 3, 1};
+                    int q = 0;
+#pragma unroll
+                    for (int k = 0; k < 6; k++)
+#pragma unroll
+                        for (int l = k; l < 6; l++) F[q++] = arow[k] * arow[l] * pr(kind[k], kind[l]);
+                } else {
+                    // dudt_4 = N*PSFy*g1(i) + N*gy1*px(i)
+                    const double arow[4] = {NPy, N * cy1, PSFy, 1.0};
+                    constexpr int kind[4] = {0, 1, 1, 2};
+                    const double u = NPy, v = N * gy1;
+                    int q = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+#pragma unroll
+                        for (int l = k; l < 4; l++) F[q++] = arow[k] * arow[l] * pr(kind[k], kind[l]);
+                        F[q++] = arow[k] * (u * pr(kind[k], 3) + v * pr(kind[k], 1));
+                    }
+                    F[q++] = u * u * pr(3, 3) + 2.0 * u * v * pr(3, 1) + v * v * pr(1, 1);
+                }
 #pragma unroll
                 for (int q = 0; q < NFISH; q++) myred[q] = F[q];
                 myred[NFISH] = ll;
                 __syncwarp();
-                const double* gr = red + (grp * G) * kRedStride;
                 for (int q = g; q <= NFISH; q += G) {
                     double s = 0.0;
-#pragma unroll
+#pragma unroll 1
                     for (int r = 0; r < BOX; r++) s += gr[r * kRedStride + q];
                     sums[q] = s;
                 }
@@ -592,7 +646,18 @@ mle_fit_kernel(const MleArgs a) {
                 for (int q = 0; q < NFISH; q++) m[q] = sums[q];
                 const double llsum = sums[NFISH];
                 double dg[NP];
-                bool ok = inv_diag_cholesky<NP>(m, dg);
+                // np.linalg.pinv drops singular values below 1e-15 * max: a tiny
+                // diagonal entry means a (numerically) null direction -> fallback
+                double dmin = INFINITY, dmax = 0.0;
+                {
+                    int q = 0;
+#pragma unroll
+                    for (int k = 0; k < NP; k++) {
+                        dmin = fmin(dmin, m[q]); dmax = fmax(dmax, m[q]);
+                        q += NP - k;
+                    }
+                }
+                bool ok = (dmin > 1e-13 * dmax) && inv_diag_cholesky<NP>(m, dg);
                 if (!ok) {
                     st_flags |= 2;
                     double Mfull[NP * NP];
@@ -623,7 +688,8 @@ mle_fit_kernel(const MleArgs a) {
                     if (g == 7) a.iterations[spot_idx] = kk;
                     if (a.status != nullptr && g == 0) a.status[spot_idx] = st_flags;
                 }
-            }
+                break;
+            }   // iteration / CRLB loop
         }   // sub
         __syncwarp();   // everyone is done reading this stage before it is refilled
         cur_tma = next_tma;

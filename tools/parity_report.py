@@ -26,7 +26,9 @@ def report(n, box, method, seed=0):
         "rms_rel_photons_bg": np.sqrt(((d[:, 2:4] / oth[:, 2:4]) ** 2).mean(0)).tolist(),
         "max_abs_same_iter": np.abs(d[same]).max(0).tolist(),
         "theta_bit_identical_rows": float((th.view(np.uint32) == oth.view(np.uint32)).all(1).mean()),
-        "crlb_max_rel_same_iter": float(np.nanmax(np.abs(cr[same] - ocr[same]) / np.abs(ocr[same]))),
+        "crlb_max_rel_same_iter": float(np.nanmax((np.abs(cr - ocr) / np.where(ocr != 0, np.abs(ocr), np.nan))[same])),
+        "crlb_zero_pattern_equal": bool((((cr == 0) == (ocr == 0))[same]).all()),
+        "n_singular_fisher": int((ocr == 0).any(1).sum()),
         "loglik_max_abs_same_iter": float(np.abs(ll[same] - oll[same]).max()),
     }
     return out
