@@ -1,0 +1,104 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: index sharding, the single
+all-gather of packed fit outputs, variable-length gathers and the image all-reduce.
+The per-rank compute is the CPU oracle here (test infrastructure); on B200 it is the CUDA
+library -- the plumbing is backend-agnostic."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from picasso_b200 import distributed as pbd
+    from picasso_b200 import testing
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        spots = testing.synthetic_spots(1001, 7, seed=4)     # odd count: uneven shards
+        fit = lambda s: oracle.gaussmle(s, 0.001, 100, "sigmaxy")
+        th, cr, ll, it = pbd.sharded_fit(dist, torch, spots, fit)
+        # variable-length gather: each rank identifies its share of frames
+        movie = testing.synthetic_movie(6, 48, 48, emitters_per_frame=4, seed=9)
+        lo, hi = pbd.my_shard(len(movie), rank, world)
+        fr, x, y, ng = oracle.identify_movie(movie[lo:hi], 3000, 7)
+        fr = fr + lo
+        g = pbd.all_gather_variable(dist, torch, (fr, x, y, ng))
+        # image all-reduce: render shards of the localisations
+        rng = np.random.default_rng(1)
+        locs = {"x": rng.uniform(0, 16, 500).astype(np.float32),
+                "y": rng.uniform(0, 16, 500).astype(np.float32),
+                "lpx": np.full(500, 0.1, np.float32), "lpy": np.full(500, 0.1, np.float32)}
+        info = [{"Height": 16, "Width": 16, "Pixelsize": 100}]
+        lo, hi = pbd.my_shard(500, rank, world)
+        part = {k: v[lo:hi] for k, v in locs.items()}
+        n_part, img = oracle.render(part, info, oversampling=4, blur_method="gaussian")
+        img = pbd.all_reduce_image(dist, torch, img)
+        if rank == 0:
+            q.put((th, cr, ll, it, g, img))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_plumbing(oracle):
+    import torch.multiprocessing as mp
+
+    from picasso_b200 import testing
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    th, cr, ll, it, g, img = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    spots = testing.synthetic_spots(1001, 7, seed=4)
+    oth, ocr, oll, oit = oracle.gaussmle(spots, 0.001, 100, "sigmaxy")
+    np.testing.assert_array_equal(th, oth)
+    np.testing.assert_array_equal(cr, ocr)
+    np.testing.assert_array_equal(ll, oll)
+    np.testing.assert_array_equal(it, oit)
+    movie = testing.synthetic_movie(6, 48, 48, emitters_per_frame=4, seed=9)
+    fr, x, y, ng = oracle.identify_movie(movie, 3000, 7)
+    np.testing.assert_array_equal(g[0], fr)
+    np.testing.assert_array_equal(g[1], x)
+    np.testing.assert_array_equal(g[3], ng)
+    rng = np.random.default_rng(1)
+    locs = {"x": rng.uniform(0, 16, 500).astype(np.float32),
+            "y": rng.uniform(0, 16, 500).astype(np.float32),
+            "lpx": np.full(500, 0.1, np.float32), "lpy": np.full(500, 0.1, np.float32)}
+    n_all, ref = oracle.render(locs, [{"Height": 16, "Width": 16, "Pixelsize": 100}],
+                               oversampling=4, blur_method="gaussian")
+    np.testing.assert_allclose(img, ref, rtol=1e-5, atol=1e-7)
+
+
+def test_shard_bounds():
+    from picasso_b200 import distributed as pbd
+
+    assert pbd.shard_bounds(10, 4) == [0, 2, 5, 7, 10]
+    assert pbd.shard_bounds(0, 3) == [0, 0, 0, 0]
+    for n in (1, 7, 1000, 10_000_001):
+        b = pbd.shard_bounds(n, 8)
+        assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(8))
+        assert max(b[i + 1] - b[i] for i in range(8)) - min(b[i + 1] - b[i] for i in range(8)) <= 1
