@@ -61,7 +61,7 @@ struct MleArgs {
     int* status;          // (n,) nullable
 };
 
-constexpr int kNFx = 13;          // per-column x-factors kept in shared memory
+constexpr int kNFx = 14;          // per-column x-factors kept in shared memory (12 used)
 
 template <int BOX, int G>
 struct MleSmem {
@@ -69,7 +69,7 @@ struct MleSmem {
     static constexpr int PIX = BOX * BOX;
     static constexpr int kRoiBytes = 2 * kTileSpots * PIX * 4;          // 2 TMA stages (f32)
     static constexpr int kDataBytes = ((S * PIX * 8 + 15) / 16) * 16;    // current spots as f64
-    static constexpr int kFxBytes = S * kNFx * BOX * 8;
+    static constexpr int kFxBytes = ((S * kNFx * BOX * 8 + 15) / 16) * 16;
     static constexpr int kRedBytes = 32 * kRedStride * 8;
     static constexpr int kSumBytes = S * 24 * 8;
     static constexpr int kBarBytes = 16;
@@ -450,18 +450,19 @@ mle_fit_kernel(const MleArgs a) {
                     }
                     __syncwarp();   // previous readers of fx are done
                     if (g < BOX) {
-                        fx[F_NPX * BOX + g] = (double)th[2] * PSFx;
-                        fx[F_PX * BOX + g] = PSFx;
-                        fx[F_C1 * BOX + g] = cx1;
-                        fx[F_C2 * BOX + g] = cx2;
-                        fx[F_G1 * BOX + g] = gx1;
-                        fx[F_G2 * BOX + g] = gx2;
-                        fx[F_PX2 * BOX + g] = PSFx * PSFx;
-                        fx[F_C1SQ * BOX + g] = cx1 * cx1;
-                        fx[F_G1SQ * BOX + g] = gx1 * gx1;
-                        fx[F_G1PX * BOX + g] = gx1 * PSFx;
-                        fx[F_C1PX * BOX + g] = cx1 * PSFx;
-                        fx[F_C1G1 * BOX + g] = cx1 * gx1;
+                        double* c = fx + g * kNFx;
+                        c[F_NPX] = (double)th[2] * PSFx;
+                        c[F_PX] = PSFx;
+                        c[F_C1] = cx1;
+                        c[F_C2] = cx2;
+                        c[F_G1] = gx1;
+                        c[F_G2] = gx2;
+                        c[F_PX2] = PSFx * PSFx;
+                        c[F_C1SQ] = cx1 * cx1;
+                        c[F_G1SQ] = gx1 * gx1;
+                        c[F_G1PX] = gx1 * PSFx;
+                        c[F_C1PX] = cx1 * PSFx;
+                        c[F_C1G1] = cx1 * gx1;
                     }
                     __syncwarp();
                 }
@@ -478,27 +479,38 @@ mle_fit_kernel(const MleArgs a) {
                     double d0 = 0, dpx2 = 0, dc1 = 0, dg1 = 0, dgp = 0;
                     if (g < BOX) {
                         const double* drow = dspot + g * BOX;
+                        const double2* col = reinterpret_cast<const double2*>(fx);
                         PB_PIX_UNROLL
-                        for (int i = 0; i < BOX; i++) {
-                            const double model = fma(fx[F_NPX * BOX + i], PSFy, bg);
-                            double cf = 0.0, df = 0.0;
-                            if (model > 10e-3) {
-                                const double inv = fast_rcp(model);
-                                const double t = drow[i] * inv;
-                                cf = fmin(t - 1.0, 10e4);
-                                df = fmin(t * inv, 10e4);
-                            }
+                        for (int i = 0; i < BOX; i++, col += kNFx / 2) {
+                            const double2 f0 = col[0];   // N*px, px
+                            const double2 f1 = col[1];   // c1, c2
+                            const double2 f2 = col[2];   // g1, g2
+                            const double2 f3 = col[3];   // px^2, c1^2
+                            const double2 f4 = col[4];   // g1^2, g1*px
+                            const double model = fma(f0.x, PSFy, bg);
+                            // branch-free guards (gaussmle.py:829-835): model > 0.01, cf/df <= 1e5
+                            // (NaN/inf from a non-positive model are discarded by okm;
+                            //  '>' selects instead of fmin keep ptxas from emitting the
+                            //  NaN-aware DSETP.MIN sequences)
+                            const bool okm = model > 10e-3;
+                            const double inv = fast_rcp(model);
+                            const double t = drow[i] * inv;
+                            double cf = t - 1.0, df = t * inv;
+                            cf = cf > 10e4 ? 10e4 : cf;
+                            df = df > 10e4 ? 10e4 : df;
+                            cf = okm ? cf : 0.0;
+                            df = okm ? df : 0.0;
                             c0 += cf;
-                            cpx = fma(cf, fx[F_PX * BOX + i], cpx);
-                            cc1 = fma(cf, fx[F_C1 * BOX + i], cc1);
-                            cc2 = fma(cf, fx[F_C2 * BOX + i], cc2);
-                            cg1 = fma(cf, fx[F_G1 * BOX + i], cg1);
-                            cg2 = fma(cf, fx[F_G2 * BOX + i], cg2);
+                            cpx = fma(cf, f0.y, cpx);
+                            cc1 = fma(cf, f1.x, cc1);
+                            cc2 = fma(cf, f1.y, cc2);
+                            cg1 = fma(cf, f2.x, cg1);
+                            cg2 = fma(cf, f2.y, cg2);
                             d0 += df;
-                            dpx2 = fma(df, fx[F_PX2 * BOX + i], dpx2);
-                            dc1 = fma(df, fx[F_C1SQ * BOX + i], dc1);
-                            dg1 = fma(df, fx[F_G1SQ * BOX + i], dg1);
-                            if constexpr (METHOD == 0) dgp = fma(df, fx[F_G1PX * BOX + i], dgp);
+                            dpx2 = fma(df, f3.x, dpx2);
+                            dc1 = fma(df, f3.y, dc1);
+                            dg1 = fma(df, f4.x, dg1);
+                            if constexpr (METHOD == 0) dgp = fma(df, f4.y, dgp);
                         }
                     }
                     const double Ncy1 = N * cy1, Ncy2 = N * cy2;
@@ -579,18 +591,19 @@ mle_fit_kernel(const MleArgs a) {
                     const float* frow = sp + g * BOX;
 #pragma unroll 1
                     for (int i = 0; i < BOX; i++) {
-                        const double model = fma(fx[F_NPX * BOX + i], PSFy, bg);
+                        const double* c = fx + i * kNFx;
+                        const double model = fma(c[F_NPX], PSFy, bg);
                         const double w = 1.0 / model;
-                        ac[0] = fma(w, fx[F_C1SQ * BOX + i], ac[0]);   // c1 c1
-                        ac[1] = fma(w, fx[F_C1PX * BOX + i], ac[1]);   // c1 px
-                        ac[2] = fma(w, fx[F_C1 * BOX + i], ac[2]);     // c1 1
-                        ac[3] = fma(w, fx[F_C1G1 * BOX + i], ac[3]);   // c1 g1
-                        ac[4] = fma(w, fx[F_PX2 * BOX + i], ac[4]);    // px px
-                        ac[5] = fma(w, fx[F_PX * BOX + i], ac[5]);     // px 1
-                        ac[6] = fma(w, fx[F_G1PX * BOX + i], ac[6]);   // px g1
-                        ac[7] += w;                                    // 1 1
-                        ac[8] = fma(w, fx[F_G1 * BOX + i], ac[8]);     // 1 g1
-                        ac[9] = fma(w, fx[F_G1SQ * BOX + i], ac[9]);   // g1 g1
+                        ac[0] = fma(w, c[F_C1SQ], ac[0]);   // c1 c1
+                        ac[1] = fma(w, c[F_C1PX], ac[1]);   // c1 px
+                        ac[2] = fma(w, c[F_C1], ac[2]);     // c1 1
+                        ac[3] = fma(w, c[F_C1G1], ac[3]);   // c1 g1
+                        ac[4] = fma(w, c[F_PX2], ac[4]);    // px px
+                        ac[5] = fma(w, c[F_PX], ac[5]);     // px 1
+                        ac[6] = fma(w, c[F_G1PX], ac[6]);   // px g1
+                        ac[7] += w;                         // 1 1
+                        ac[8] = fma(w, c[F_G1], ac[8]);     // 1 g1
+                        ac[9] = fma(w, c[F_G1SQ], ac[9]);   // g1 g1
                         const float dataf = frow[i];
                         if (model > 0.0) {
                             if (dataf > 0.0f)

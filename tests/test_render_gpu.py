@@ -95,7 +95,7 @@ def test_render_api_contract():
         pbrender.render(locs, info, disp_px_size=25, blur_method="nope")
     with pytest.raises(KeyError):
         pbrender.render(locs, [{"Height": 8, "Width": 8}], disp_px_size=25)
-    with pytest.raises(ValueError):
+    with pytest.raises(KeyError):      # dict info without a viewport: info[0] fails like the reference
         pbrender.render(locs, {"Pixelsize": 100}, disp_px_size=25)
     # empty locs
     n0, img0 = pbrender.render(locs.iloc[:0], info, disp_px_size=25, blur_method="gaussian")

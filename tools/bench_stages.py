@@ -1,0 +1,267 @@
+"""Stage measurements for the non-headline BASELINE.json configs (3: identify + get_spots +
+gausslq end to end; 4: render 50 M localisations; 5: RCC cross-correlation), one JSON line
+each, with the HBM roofline of the dominant kernel.  Run on the GPU box:
+
+    python tools/bench_stages.py [identify] [render] [rcc] [--small]
+
+Numbers are kept under profiles/.  (bench.py remains the headline MLE metric.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def ev_time(torch, fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def gen_movie_device(torch, F, Y, X, per_frame=60, seed=1, dev="cuda"):
+    """Config 3 movie on the device: 100 + Poisson(20 + emitters), uint16."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    movie = torch.empty((F, Y, X), dtype=torch.int16, device=dev)
+    r = 5
+    oy, ox = torch.meshgrid(torch.arange(-r, r + 1, device=dev), torch.arange(-r, r + 1, device=dev),
+                            indexing="ij")
+    step = 100
+    for f0 in range(0, F, step):
+        nf = min(step, F - f0)
+        mu = torch.full((nf, Y, X), 20.0, device=dev)
+        n = nf * per_frame
+        fx = 8 + (X - 16) * torch.rand(n, generator=g, device=dev)
+        fy = 8 + (Y - 16) * torch.rand(n, generator=g, device=dev)
+        ff = torch.arange(nf, device=dev).repeat_interleave(per_frame)
+        cx, cy = fx.floor().long(), fy.floor().long()
+        px = cx[:, None, None] + ox[None]
+        py = cy[:, None, None] + oy[None]
+        val = 2000.0 * torch.exp(-0.5 * (((px - fx[:, None, None]) / 1.1) ** 2 +
+                                         ((py - fy[:, None, None]) / 1.1) ** 2))
+        idx = (ff[:, None, None] * Y + py) * X + px
+        mu.view(-1).index_add_(0, idx.reshape(-1), val.reshape(-1))
+        movie[f0:f0 + nf] = (100 + torch.poisson(mu, generator=g)).clamp_(0, 65535).to(torch.int32).to(torch.int16)
+    return movie.view(torch.uint16)
+
+
+def stage_identify(torch, small):
+    from picasso_b200 import _lib, gausslq, localize
+
+    lib = _lib.load()
+    localize._declare(lib)
+    vp = C.c_void_p
+    lib.pb_identify_dev.argtypes = [vp, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_longlong, C.c_int,
+                                    C.c_double, vp, vp, vp, vp, vp, C.c_size_t, vp, vp]
+    lib.pb_identify_dev.restype = C.c_int
+    F, Y, X = (200, 512, 512) if small else (2000, 512, 512)
+    movie = gen_movie_device(torch, F, Y, X)
+    cap = F * 256
+    fr = torch.empty(cap, dtype=torch.int64, device="cuda"); xs = torch.empty_like(fr); ys = torch.empty_like(fr)
+    ng = torch.empty(cap, dtype=torch.float32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        cnt.zero_()
+        rc = lib.pb_identify_dev(movie.data_ptr(), 0, F, Y, X, 0, 7, 5000.0, None, fr.data_ptr(),
+                                 xs.data_ptr(), ys.data_ptr(), ng.data_ptr(), cap, cnt.data_ptr(), st)
+        assert rc == 0
+    ms = ev_time(torch, run)
+    n_found = int(cnt.item())
+    bytes_alg = F * Y * X * 2 + n_found * 28
+    ach = bytes_alg / (ms * 1e-3) / 1e9
+    # end to end through the Python API with a host movie (H2D inside), incl. get_spots + LQ
+    hmovie = movie.cpu().numpy()
+    cam = {"Baseline": 100, "Sensitivity": 1.0, "Gain": 1, "Pixelsize": 130}
+    localize.identify(hmovie[:8], 5000, 7, return_info=False)
+    t0 = time.perf_counter()
+    ids = localize.identify(hmovie, 5000, 7, return_info=False)
+    t1 = time.perf_counter()
+    spots = localize.get_spots(hmovie, ids, 7, cam)
+    t2 = time.perf_counter()
+    theta = gausslq.fit_spots(spots)
+    t3 = time.perf_counter()
+    # CPU oracle on a bounded sample
+    import oracle
+    oracle.build()
+    nf_cpu = 16
+    t4 = time.perf_counter()
+    ofr, ox, oy, ong = oracle.identify_movie(hmovie[:nf_cpu], 5000, 7)
+    t5 = time.perf_counter()
+    ns = min(len(spots), 20000)
+    oracle.fit_spots_lq(spots[:ns], nthreads=os.cpu_count())
+    t6 = time.perf_counter()
+    sel = ids["frame"].to_numpy() < nf_cpu
+    same = (np.array_equal(ids["x"].to_numpy()[sel], ox) and np.array_equal(ids["y"].to_numpy()[sel], oy))
+    print(json.dumps({
+        "stage": "identify+get_spots+gausslq (config 3)", "movie": [F, Y, X], "n_identified": n_found,
+        "identify_kernel_ms": ms, "identify_fps": F / (ms * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks(), "unit": "GB/s",
+                     "frac": ach / peaks(), "algorithmic_bytes": bytes_alg},
+        "e2e_seconds": {"identify_host_movie": t1 - t0, "get_spots": t2 - t1, "gausslq": t3 - t2,
+                        "total": t3 - t0},
+        "e2e_fps": F / (t3 - t0), "lq_fits_per_s_e2e": len(spots) / (t3 - t2),
+        "cpu_oracle": {"identify_fps_1thread": nf_cpu / (t5 - t4),
+                       "lq_fits_per_s_allcores": ns / (t6 - t5), "cores": os.cpu_count()},
+        "identifications_match_oracle_sample": bool(same)}), flush=True)
+    # LQ kernel alone, device resident
+    lib.pb_lq_fit_dev.argtypes = [C.c_size_t, C.c_int, vp, vp, vp, vp, vp]
+    dsp = torch.from_numpy(spots).cuda()
+    dth = torch.empty((len(spots), 6), device="cuda")
+    ms_lq = ev_time(torch, lambda: lib.pb_lq_fit_dev(len(spots), 7, dsp.data_ptr(), dth.data_ptr(),
+                                                    None, None, st))
+    print(json.dumps({"stage": "gausslq kernel (device resident)", "n": len(spots), "ms": ms_lq,
+                      "fits_per_s": len(spots) / (ms_lq * 1e-3)}), flush=True)
+
+
+def stage_render(torch, small):
+    from picasso_b200 import _lib, render as pbrender
+
+    lib = _lib.load()
+    pbrender._declare(lib)
+    n = 5_000_000 if small else 50_000_000
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    x = 512 * torch.rand(n, generator=g, device="cuda")
+    y = 512 * torch.rand(n, generator=g, device="cuda")
+    lpx = 0.02 + 0.06 * torch.rand(n, generator=g, device="cuda")
+    lpy = 0.02 + 0.06 * torch.rand(n, generator=g, device="cuda")
+    npx = 10240
+    img = torch.empty((npx, npx), device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    wsb = lib.pb_render_workspace_bytes(n, npx, npx)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    out = {"stage": "render (config 4)", "n_locs": n, "image": [npx, npx]}
+    for name, mode, use_ws in (("hist", 0, True), ("gaussian_tiled", 1, True), ("gaussian_direct", 1, False)):
+        def run():
+            rc = lib.pb_render_dev(n, x.data_ptr(), y.data_ptr(), lpx.data_ptr(), lpy.data_ptr(), 20.0,
+                                   0.0, 0.0, 512.0, 512.0, 0.0, mode, img.data_ptr(), npx, npx,
+                                   cnt.data_ptr(), ws.data_ptr() if use_ws else None,
+                                   wsb if use_ws else 0, st)
+            assert rc == 0
+        ms = ev_time(torch, run, warm=1, reps=3)
+        alg = n * (16 if mode else 8) + npx * npx * 4
+        out[name] = {"ms": ms, "locs_per_s": n / (ms * 1e-3), "achieved_GBs": alg / (ms * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peaks(), "algorithmic_bytes": alg}
+    # end to end through the Python API (host arrays in, host image out)
+    import pandas as pd
+    import warnings
+    m = min(n, 10_000_000)
+    locs = pd.DataFrame({"x": x[:m].cpu().numpy(), "y": y[:m].cpu().numpy(),
+                         "lpx": lpx[:m].cpu().numpy(), "lpy": lpy[:m].cpu().numpy()})
+    info = [{"Height": 512, "Width": 512, "Frames": 1, "Pixelsize": 130}]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pbrender.render(locs.iloc[:1000], info, oversampling=20, blur_method="gaussian")
+        t0 = time.perf_counter()
+        k, image = pbrender.render(locs, info, oversampling=20, blur_method="gaussian")
+        t1 = time.perf_counter()
+    out["e2e_python_api"] = {"n_locs": m, "seconds": t1 - t0, "locs_per_s": m / (t1 - t0)}
+    import oracle
+    oracle.build()
+    mc = 1_000_000
+    sub = {k_: v.to_numpy()[:mc] for k_, v in locs.items()}
+    t0 = time.perf_counter()
+    kc, oimg = oracle.render(sub, info, oversampling=20, blur_method="gaussian")
+    t1 = time.perf_counter()
+    out["cpu_oracle"] = {"n_locs": mc, "locs_per_s_1thread": mc / (t1 - t0)}
+    # parity of the sub-sample
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kg, gimg = pbrender.render(locs.iloc[:mc], info, oversampling=20, blur_method="gaussian")
+    big = oimg > 1e-3 * oimg.max()
+    out["parity_vs_oracle_1M"] = {"n_equal": kg == kc,
+                                  "max_rel_on_bright_pixels": float(np.max(np.abs(gimg[big] - oimg[big]) / oimg[big]))}
+    print(json.dumps(out), flush=True)
+
+
+def stage_rcc(torch, small):
+    from picasso_b200 import _lib, imageprocess
+
+    lib = _lib.load()
+    imageprocess._declare(lib)
+    vp = C.c_void_p
+    lib.pb_rcc_spectra_dev.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.pb_rcc_windows_dev.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, vp, C.c_int, vp, C.c_size_t, vp]
+    n_seg, Y, X = (40, 2048, 2048) if small else (200, 4096, 4096)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    seg = torch.zeros((n_seg, Y, X), device="cuda")
+    # sparse blobs shifted a little per segment
+    npts = 20000
+    py = torch.randint(16, Y - 16, (npts,), generator=g, device="cuda")
+    px = torch.randint(16, X - 16, (npts,), generator=g, device="cuda")
+    for s in range(n_seg):
+        sy, sx = int(round(3 * math.sin(s / 7))), int(round(s / 20))
+        seg[s].index_put_((py + sy, px + sx), torch.ones(npts, device="cuda"), accumulate=True)
+    spec = torch.empty((n_seg, Y, X // 2 + 1, 2), device="cuda")
+    sums = torch.empty(n_seg, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    t_spec = ev_time(torch, lambda: lib.pb_rcc_spectra_dev(n_seg, Y, X, seg.data_ptr(), spec.data_ptr(),
+                                                          sums.data_ptr(), st), warm=1, reps=2)
+    pi, pj = np.triu_indices(n_seg, 1)
+    n_pairs = len(pi)
+    dpi = torch.from_numpy(pi.astype(np.int32)).cuda(); dpj = torch.from_numpy(pj.astype(np.int32)).cuda()
+    batch = 8
+    wsb = batch * (Y * (X // 2 + 1) * 8 + Y * X * 4)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    H = W = 32
+    win = torch.empty((n_pairs, H, W), device="cuda")
+    Y0, X0 = (Y - 32) // 2, (X - 32) // 2
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rc = lib.pb_rcc_windows_dev(n_pairs, dpi.data_ptr(), dpj.data_ptr(), Y, X, spec.data_ptr(), Y0, X0, H, W,
+                                win.data_ptr(), batch, ws.data_ptr(), wsb, st)
+    torch.cuda.synchronize()
+    t_pairs = time.perf_counter() - t0
+    assert rc == 0
+    traffic = n_pairs * (3 * Y * (X // 2 + 1) * 8 + 2 * Y * X * 4)   # mul: 2 reads + 1 write; C2R: >= 1 read + 1 write
+    # CPU: numpy xcorr for one pair (f64, pocketfft)
+    a = seg[0].cpu().numpy().astype(np.float64); b = seg[1].cpu().numpy().astype(np.float64)
+    t0 = time.perf_counter()
+    xc = np.fft.fftshift(np.real(np.fft.ifft2(np.fft.fft2(a) * np.conj(np.fft.fft2(b))))) / np.sqrt(a.size)
+    t_cpu = time.perf_counter() - t0
+    gwin = win[0].cpu().numpy()
+    ref = xc[Y0:Y0 + 32, X0:X0 + 32]
+    print(json.dumps({
+        "stage": "rcc (config 5)", "n_seg": n_seg, "image": [Y, X], "n_pairs": n_pairs,
+        "forward_r2c_all_segments_ms": t_spec, "all_pairs_seconds": t_pairs,
+        "pairs_per_s": n_pairs / t_pairs,
+        "roofline": {"bound": "hbm", "achieved": traffic / t_pairs / 1e9, "peak": peaks(), "unit": "GB/s",
+                     "frac": traffic / t_pairs / 1e9 / peaks(),
+                     "note": "minimum traffic of multiply + C2R passes; cuFFT does more than one pass"},
+        "cpu_numpy_xcorr_one_pair_s": t_cpu, "cpu_all_pairs_extrapolated_h": t_cpu * n_pairs / 3600,
+        "window_max_abs_err_vs_numpy_f64": float(np.abs(gwin - ref).max()),
+        "window_peak": float(ref.max())}), flush=True)
+
+
+if __name__ == "__main__":
+    import torch
+
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    small = "--small" in sys.argv
+    which = args or ["identify", "render", "rcc"]
+    for w in which:
+        {"identify": stage_identify, "render": stage_render, "rcc": stage_rcc}[w](torch, small)

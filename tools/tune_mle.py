@@ -16,7 +16,7 @@ CSRC = os.path.join(ROOT, "picasso_b200", "csrc")
 NVCC = "/usr/local/cuda/bin/nvcc"
 
 VARIANTS = {}
-for minb, unroll in itertools.product((3, 4, 5), (1, 8)):
+for minb, unroll in itertools.product((4, 5), (1, 8)):
     VARIANTS[f"b{minb}_u{unroll}"] = [f"-DPB_MLE_MINB={minb}", f"-DPB_MLE_PIX_UNROLL={unroll}"]
 
 
