@@ -43,6 +43,9 @@ EPS = 0.001
 MAX_IT = 100
 METHOD = "sigmaxy"
 BYTES_PER_SPOT = BOX * BOX * 4 + 56   # 196 B ROI read + 56 B results written
+# dram__bytes_read.sum + dram__bytes_write.sum of mle_fit_kernel<7,8,1> for 1 M spots from the
+# committed `ncu --set full` capture (profiles/r01_mle_ncu.md): 197.5 MB + 41.1 MB
+NCU_DRAM_BYTES_PER_SPOT = 238.6
 
 
 def parse():
@@ -122,6 +125,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cpu_info():
+    """Threads the CPU arm can really use: affinity mask and cgroup quota, not just cpu_count."""
+    n = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = n
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    usable = aff if quota is None else max(1, min(aff, int(math.ceil(quota))))
+    return {"cpu_count": n, "affinity": aff, "cgroup_quota_cpus": quota, "threads_used": usable}
+
+
 def cpu_oracle_rate(seconds: float, threads: int):
     """Time the CPU oracle on a bounded sample of the same workload."""
     import oracle
@@ -145,7 +166,8 @@ def run_reference(args, rank, world):
     """--impl reference: the reference algorithm on the host CPU (oracle port)."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    cpu = host_cpu_info()
+    threads = cpu["threads_used"]
     per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     rates, n_done, t_tot = [], 0, 0.0
     for i in range(args.warmup + args.steps):
@@ -164,6 +186,7 @@ def run_reference(args, rank, world):
         "config": {"workload": "configs[1]: 7x7 MLE sigmaxy eps=1e-3 max_it=100 (bounded CPU sample)",
                    "box": BOX, "method": METHOD},
         "cpu_baseline": {"value": value, "unit": "fits/s", "cores": threads, "kind": "port",
+                         "host": cpu,
                          "sample": f"{n_done} spots in {t_tot:.1f} s, oracle C port of "
                                    "picasso.gaussmle._mlefit_sigmaxy (bit-identical to the numba "
                                    "reference), pthreads"},
@@ -333,7 +356,9 @@ def main():
                                       + ("; one NCCL all-gather of the packed outputs per step"
                                          if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_SPOT * n,
+                         "traffic_source": "ncu --set full, profiles/r01_mle_ncu.md (bytes/spot x spots per launch)",
+                         "algorithmic_bytes": BYTES_PER_SPOT * n, "peak_source": peak_src,
                          "kernel_ms": ms_kernel,
                          "note": "algorithmic 252 B/spot; the fit is FP64-issue bound, not HBM bound "
                                  "(SURVEY.md 8d) -- see DESIGN.md for the instruction roofline"},
@@ -342,10 +367,11 @@ def main():
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu:
-            threads = os.cpu_count() or 1
+            cpu = host_cpu_info()
+            threads = cpu["threads_used"]
             r, d, el = cpu_oracle_rate(args.cpu_seconds, threads)
             line["cpu_baseline"] = {
-                "value": r, "unit": "fits/s", "cores": threads, "kind": "port",
+                "value": r, "unit": "fits/s", "cores": threads, "kind": "port", "host": cpu,
                 "sample": f"{d} spots in {el:.1f} s (same distribution), oracle C port of "
                           "picasso.gaussmle._mlefit_sigmaxy, bit-identical to the numba reference"}
         print(json.dumps(line), flush=True)

@@ -120,6 +120,15 @@ int pb_get_spots_dev(const void* d_movie, int dtype, size_t n_frames, int Y, int
                      const long long* d_x, const long long* d_y, int box, float baseline,
                      float sensitivity, float gain, float* d_spots, void* stream);
 
+/* Fused identify + get_spots over a host movie chunk (one upload): the end-to-end
+ * localize path, localize.py:1787-1811 (identify -> fit2D -> get_spots).  Outputs as
+ * pb_identify (sorted by frame, y, x) plus spots (capacity, box, box) float32. */
+int pb_identify_get_spots(const void* movie, int dtype, size_t n_frames, int Y, int X,
+                          long long frame_offset, int box, double min_ng, const int* roi,
+                          float baseline, float sensitivity, float gain, long long* frame,
+                          long long* x, long long* y, float* ng, float* spots, size_t capacity,
+                          size_t* n_found);
+
 /* ---- least-squares Gaussian fit --------------------------------------------
  * Replaces picasso.gausslq.fit_spot / fit_spots / fit_spots_parallel
  * (picasso/gausslq.py:206-343: scipy.optimize.leastsq == MINPACK lmdif with

@@ -31,8 +31,12 @@ extern std::atomic<long long> g_pb_launches;
 
 namespace {
 
-constexpr int kTY = 32;     // output rows per tile
 constexpr int kTX = 128;    // output columns per tile == threads per CTA
+// output rows per tile: chosen so that kTY + 2h is a multiple of the ring period 2h+1
+// (the column walk is unrolled by exactly one period -> compact loop body, I-cache friendly)
+__host__ __device__ constexpr int tile_rows(int h) {
+    return h == 1 ? 34 : h == 2 ? 36 : h == 3 ? 36 : h == 4 ? 37 : h == 5 ? 34 : h == 6 ? 40 : 31;
+}
 constexpr int kHP = 8;      // column halo in shared memory (>= h+1, keeps 16 B alignment)
 
 struct IdArgs {
@@ -69,6 +73,9 @@ __device__ __forceinline__ T pmax(T a, T b) { return a > b ? a : b; }
 template <typename T, int H>
 __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
     constexpr int BOX = 2 * H + 1;
+    constexpr int kTY = tile_rows(H);
+    constexpr int P = 2 * H + 1;            // ring period of the column walk
+    static_assert((kTY + 2 * H) % P == 0 && kTY <= 64, "tile height must fit the ring period");
     constexpr int ROWS = kTY + 2 * H + 2;   // window halo H + gradient halo 1
     constexpr int COLS = kTX + 2 * kHP;
     static_assert(H + 1 <= kHP, "halo too small");
@@ -123,48 +130,48 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
     // scan range of the reference: i in [H, Ys-H-1), j in [H, Xs-H-1)
     const bool col_ok = (j >= H) && (j < a.Xs - H - 1);
 
-    // rolling state: row-window maxima of the last 2H+1 rows; centre/left/right
-    // of the last H+1 rows
-    T rm[2 * H + 1], cc[H + 1], ll[H + 1], rr[H + 1];
-    unsigned candmask = 0;   // bit u set: (ty0 + u, j) is a local maximum
+    // rolling state in register rings of period P = 2H+1: row-window maximum, centre,
+    // left-part and right-part maxima of the last P rows (slot = tile row mod P)
+    T rm[P], cc[P], ll[P], rr[P];
+    unsigned long long candmask = 0;   // bit u set: (ty0 + u, j) is a local maximum
 #pragma unroll
-    for (int k = 0; k < 2 * H + 1; k++) rm[k] = T(0);
-#pragma unroll
-    for (int k = 0; k < H + 1; k++) { cc[k] = T(0); ll[k] = T(0); rr[k] = T(0); }
+    for (int k = 0; k < P; k++) { rm[k] = T(0); cc[k] = T(0); ll[k] = T(0); rr[k] = T(0); }
 
+#pragma unroll 1
+    for (int t0 = 0; t0 < kTY + 2 * H; t0 += P) {
 #pragma unroll
-    for (int t = 0; t < kTY + 2 * H; t++) {
-        // tile row t+1 <-> image row ty0 - H + t
-        const T* row = &tile[t + 1][tc];
-        T L = row[-H], R = row[1];
+        for (int k = 0; k < P; k++) {
+            const int t = t0 + k;
+            // tile row t+1 <-> image row ty0 - H + t
+            const T* row = &tile[t + 1][tc];
+            T L = row[-H], R = row[1];
 #pragma unroll
-        for (int k = 1; k < H; k++) { L = pmax(L, row[-H + k]); R = pmax(R, row[1 + k]); }
-        const T Cv = row[0];
-        const T RM = pmax(pmax(L, R), Cv);
+            for (int q = 1; q < H; q++) { L = pmax(L, row[-H + q]); R = pmax(R, row[1 + q]); }
+            const T Cv = row[0];
+            rm[k] = pmax(pmax(L, R), Cv);
+            cc[k] = Cv; ll[k] = L; rr[k] = R;
+            // window centre = row t - H (slot k-H), rows above t-2H..t-H-1, below t-H+1..t
+            constexpr int dummy = 0; (void)dummy;
+            T above = rm[(k + 1) % P], below = rm[(k + P - H + 1) % P];
 #pragma unroll
-        for (int k = 0; k < 2 * H; k++) rm[k] = rm[k + 1];
-        rm[2 * H] = RM;
-#pragma unroll
-        for (int k = 0; k < H; k++) { cc[k] = cc[k + 1]; ll[k] = ll[k + 1]; rr[k] = rr[k + 1]; }
-        cc[H] = Cv; ll[H] = L; rr[H] = R;
-        if (t >= 2 * H) {
+            for (int q = 1; q < H; q++) {
+                above = pmax(above, rm[(k + 1 + q) % P]);
+                below = pmax(below, rm[(k + P - H + 1 + q) % P]);
+            }
+            const int cs = (k + P - H) % P;
             const int u = t - 2 * H;             // output row within the tile
             const int i = ty0 + u;               // image row of the window centre
-            // window rows are rm[0..2H]; centre row values are cc[0], ll[0], rr[0]
-            T above = rm[0], below = rm[H + 1];
-#pragma unroll
-            for (int k = 1; k < H; k++) { above = pmax(above, rm[k]); below = pmax(below, rm[H + 1 + k]); }
-            const T c0 = cc[0];
-            const bool is_max = col_ok && (i >= H) && (i < a.Ys - H - 1) && (c0 > above) &&
-                                (c0 > ll[0]) && (c0 >= rr[0]) && (c0 >= below);
-            if (is_max) candmask |= (1u << u);
+            const T c0 = cc[cs];
+            const bool is_max = (u >= 0) && col_ok && (i >= H) && (i < a.Ys - H - 1) &&
+                                (c0 > above) && (c0 > ll[cs]) && (c0 >= rr[cs]) && (c0 >= below);
+            if (is_max) candmask |= (1ull << u);
         }
     }
 
     // ---- net gradient for the (rare) maxima (localize.py:202-244): float32,
     // row-major accumulation, unfused IEEE ops, negative-index wrap-around
     while (candmask) {
-        const int u = __ffs(candmask) - 1;
+        const int u = __ffsll((long long)candmask) - 1;
         candmask &= candmask - 1;
         const int i = ty0 + u;
         float acc = 0.0f;
@@ -204,7 +211,8 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
 template <typename T>
 int launch_identify(const IdArgs& a, int box, cudaStream_t stream) {
     if (a.Ys <= 0 || a.Xs <= 0 || a.n_frames <= 0) return PB_OK;
-    dim3 grid((a.Xs + kTX - 1) / kTX, (a.Ys + kTY - 1) / kTY, 1);
+    const int ty = tile_rows(box / 2);
+    dim3 grid((a.Xs + kTX - 1) / kTX, (a.Ys + ty - 1) / ty, 1);
     // gridDim.z is limited to 65535: loop over frame batches
     const long long zmax = 32768;
     for (long long f0 = 0; f0 < a.n_frames; f0 += zmax) {
@@ -453,5 +461,117 @@ extern "C" int pb_get_spots(const void* movie, int dtype, size_t n_frames, int Y
     PB_CUDA_CHECK(cudaMemcpy(hs.data(), dsp.p, m * pix * 4, cudaMemcpyDeviceToHost));
     for (size_t k = 0; k < m; k++)
         memcpy(spots + sel[k] * pix, hs.data() + k * pix, pix * 4);
+    return PB_OK;
+}
+
+// Fused pass for the end-to-end localize path: every frame chunk is uploaded ONCE, spots
+// are identified and (after the host-side (frame, y, x) sort of the few identifications)
+// their ROIs are cut from the still-resident chunk.  Equivalent to pb_identify followed by
+// pb_get_spots (localize.py:1787-1811 identify -> fit2D -> get_spots) without the second
+// upload of the movie.  `spots` must hold capacity * box * box floats.
+extern "C" int pb_identify_get_spots(const void* movie, int dtype, size_t n_frames, int Y, int X,
+                                     long long frame_offset, int box, double min_ng,
+                                     const int* roi, float baseline, float sensitivity, float gain,
+                                     long long* frame, long long* x, long long* y, float* ng,
+                                     float* spots, size_t capacity, size_t* n_found) {
+    if (!n_found) { pb_set_error("pb_identify_get_spots: n_found is null"); return PB_ERR_INVALID; }
+    *n_found = 0;
+    if (n_frames == 0) return PB_OK;
+    if (!movie) { pb_set_error("pb_identify_get_spots: null movie"); return PB_ERR_INVALID; }
+    const size_t fsz = (size_t)Y * X * dtype_size(dtype);
+    const size_t pix = (size_t)box * box;
+    size_t chunk = std::max<size_t>(1, (128u << 20) / fsz);
+    chunk = std::min(chunk, n_frames);
+    // per-chunk device capacity for identifications (grown on demand)
+    size_t dcap = std::max<size_t>(4096, chunk * 512);
+    DevBuf mv[2], dfr, dx, dy, dng, dcnt, dsp;
+    int rc;
+    for (int s = 0; s < 2; s++) if ((rc = mv[s].alloc(chunk * fsz))) return rc;
+    auto alloc_ids = [&](size_t cap) -> int {
+        DevBuf* bufs[5] = {&dfr, &dx, &dy, &dng, &dsp};
+        for (auto* b : bufs) { if (b->p) cudaFree(b->p); b->p = nullptr; }
+        int r;
+        if ((r = dfr.alloc(cap * 8)) || (r = dx.alloc(cap * 8)) || (r = dy.alloc(cap * 8)) ||
+            (r = dng.alloc(cap * 4)) || (r = dsp.alloc(cap * pix * 4)))
+            return r;
+        return PB_OK;
+    };
+    if ((rc = alloc_ids(dcap)) || (rc = dcnt.alloc(8))) return rc;
+    cudaStream_t st[2];
+    for (int s = 0; s < 2; s++) PB_CUDA_CHECK(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+    auto upload = [&](size_t c) {
+        const size_t f0 = c * chunk;
+        if (f0 >= n_frames) return;
+        const size_t nf = std::min(chunk, n_frames - f0);
+        cudaMemcpyAsync(mv[c & 1].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz,
+                        cudaMemcpyHostToDevice, st[c & 1]);
+    };
+    upload(0);
+    size_t total = 0;
+    bool overflow = false;
+    std::vector<long long> hf, hx, hy;
+    std::vector<float> hn;
+    std::vector<size_t> order;
+    rc = PB_OK;
+    const size_t nchunks = (n_frames + chunk - 1) / chunk;
+    for (size_t c = 0; c < nchunks && rc == PB_OK; c++) {
+        const int s = (int)(c & 1);
+        const size_t f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        unsigned long long found = 0;
+        for (;;) {   // retry loop if the per-chunk device capacity was too small
+            cudaMemsetAsync(dcnt.p, 0, 8, st[s]);
+            rc = pb_identify_dev(mv[s].p, dtype, nf, Y, X, frame_offset + (long long)f0, box, min_ng,
+                                 roi, static_cast<long long*>(dfr.p), static_cast<long long*>(dx.p),
+                                 static_cast<long long*>(dy.p), static_cast<float*>(dng.p), dcap,
+                                 static_cast<unsigned long long*>(dcnt.p), st[s]);
+            if (rc != PB_OK) break;
+            cudaMemcpyAsync(&found, dcnt.p, 8, cudaMemcpyDeviceToHost, st[s]);
+            cudaStreamSynchronize(st[s]);
+            if (found <= dcap) break;
+            dcap = (size_t)found;
+            if ((rc = alloc_ids(dcap))) break;
+        }
+        if (rc != PB_OK) break;
+        upload(c + 1);   // next chunk streams in while this one is post-processed
+        if (total + found > capacity) overflow = true;
+        if (!overflow && found) {
+            hf.resize(found); hx.resize(found); hy.resize(found); hn.resize(found); order.resize(found);
+            cudaMemcpyAsync(hf.data(), dfr.p, found * 8, cudaMemcpyDeviceToHost, st[s]);
+            cudaMemcpyAsync(hx.data(), dx.p, found * 8, cudaMemcpyDeviceToHost, st[s]);
+            cudaMemcpyAsync(hy.data(), dy.p, found * 8, cudaMemcpyDeviceToHost, st[s]);
+            cudaMemcpyAsync(hn.data(), dng.p, found * 4, cudaMemcpyDeviceToHost, st[s]);
+            cudaStreamSynchronize(st[s]);
+            std::iota(order.begin(), order.end(), 0);
+            std::sort(order.begin(), order.end(), [&](size_t p, size_t q) {
+                if (hf[p] != hf[q]) return hf[p] < hf[q];
+                if (hy[p] != hy[q]) return hy[p] < hy[q];
+                return hx[p] < hx[q];
+            });
+            for (size_t k = 0; k < found; k++) {
+                frame[total + k] = hf[order[k]]; x[total + k] = hx[order[k]];
+                y[total + k] = hy[order[k]]; ng[total + k] = hn[order[k]];
+            }
+            cudaMemcpyAsync(dfr.p, frame + total, found * 8, cudaMemcpyHostToDevice, st[s]);
+            cudaMemcpyAsync(dx.p, x + total, found * 8, cudaMemcpyHostToDevice, st[s]);
+            cudaMemcpyAsync(dy.p, y + total, found * 8, cudaMemcpyHostToDevice, st[s]);
+            rc = pb_get_spots_dev(mv[s].p, dtype, nf, Y, X, frame_offset + (long long)f0, found,
+                                  static_cast<long long*>(dfr.p), static_cast<long long*>(dx.p),
+                                  static_cast<long long*>(dy.p), box, baseline, sensitivity, gain,
+                                  static_cast<float*>(dsp.p), st[s]);
+            if (rc != PB_OK) break;
+            cudaMemcpyAsync(spots + total * pix, dsp.p, found * pix * 4, cudaMemcpyDeviceToHost, st[s]);
+            cudaStreamSynchronize(st[s]);
+        }
+        total += found;
+    }
+    for (int s = 0; s < 2; s++) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); }
+    cudaError_t e = cudaGetLastError();
+    if (rc != PB_OK) return rc;
+    if (e != cudaSuccess) { pb_set_error("pb_identify_get_spots: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    *n_found = total;
+    if (overflow) {
+        pb_set_error("pb_identify_get_spots: found %zu spots, capacity %zu", total, capacity);
+        return PB_ERR_CAPACITY;
+    }
     return PB_OK;
 }

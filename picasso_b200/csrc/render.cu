@@ -115,6 +115,7 @@ constexpr int kLanes = 8;     // lanes per localisation in the direct splat kern
 __global__ void render_splat_kernel(const RenderArgs a) {
     const int lane = threadIdx.x & 31;
     const int g = lane & (kLanes - 1);
+    const unsigned gmask = 0xffu << (lane & ~(kLanes - 1));   // the 8 lanes sharing a localisation
     const long long groups = ((long long)gridDim.x * blockDim.x) / kLanes;
     const long long gid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kLanes;
     unsigned long long local = 0;
@@ -128,13 +129,20 @@ __global__ void render_splat_kernel(const RenderArgs a) {
         if (!s.in_view) continue;
         const int nx = s.j_max - s.j_min, ny = s.i_max - s.i_min;
         if (nx <= 0 || ny <= 0) continue;
-        for (int j0 = 0; j0 < nx; j0 += kLanes) {
-            const int j = s.j_min + j0 + g;
-            const bool jok = (j0 + g) < nx;
-            const float gx = jok ? splat_gx(s, j) : 0.0f;
-            for (int i = s.i_min; i < s.i_max; i++) {
-                const float gy = splat_gy(s, i);
-                if (jok) atomicAdd(a.image + (size_t)i * a.npx + j, __fmul_rn(gy, gx));
+        // lane g evaluates ONE column kernel value and ONE row kernel value per 8x8 chunk;
+        // row values are passed around the 8-lane group with shuffles
+        for (int i0 = 0; i0 < ny; i0 += kLanes) {
+            const float gy_mine = (i0 + g < ny) ? splat_gy(s, s.i_min + i0 + g) : 0.0f;
+            const int nr = min(kLanes, ny - i0);
+            for (int j0 = 0; j0 < nx; j0 += kLanes) {
+                const int j = s.j_min + j0 + g;
+                const bool jok = (j0 + g) < nx;
+                const float gx = jok ? splat_gx(s, j) : 0.0f;
+                for (int rr = 0; rr < nr; rr++) {
+                    const float gy = __shfl_sync(gmask, gy_mine, rr, kLanes);
+                    if (jok)
+                        atomicAdd(a.image + (size_t)(s.i_min + i0 + rr) * a.npx + j, __fmul_rn(gy, gx));
+                }
             }
         }
     }
@@ -233,23 +241,29 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
     for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) acc[q] = 0.0f;
     __syncthreads();
     const int g = threadIdx.x & (kLanes - 1);
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kLanes - 1));
     const unsigned int grp = threadIdx.x / kLanes, ngrp = blockDim.x / kLanes;
     for (unsigned int q = first + grp; q < last; q += ngrp) {
         const Splat s = make_splat(a, (long long)order[q]);
         const int nx = s.j_max - s.j_min, ny = s.i_max - s.i_min;
         if (nx <= 0 || ny <= 0) continue;
-        for (int j0 = 0; j0 < nx; j0 += kLanes) {
-            const int j = s.j_min + j0 + g;
-            const bool jok = (j0 + g) < nx;
-            const float gx = jok ? splat_gx(s, j) : 0.0f;
-            const bool jin = (j >= tx0) && (j < tx0 + kTile);
-            for (int i = s.i_min; i < s.i_max; i++) {
-                const float v = __fmul_rn(splat_gy(s, i), gx);
-                if (!jok) continue;
-                if (jin && i >= ty0 && i < ty0 + kTile)
-                    atomicAdd(&acc[(i - ty0) * kTile + (j - tx0)], v);
-                else
-                    atomicAdd(a.image + (size_t)i * a.npx + j, v);
+        for (int i0 = 0; i0 < ny; i0 += kLanes) {
+            const float gy_mine = (i0 + g < ny) ? splat_gy(s, s.i_min + i0 + g) : 0.0f;
+            const int nr = min(kLanes, ny - i0);
+            for (int j0 = 0; j0 < nx; j0 += kLanes) {
+                const int j = s.j_min + j0 + g;
+                const bool jok = (j0 + g) < nx;
+                const float gx = jok ? splat_gx(s, j) : 0.0f;
+                const bool jin = (j >= tx0) && (j < tx0 + kTile);
+                for (int r = 0; r < nr; r++) {
+                    const int i = s.i_min + i0 + r;
+                    const float v = __fmul_rn(__shfl_sync(gmask, gy_mine, r, kLanes), gx);
+                    if (!jok) continue;
+                    if (jin && i >= ty0 && i < ty0 + kTile)
+                        atomicAdd(&acc[(i - ty0) * kTile + (j - tx0)], v);
+                    else
+                        atomicAdd(a.image + (size_t)i * a.npx + j, v);
+                }
             }
         }
     }

@@ -35,6 +35,9 @@ def _declare(lib):
     lib.pb_identify.restype = i32
     lib.pb_get_spots.argtypes = [vp, i32, sz, i32, i32, i64, sz, vp, vp, vp, i32, f32, f32, f32, vp]
     lib.pb_get_spots.restype = i32
+    lib.pb_identify_get_spots.argtypes = [vp, i32, sz, i32, i32, i64, i32, f64, vp, f32, f32, f32,
+                                          vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
+    lib.pb_identify_get_spots.restype = i32
     lib._localize_declared = True
 
 
@@ -271,6 +274,80 @@ def get_spots(movie, identifications: pd.DataFrame, box: int, camera_info: dict)
     return spots
 
 
+def _identify_and_cut(movie, minimum_ng, box, camera_info, roi=None, frame_bounds=None,
+                      progress_callback=None):
+    """identify + get_spots in one pass over the movie (each frame chunk is uploaded once).
+    Returns (identifications DataFrame, spots float32 (n, box, box)); identical to
+    ``identify`` followed by ``get_spots``."""
+    lib = _lib_ready()
+    N = len(movie)
+    lo, hi = _frame_range(N, frame_bounds)
+    roi_arr = _roi_array(roi)
+    baseline = float(camera_info["Baseline"])
+    sensitivity = float(camera_info["Sensitivity"])
+    gain = float(camera_info["Gain"])
+    parts = []
+    step = _frames_per_chunk(movie) if N else 1
+    f = 0
+    while f < N:
+        f1 = min(N, f + step)
+        a, b = max(f, lo), min(f1, hi + 1)
+        if a < b:
+            chunk, dtype = _as_device_movie(_movie_chunk(movie, a, b))
+            F, Y, X = chunk.shape
+            capacity = max(4096, 512 * F)
+            while True:
+                fr = np.empty(capacity, np.int64); xs = np.empty(capacity, np.int64)
+                ys = np.empty(capacity, np.int64); ng = np.empty(capacity, np.float32)
+                sp = np.empty((capacity, box, box), np.float32)
+                found = C.c_size_t(0)
+                rc = lib.pb_identify_get_spots(
+                    _lib.ptr(chunk), dtype, F, Y, X, a, int(box), float(minimum_ng),
+                    _lib.ptr(roi_arr) if roi_arr is not None else None, baseline, sensitivity, gain,
+                    _lib.ptr(fr), _lib.ptr(xs), _lib.ptr(ys), _lib.ptr(ng), _lib.ptr(sp), capacity,
+                    C.byref(found))
+                if rc == 4:
+                    capacity = int(found.value)
+                    continue
+                _lib.check(rc)
+                n = int(found.value)
+                parts.append((fr[:n], xs[:n], ys[:n], ng[:n], sp[:n]))
+                break
+        if callable(progress_callback):
+            progress_callback(f1)
+        f = f1
+    if parts:
+        cat = [np.concatenate([p[k] for p in parts]) for k in range(5)]
+    else:
+        cat = [np.zeros(0, np.int64)] * 3 + [np.zeros(0, np.float32),
+                                             np.zeros((0, box, box), np.float32)]
+    ids = pd.DataFrame({"frame": cat[0].astype(int), "x": cat[1].astype(int),
+                        "y": cat[2].astype(int), "net_gradient": cat[3].astype(np.float32)})
+    return ids, np.ascontiguousarray(cat[4])
+
+
+def _fit_spots(spots, identifications, box, camera_info, fitting_method, eps, max_it, mle_method,
+               progress_callback):
+    from . import gausslq, gaussmle
+
+    em = camera_info["Gain"] > 1
+    if fitting_method == "gausslq":
+        theta = gausslq.fit_spots(spots, progress_callback)
+        return gausslq.locs_from_fits(identifications, theta, box, em)
+    if fitting_method == "gausslq-gpu":
+        if callable(progress_callback):
+            progress_callback(1)
+        theta = gausslq.fit_spots_gpufit(spots)
+        return gausslq.locs_from_fits_gpufit(identifications, theta, box, em)
+    if fitting_method == "gaussmle":
+        thetas, CRLBs, llhoods, iterations = gaussmle.gaussmle(spots, eps, max_it, mle_method,
+                                                               progress_callback)
+        return gaussmle.locs_from_fits(identifications, thetas, CRLBs, llhoods, iterations, box)
+    raise NotImplementedError(
+        "fitting_method='avg' (picasso.avgroi) is outside the B200 hot path; "
+        "use the reference implementation")
+
+
 def fit2D(movie, movie_info, camera_info, identifications, box,
           fitting_method: Literal["gausslq", "gausslq-gpu", "gaussmle", "avg"] = "gausslq",
           eps: float = 0.001, max_it: int = 100,
@@ -281,8 +358,6 @@ def fit2D(movie, movie_info, camera_info, identifications, box,
     Returns ``(locs DataFrame | None, new_info dict)``.  ``multiprocess`` is
     accepted for compatibility; every method runs on the GPU.
     """
-    from . import gausslq, gaussmle
-
     assert hasattr(movie, "__getitem__") and hasattr(movie, "__len__"), \
         "movie must be a movie loaded by picasso.io.load_movie"
     assert isinstance(movie_info, list), "movie_info must be a list"
@@ -304,23 +379,8 @@ def fit2D(movie, movie_info, camera_info, identifications, box,
         locs = None
     else:
         spots = get_spots(movie, identifications, box, camera_info)
-        em = camera_info["Gain"] > 1
-        if fitting_method == "gausslq":
-            theta = gausslq.fit_spots(spots, progress_callback)
-            locs = gausslq.locs_from_fits(identifications, theta, box, em)
-        elif fitting_method == "gausslq-gpu":
-            if callable(progress_callback):
-                progress_callback(1)
-            theta = gausslq.fit_spots_gpufit(spots)
-            locs = gausslq.locs_from_fits_gpufit(identifications, theta, box, em)
-        elif fitting_method == "gaussmle":
-            thetas, CRLBs, llhoods, iterations = gaussmle.gaussmle(
-                spots, eps, max_it, mle_method, progress_callback)
-            locs = gaussmle.locs_from_fits(identifications, thetas, CRLBs, llhoods, iterations, box)
-        else:
-            raise NotImplementedError(
-                "fitting_method='avg' (picasso.avgroi) is outside the B200 hot path; "
-                "use the reference implementation")
+        locs = _fit_spots(spots, identifications, box, camera_info, fitting_method, eps, max_it,
+                          mle_method, progress_callback)
     localize_info = {
         "Generated by": f"Picasso: v{__version__} Fit 2D (picasso_b200)",
         "Fit method": fitting_method,
@@ -348,15 +408,32 @@ def localize(movie, camera_info: dict, parameters: dict, *, roi=None, frame_boun
             "explicitly.", DeprecationWarning, stacklevel=2)
     if movie_info is None:
         movie_info = []
-    identifications, identify_info = identify(
-        movie, parameters["Min. Net Gradient"], parameters["Box Size"], roi=roi,
-        frame_bounds=frame_bounds, threaded=threaded,
-        progress_callback=identification_progress_callback, return_info=True)
-    locs, fit_info = fit2D(
-        movie=movie, movie_info=movie_info, camera_info=camera_info,
-        identifications=identifications, box=parameters["Box Size"],
-        fitting_method=fitting_method, eps=eps, max_it=max_it, mle_method=mle_method,
-        multiprocess=threaded, progress_callback=fit_progress_callback)
+    box = parameters["Box Size"]
+    minimum_ng = parameters["Min. Net Gradient"]
+    assert isinstance(camera_info, dict), "camera_info must be a dict"
+    assert fitting_method in ["gausslq", "gausslq-gpu", "gaussmle", "avg"], (
+        "fitting_method must be one of 'gausslq', 'gausslq-gpu', 'gaussmle', or 'avg'")
+    if "Pixelsize" not in camera_info:
+        warnings.warn("Camera info in picasso.localize.fit2D does not contain 'Pixelsize', "
+                      "i.e., effective camera pixel size in nm. Assuming 130.")
+        camera_info["Pixelsize"] = 130
+    # identify + get_spots fused: each movie chunk crosses PCIe once
+    identifications, spots = _identify_and_cut(
+        movie, minimum_ng, box, camera_info, roi=roi, frame_bounds=frame_bounds,
+        progress_callback=identification_progress_callback
+        if callable(identification_progress_callback) else None)
+    identify_info = {
+        "Generated by": f"Picasso: v{__version__} Identify (picasso_b200)",
+        "Min. Net Gradient": minimum_ng, "Box Size": box, "ROI": roi, "Frame Bounds": frame_bounds,
+    }
+    locs = _fit_spots(spots, identifications, box, camera_info, fitting_method, eps, max_it,
+                      mle_method, fit_progress_callback)
+    fit_info = {"Generated by": f"Picasso: v{__version__} Fit 2D (picasso_b200)",
+                "Fit method": fitting_method}
+    if fitting_method == "gaussmle":
+        fit_info["Convergence criterion"] = eps
+        fit_info["Max iterations"] = max_it
+    fit_info = fit_info | camera_info
     info = movie_info + [identify_info] + [fit_info]
     if return_info:
         return locs, info

@@ -126,3 +126,46 @@ def test_progress_abort_and_empty():
     assert empty.shape == (0, 7, 7)
     with pytest.warns(DeprecationWarning):
         localize.identify(movie, 5000, 7)
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+@pytest.mark.parametrize("method", ["gausslq", "gaussmle", "gausslq-gpu"])
+def test_localize_equals_identify_plus_fit2d(method):
+    """Reference test_localize.py:849-1069: localize == identify + fit2D; metadata keys;
+    the fused one-upload path gives the same table as the two-call path."""
+    movie = testing.synthetic_movie(16, 96, 80, emitters_per_frame=8, seed=21)
+    cam = {"Baseline": 100, "Sensitivity": 1.0, "Gain": 1, "Pixelsize": 130}
+    params = {"Min. Net Gradient": 5000, "Box Size": 7}
+    locs, info = localize.localize(movie, dict(cam), params, fitting_method=method,
+                                   return_info=True, movie_info=[{"Frames": 16}])
+    ids = localize.identify(movie, 5000, 7, return_info=False)
+    locs2, fit_info = localize.fit2D(movie, [{"Frames": 16}], dict(cam), ids, 7,
+                                     fitting_method=method)
+    assert len(locs) == len(ids) == len(locs2) > 50
+    pd.testing.assert_frame_equal(locs.reset_index(drop=True), locs2.reset_index(drop=True))
+    assert info[0] == {"Frames": 16} and info[1]["Box Size"] == 7
+    assert info[2]["Fit method"] == method and info[2]["Pixelsize"] == 130
+    if method == "gaussmle":
+        assert info[2]["Convergence criterion"] == 0.001 and info[2]["Max iterations"] == 100
+        assert list(locs.columns) == ["frame", "x", "y", "photons", "sx", "sy", "bg", "lpx", "lpy",
+                                      "ellipticity", "net_gradient", "log_likelihood", "iterations",
+                                      "photons_unc", "bg_unc", "sx_unc", "sy_unc"]
+        assert locs["frame"].dtype == np.uint32 and locs["iterations"].dtype == np.uint32
+    # positions land near the identification pixel
+    assert (np.abs(locs["x"].to_numpy() - ids["x"].to_numpy()) < 2).all()
+
+
+def test_fit2d_argument_contract():
+    movie = testing.synthetic_movie(2, 40, 40, emitters_per_frame=2, seed=3)
+    ids = localize.identify(movie, 5000, 7, return_info=False)
+    cam = {"Baseline": 100, "Sensitivity": 1.0, "Gain": 1}
+    with pytest.warns(UserWarning, match="Pixelsize"):
+        locs, info = localize.fit2D(movie, [], cam, ids, 7)
+    assert cam["Pixelsize"] == 130 and len(locs) == len(ids)
+    with pytest.raises(AssertionError):
+        localize.fit2D(movie, [], cam, ids, 7, fitting_method="nope")
+    with pytest.raises(AssertionError):
+        localize.fit2D(movie, [], cam, ids, 7, eps=-1)
+    assert localize.fit2D(movie, [], cam, ids, 7, abort_callback=lambda: True)[0] is None
+    with pytest.raises(NotImplementedError):
+        localize.fit2D(movie, [], cam, ids, 7, fitting_method="avg")
