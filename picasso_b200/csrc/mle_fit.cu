@@ -45,6 +45,9 @@ constexpr int kRedStride = 23;     // doubles per lane in the reduction scratch 
 #ifndef PB_MLE_PIX_UNROLL
 #define PB_MLE_PIX_UNROLL 1   // unroll factor of the per-row pixel loops
 #endif
+#ifndef PB_MLE_LIBM_ERF
+#define PB_MLE_LIBM_ERF 0      // 1: CUDA libdevice erf(); 0: erf_from_gauss (shares the exp)
+#endif
 #define PB_STR2(x) #x
 #define PB_STR(x) PB_STR2(x)
 #define PB_PIX_UNROLL _Pragma(PB_STR(unroll PB_MLE_PIX_UNROLL))
@@ -203,6 +206,34 @@ __device__ __forceinline__ bool inv_diag_cholesky(const double* m, double* diag)
         diag[j] = acc * d[j] * d[j];
     }
     return true;
+}
+
+// erf(z) from the Gaussian term A = exp(-z^2) the kernel computes anyway:
+//   erf(z) = sign(z) * (1 - A * P(x)),  t = 1/(1 + |z|/2),  x = (8 t - 5) / 3,
+// P = degree-16 fit of erfcx on z in [0, 6] (tools/gen_erf_coeffs.py: max abs error
+// 2.2e-15 in float64 Horner form; beyond |z| = 6, A < 3e-16 so the term vanishes).
+// One branch-free polynomial instead of libdevice's two-branch erf (both branches execute
+// when the 8 edges of a spot straddle |z| ~ 1).
+__constant__ double kErfcxPoly[17] = {
+    0.3785374169292369,      0.4221875836134109,     0.16940759095488894,
+    0.03299342947957943,     -0.0016702444148986467, -0.001665364388974453,
+    0.00013358437327083263,  0.00010054202594586505, -2.2700690081718415e-05,
+    -4.271484393949245e-06,  2.839667893118267e-06,  -2.8180849640529505e-07,
+    -2.0096403079505821e-07, 8.619074557878024e-08,  -3.971810944694673e-09,
+    -7.52808888456569e-09,   2.015803325273065e-09,
+};
+
+__device__ __forceinline__ double fast_rcp(double x);
+
+__device__ __forceinline__ double erf_from_gauss(double z, double A) {
+    double a = fabs(z);
+    a = a > 6.0 ? 6.0 : a;
+    const double t = fast_rcp(fma(0.5, a, 1.0));
+    const double x = fma(t, 2.6666666666666665, -1.6666666666666667);
+    double p = kErfcxPoly[16];
+#pragma unroll
+    for (int k = 15; k >= 0; k--) p = fma(p, x, kErfcxPoly[k]);
+    return copysign(fma(-A, p, 1.0), z);
 }
 
 template <int BOX, int G, int METHOD>   // METHOD 1 = sigmaxy (6 par), 0 = sigma (5 par)
@@ -402,11 +433,16 @@ mle_fit_kernel(const MleArgs a) {
                     // edge g: minus edge of pixel g == plus edge of pixel g-1 (exact)
                     const double ex = ((double)g - (double)th[0]) - 0.5;
                     const double ey = ((double)g - (double)th[1]) - 0.5;
-                    const double Ex = erf(ex * (kInvSqrt2 * rsx));
-                    const double Ey = erf(ey * (kInvSqrt2 * rsy));
                     const double tx = ex * rsx, ty = ey * rsy;
                     const double qx = 0.5 * tx * tx, qy = 0.5 * ty * ty;
                     const double Ax = exp(-qx), Ay = exp(-qy);
+#if PB_MLE_LIBM_ERF
+                    const double Ex = erf(ex * (kInvSqrt2 * rsx));
+                    const double Ey = erf(ey * (kInvSqrt2 * rsy));
+#else
+                    const double Ex = erf_from_gauss(ex * (kInvSqrt2 * rsx), Ax);
+                    const double Ey = erf_from_gauss(ey * (kInvSqrt2 * rsy), Ay);
+#endif
                     // plus-edge values from the next lane
                     const double Exp_ = pb_gshfl_down1<G>(Ex), Eyp_ = pb_gshfl_down1<G>(Ey);
                     const double Axp = pb_gshfl_down1<G>(Ax), Ayp = pb_gshfl_down1<G>(Ay);

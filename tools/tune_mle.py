@@ -16,8 +16,9 @@ CSRC = os.path.join(ROOT, "picasso_b200", "csrc")
 NVCC = "/usr/local/cuda/bin/nvcc"
 
 VARIANTS = {}
-for minb, unroll in itertools.product((4, 5), (1, 8)):
-    VARIANTS[f"b{minb}_u{unroll}"] = [f"-DPB_MLE_MINB={minb}", f"-DPB_MLE_PIX_UNROLL={unroll}"]
+for erf, unroll in itertools.product((0, 1), (1, 8)):
+    VARIANTS[f"b4_u{unroll}_{'libm' if erf else 'gauss'}erf"] = [
+        "-DPB_MLE_MINB=4", f"-DPB_MLE_PIX_UNROLL={unroll}", f"-DPB_MLE_LIBM_ERF={erf}"]
 
 
 def build():
