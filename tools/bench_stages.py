@@ -92,6 +92,10 @@ def stage_identify(torch, small):
     n_found = int(cnt.item())
     bytes_alg = F * Y * X * 2 + n_found * 28
     ach = bytes_alg / (ms * 1e-3) / 1e9
+    if KERNEL_ONLY:
+        print(json.dumps({"stage": "identify kernel", "movie": [F, Y, X], "ms": ms,
+                          "achieved_GBs": ach, "frac": ach / peaks()}), flush=True)
+        return
     # end to end through the Python API with a host movie (H2D inside), incl. get_spots + LQ
     hmovie = movie.cpu().numpy()
     cam = {"Baseline": 100, "Sensitivity": 1.0, "Gain": 1, "Pixelsize": 130}
@@ -171,6 +175,9 @@ def stage_render(torch, small):
         alg = n * (16 if mode else 8) + npx * npx * 4
         out[name] = {"ms": ms, "locs_per_s": n / (ms * 1e-3), "achieved_GBs": alg / (ms * 1e-3) / 1e9,
                      "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peaks(), "algorithmic_bytes": alg}
+    if KERNEL_ONLY:
+        print(json.dumps(out), flush=True)
+        return
     # end to end through the Python API (host arrays in, host image out)
     import pandas as pd
     import warnings
@@ -262,6 +269,8 @@ def stage_rcc(torch, small):
         "window_max_abs_err_vs_numpy_f64": float(np.abs(gwin - ref).max()),
         "window_peak": float(ref.max())}), flush=True)
 
+
+KERNEL_ONLY = "--kernel-only" in sys.argv
 
 if __name__ == "__main__":
     import torch
