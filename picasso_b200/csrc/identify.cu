@@ -38,6 +38,7 @@ __host__ __device__ constexpr int tile_rows(int h) {
     return h == 1 ? 34 : h == 2 ? 36 : h == 3 ? 36 : h == 4 ? 37 : h == 5 ? 34 : h == 6 ? 40 : 31;
 }
 constexpr int kHP = 8;      // column halo in shared memory (>= h+1, keeps 16 B alignment)
+constexpr int kCandCap = 96;   // per-warp list of local maxima awaiting their net gradient
 
 struct IdArgs {
     const void* movie;      // frames [n_frames][Y][X]
@@ -60,11 +61,14 @@ template <> struct PixTraits<unsigned short> {
     using Vec = uint4;              // 8 pixels
     static constexpr int kPerVec = 8;
     __device__ static float to_f32(unsigned short v) { return (float)v; }
+    // f32(a) - f32(b) for uint16 a, b: the difference is an exact integer
+    __device__ static float diff(unsigned short a, unsigned short b) { return (float)((int)a - (int)b); }
 };
 template <> struct PixTraits<float> {
     using Vec = float4;             // 4 pixels
     static constexpr int kPerVec = 4;
     __device__ static float to_f32(float v) { return v; }
+    __device__ static float diff(float a, float b) { return __fsub_rn(a, b); }
 };
 
 template <typename T>
@@ -168,32 +172,84 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
         }
     }
 
-    // ---- net gradient for the (rare) maxima (localize.py:202-244): float32,
-    // row-major accumulation, unfused IEEE ops, negative-index wrap-around
+    // ---- net gradient of the local maxima (localize.py:202-244) -------------------
+    // float32, row-major accumulation, unfused IEEE ops, numba's negative-index wrap.
+    // Noise alone makes ~1 pixel in BOX^2 a local maximum, unevenly spread over the
+    // lanes, so the warp's candidates are first compacted into a shared list and then
+    // dealt out one per lane (the per-candidate sum stays sequential -> bit-exact).
+    __shared__ unsigned short cand_list[kTX / 32][kCandCap];
+    const int lane = tid & 31, wid = tid >> 5;
+    const int mine = __popcll(candmask);
+    int prefix = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, prefix, o);
+        if (lane >= o) prefix += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, prefix, 31);
+    int wpos = prefix - mine;
+    // a warp-tile rarely holds more than a few dozen maxima; if the list overflows the
+    // excess stays in candmask and is handled by its own lane afterwards
+    unsigned long long left = 0;
     while (candmask) {
         const int u = __ffsll((long long)candmask) - 1;
         candmask &= candmask - 1;
+        if (wpos < kCandCap) cand_list[wid][wpos] = (unsigned short)((u << 8) | lane);
+        else left |= (1ull << u);
+        wpos++;
+    }
+    __syncwarp();
+    const int listed = min(total, kCandCap);
+    for (int base = 0; base < listed || __any_sync(0xffffffffu, left != 0); base += 32) {
+        int u = -1, cl = lane;
+        if (base + lane < listed) {
+            const unsigned short e = cand_list[wid][base + lane];
+            u = e >> 8; cl = e & 0xff;
+        } else if (base >= listed && left) {
+            u = __ffsll((long long)left) - 1;
+            left &= left - 1;
+        }
+        if (u < 0) continue;
         const int i = ty0 + u;
+        const int jc = tx0 + (wid << 5) + cl;          // image column of the candidate
+        const int tcc = kHP + (wid << 5) + cl;         // its tile column
+        const int tr_c = u + H + 1;                    // tile row of the centre
         float acc = 0.0f;
-        const int tr_c = u + H + 1;      // tile row of the centre
-        for (int kk = -H; kk <= H; kk++) {
-            for (int mm = -H; mm <= H; mm++) {
-                if (kk == 0 && mm == 0) continue;
-                const int k = i + kk, m = j + mm;
-                float up, lf;
-                const float dn = PixTraits<T>::to_f32(tile[tr_c + kk + 1][tc + mm]);
-                const float rt = PixTraits<T>::to_f32(tile[tr_c + kk][tc + mm + 1]);
-                if (k - 1 >= 0) up = PixTraits<T>::to_f32(tile[tr_c + kk - 1][tc + mm]);
-                else  // numba negative index: frame[-1] is the LAST image row
-                    up = PixTraits<T>::to_f32(frame[(size_t)(a.y0 + a.Ys - 1) * a.X + a.x0 + m]);
-                if (m - 1 >= 0) lf = PixTraits<T>::to_f32(tile[tr_c + kk][tc + mm - 1]);
-                else
-                    lf = PixTraits<T>::to_f32(frame[(size_t)(a.y0 + k) * a.X + a.x0 + a.Xs - 1]);
-                const float gy = __fsub_rn(dn, up);
-                const float gx = __fsub_rn(rt, lf);
-                const int q = (kk + H) * BOX + (mm + H);
-                const float tsum = __fadd_rn(__fmul_rn(gy, uy[q]), __fmul_rn(gx, ux[q]));
-                acc = __fadd_rn(acc, tsum);
+        if (i > H && jc > H) {
+            // interior: every neighbour is in the tile; u16 differences are exact integers
+#pragma unroll 1
+            for (int kk = -H; kk <= H; kk++) {
+                const T* r0 = &tile[tr_c + kk - 1][tcc];
+                const T* r1 = &tile[tr_c + kk][tcc];
+                const T* r2 = &tile[tr_c + kk + 1][tcc];
+#pragma unroll
+                for (int mm = -H; mm <= H; mm++) {
+                    if (kk == 0 && mm == 0) continue;
+                    const float gy = PixTraits<T>::diff(r2[mm], r0[mm]);
+                    const float gx = PixTraits<T>::diff(r1[mm + 1], r1[mm - 1]);
+                    const int q = (kk + H) * BOX + (mm + H);
+                    acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(gy, uy[q]), __fmul_rn(gx, ux[q])));
+                }
+            }
+        } else {
+            for (int kk = -H; kk <= H; kk++) {
+                for (int mm = -H; mm <= H; mm++) {
+                    if (kk == 0 && mm == 0) continue;
+                    const int k = i + kk, m = jc + mm;
+                    float up, lf;
+                    const float dn = PixTraits<T>::to_f32(tile[tr_c + kk + 1][tcc + mm]);
+                    const float rt = PixTraits<T>::to_f32(tile[tr_c + kk][tcc + mm + 1]);
+                    if (k - 1 >= 0) up = PixTraits<T>::to_f32(tile[tr_c + kk - 1][tcc + mm]);
+                    else  // numba negative index: frame[-1] is the LAST image row
+                        up = PixTraits<T>::to_f32(frame[(size_t)(a.y0 + a.Ys - 1) * a.X + a.x0 + m]);
+                    if (m - 1 >= 0) lf = PixTraits<T>::to_f32(tile[tr_c + kk][tcc + mm - 1]);
+                    else
+                        lf = PixTraits<T>::to_f32(frame[(size_t)(a.y0 + k) * a.X + a.x0 + a.Xs - 1]);
+                    const float gy = __fsub_rn(dn, up);
+                    const float gx = __fsub_rn(rt, lf);
+                    const int q = (kk + H) * BOX + (mm + H);
+                    acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(gy, uy[q]), __fmul_rn(gx, ux[q])));
+                }
             }
         }
         if ((double)acc > a.min_ng_d) {
@@ -201,7 +257,7 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
             if (slot < a.capacity) {
                 a.out_frame[slot] = f + a.frame_offset;
                 a.out_y[slot] = i + a.y0;
-                a.out_x[slot] = j + a.x0;
+                a.out_x[slot] = jc + a.x0;
                 a.out_ng[slot] = acc;
             }
         }

@@ -43,7 +43,7 @@ constexpr int kRedStride = 23;     // doubles per lane in the reduction scratch 
 #define PB_MLE_MINB 4          // min resident CTAs per SM requested from ptxas
 #endif
 #ifndef PB_MLE_PIX_UNROLL
-#define PB_MLE_PIX_UNROLL 1   // unroll factor of the per-row pixel loops
+#define PB_MLE_PIX_UNROLL 8   // unroll factor of the per-row pixel loops
 #endif
 #ifndef PB_MLE_LIBM_ERF
 #define PB_MLE_LIBM_ERF 0      // 1: CUDA libdevice erf(); 0: erf_from_gauss (shares the exp)

@@ -102,3 +102,31 @@ def test_mle_degenerate_spots(oracle):
     assert np.isfinite(th[4]).all()
     oth, *_ = oracle.gaussmle(spots[4:5], 0.001, 100)
     np.testing.assert_allclose(th[4], oth[0], rtol=1e-4, atol=1e-4)
+
+
+def test_mle_large_batch_properties(oracle):
+    """Full-size style checks through size-independent properties (2 M spots, several
+    host chunks / thousands of TMA tiles): every result depends only on its own ROI --
+    a tiled copy of a small batch reproduces the small batch bit-for-bit, at any offset,
+    and a permutation of the input permutes the output."""
+    base = testing.synthetic_spots(4099, 7, seed=17)          # prime-ish: no alignment luck
+    reps = 488
+    big = np.tile(base, (reps, 1, 1))                         # 2 000 312 spots
+    th, cr, ll, it = gaussmle.gaussmle(big, 0.001, 100)
+    th0, cr0, ll0, it0 = gaussmle.gaussmle(base, 0.001, 100)
+    n = len(base)
+    for r in (0, 1, 137, reps - 1):
+        sl = slice(r * n, (r + 1) * n)
+        np.testing.assert_array_equal(th[sl], th0)
+        np.testing.assert_array_equal(cr[sl], cr0)
+        np.testing.assert_array_equal(ll[sl], ll0)
+        np.testing.assert_array_equal(it[sl], it0)
+    # checksum of checksums over all repetitions
+    assert it.astype(np.int64).sum() == reps * it0.astype(np.int64).sum()
+    perm = np.random.default_rng(0).permutation(n)
+    thp, crp, llp, itp = gaussmle.gaussmle(base[perm], 0.001, 100)
+    np.testing.assert_array_equal(thp, th0[perm])
+    np.testing.assert_array_equal(itp, it0[perm])
+    # and the small batch itself is right
+    oth, _, _, oit = oracle.gaussmle(base, 0.001, 100, nthreads=8)
+    assert (it0 == oit).mean() >= 0.99
