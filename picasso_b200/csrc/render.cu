@@ -19,9 +19,10 @@
 //                          j, j+8, ...; a row's 8 consecutive pixels share one or
 //                          two 32 B sectors, so the L2 atomic unit sees coalesced
 //                          reductions.  Used for small batches.
-//   render_tiled_kernel    localisations are binned by 64x64-pixel tile
-//                          (counting sort on the device); one CTA accumulates its
-//                          tile in shared memory with shared-memory atomics and
+//   render_tiled_kernel    localisations are binned by 64x64-pixel tile (counting
+//                          sort on the device, the float4 records are scattered into
+//                          tile order); one CTA accumulates its tile in shared memory,
+//                          one THREAD per localisation, with shared-memory atomics and
 //                          flushes it once with coalesced reductions; window parts
 //                          that cross the tile edge go straight to global atomics.
 #include <algorithm>
@@ -218,51 +219,92 @@ __global__ void render_scan_kernel(const unsigned int* __restrict__ count,
     if (t == 1023) start[ntiles] = part[1023];
 }
 
-// pass 3: scatter localisation indices into tile order
-__global__ void render_scatter_kernel(long long n, const int* __restrict__ tile_of,
+// pass 3: scatter the localisations themselves (x, y, lpx, lpy as one float4) into tile
+// order, so the accumulation pass streams them with coalesced 16 B loads
+__global__ void render_scatter_kernel(const RenderArgs a, const int* __restrict__ tile_of,
                                       unsigned int* __restrict__ cursor,
-                                      unsigned int* __restrict__ order) {
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+                                      float4* __restrict__ sorted) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
          k += (long long)gridDim.x * blockDim.x) {
         const int t = tile_of[k];
-        if (t >= 0) order[atomicAdd(cursor + t, 1u)] = (unsigned int)k;
+        if (t >= 0)
+            sorted[atomicAdd(cursor + t, 1u)] = make_float4(a.x[k], a.y[k], a.lpx[k], a.lpy[k]);
     }
 }
 
-// pass 4: one CTA per tile, shared-memory accumulation
+// pass 4: one CTA per tile; ONE THREAD per localisation.  The thread evaluates its 1-D
+// column kernel once into shared memory (gxs[jj][tid], conflict-free), then walks the
+// window rows adding gy * gx into the CTA's shared tile with shared-memory atomics; window
+// parts outside the tile go to global atomics.  The window geometry and sigma follow the
+// reference in float64 / float32 exactly; the two exponentials per pixel row/column are
+// evaluated with expf on a float64-computed offset (per-pixel relative deviation ~1e-6,
+// far inside the 1e-4 render tolerance).
+constexpr int kMaxWin = 16;               // windows wider than this take the generic path
+
 __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, int tiles_x,
                                                            const unsigned int* __restrict__ start,
-                                                           const unsigned int* __restrict__ order) {
+                                                           const float4* __restrict__ sorted) {
     __shared__ float acc[kTile * kTile];
+    __shared__ float gxs[kMaxWin][256];
     const int tile = blockIdx.x;
     const unsigned int first = start[tile], last = start[tile + 1];
     if (first == last) return;
     const int ty0 = (tile / tiles_x) * kTile, tx0 = (tile % tiles_x) * kTile;
     for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) acc[q] = 0.0f;
     __syncthreads();
-    const int g = threadIdx.x & (kLanes - 1);
-    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kLanes - 1));
-    const unsigned int grp = threadIdx.x / kLanes, ngrp = blockDim.x / kLanes;
-    for (unsigned int q = first + grp; q < last; q += ngrp) {
-        const Splat s = make_splat(a, (long long)order[q]);
-        const int nx = s.j_max - s.j_min, ny = s.i_max - s.i_min;
+    const int tid = threadIdx.x;
+    for (unsigned int q = first + tid; q < last; q += blockDim.x) {
+        const float4 L = sorted[q];
+        // ---- window and sigmas exactly as _draw_gaussian_loc (render.py:505-525) ----
+        const double x_ = a.os * ((double)L.x - a.x_min);
+        const double y_ = a.os * ((double)L.y - a.y_min);
+        const float bw = __fmul_rn(a.osf, fmaxf(L.z, a.mbw));
+        const float bh = __fmul_rn(a.osf, fmaxf(L.w, a.mbw));
+        float sx, sy;
+        if (a.mode == 2) { sy = __fdiv_rn(__fadd_rn(bh, bw), 2.0f); sx = sy; }
+        else { sx = bw; sy = bh; }
+        const double moy = 3.0 * (double)sy, mox = 3.0 * (double)sx;
+        const int i_min = max((int)(y_ - moy), 0);
+        const int i_max = min((int)(y_ + moy + 1.0), a.npy);
+        const int j_min = max((int)(x_ - mox), 0);
+        const int j_max = min((int)(x_ + mox) + 1, a.npx);
+        const int nx = j_max - j_min, ny = i_max - i_min;
         if (nx <= 0 || ny <= 0) continue;
-        for (int i0 = 0; i0 < ny; i0 += kLanes) {
-            const float gy_mine = (i0 + g < ny) ? splat_gy(s, s.i_min + i0 + g) : 0.0f;
-            const int nr = min(kLanes, ny - i0);
-            for (int j0 = 0; j0 < nx; j0 += kLanes) {
-                const int j = s.j_min + j0 + g;
-                const bool jok = (j0 + g) < nx;
-                const float gx = jok ? splat_gx(s, j) : 0.0f;
-                const bool jin = (j >= tx0) && (j < tx0 + kTile);
-                for (int r = 0; r < nr; r++) {
-                    const int i = s.i_min + i0 + r;
-                    const float v = __fmul_rn(__shfl_sync(gmask, gy_mine, r, kLanes), gx);
-                    if (!jok) continue;
-                    if (jin && i >= ty0 && i < ty0 + kTile)
-                        atomicAdd(&acc[(i - ty0) * kTile + (j - tx0)], v);
-                    else
-                        atomicAdd(a.image + (size_t)i * a.npx + j, v);
+        const float inv_2sx2 = 1.0f / (2.0f * sx * sx);
+        const float inv_2sy2 = 1.0f / (2.0f * sy * sy);
+        const float norm = 1.0f / (6.2831853071795862f * sx * sy);
+        const float dx0 = (float)((double)j_min + 0.5 - x_);   // offsets relative to the centre,
+        const float dy0 = (float)((double)i_min + 0.5 - y_);   // formed in f64 (x_ can be ~1e4)
+        if (nx <= kMaxWin) {
+#pragma unroll 1
+            for (int jj = 0; jj < nx; jj++) {
+                const float dx = dx0 + (float)jj;
+                gxs[jj][tid] = expf(-dx * dx * inv_2sx2);
+            }
+#pragma unroll 1
+            for (int ii = 0; ii < ny; ii++) {
+                const float dy = dy0 + (float)ii;
+                const float gy = norm * expf(-dy * dy * inv_2sy2);
+                const int i = i_min + ii;
+                const bool iin = (i >= ty0) && (i < ty0 + kTile);
+                float* grow = a.image + (size_t)i * a.npx;
+                float* srow = acc + (i - ty0) * kTile - tx0;
+#pragma unroll 1
+                for (int jj = 0; jj < nx; jj++) {
+                    const int j = j_min + jj;
+                    const float v = gy * gxs[jj][tid];
+                    if (iin && j >= tx0 && j < tx0 + kTile) atomicAdd(srow + j, v);
+                    else atomicAdd(grow + j, v);
+                }
+            }
+        } else {   // very wide kernels (sigma > 2.5 display px): no column cache
+            for (int ii = 0; ii < ny; ii++) {
+                const float dy = dy0 + (float)ii;
+                const float gy = norm * expf(-dy * dy * inv_2sy2);
+                for (int jj = 0; jj < nx; jj++) {
+                    const float dx = dx0 + (float)jj;
+                    atomicAdd(a.image + (size_t)(i_min + ii) * a.npx + j_min + jj,
+                              gy * expf(-dx * dx * inv_2sx2));
                 }
             }
         }
@@ -280,7 +322,7 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
 // Workspace (bytes) pb_render_dev needs for the tiled path; 0 => use the direct path.
 extern "C" size_t pb_render_workspace_bytes(size_t n, int n_pixel_y, int n_pixel_x) {
     const size_t tiles = (size_t)((n_pixel_y + kTile - 1) / kTile) * ((n_pixel_x + kTile - 1) / kTile);
-    return n * 8 + (tiles + 1) * 12 + 256;
+    return n * 20 + (tiles + 1) * 12 + 256;   // tile_of (4 B) + sorted float4 (16 B) per loc
 }
 
 extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
@@ -311,7 +353,7 @@ extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const
     const long long ntiles = (long long)tiles_x * tiles_y;
     const size_t need = pb_render_workspace_bytes(n, n_pixel_y, n_pixel_x);
     const bool tiled = d_workspace && workspace_bytes >= need && n >= 65536 && n < 0xffffffffull &&
-                       ntiles >= 64;
+                       ntiles >= 64 && ((reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0);
     if (!tiled) {
         long long want = ((long long)n * kLanes + threads - 1) / threads;
         int grid = (int)std::min<long long>(want, 148 * 16);
@@ -320,19 +362,19 @@ extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const
         PB_CUDA_CHECK(cudaGetLastError());
         return PB_OK;
     }
-    // workspace layout: tile_of[n] i32 | order[n] u32 | count[T] | start[T+1] | cursor[T]
+    // workspace layout: sorted[n] float4 | tile_of[n] i32 | count[T] | start[T+1] | cursor[T]
     char* w = static_cast<char*>(d_workspace);
-    int* tile_of = reinterpret_cast<int*>(w);
-    unsigned int* order = reinterpret_cast<unsigned int*>(w + n * 4);
-    unsigned int* tcount = reinterpret_cast<unsigned int*>(w + n * 8);
+    float4* sorted = reinterpret_cast<float4*>(w);
+    int* tile_of = reinterpret_cast<int*>(w + n * 16);
+    unsigned int* tcount = reinterpret_cast<unsigned int*>(w + n * 20);
     unsigned int* tstart = tcount + ntiles;
     unsigned int* tcursor = tstart + ntiles + 1;
     PB_CUDA_CHECK(cudaMemsetAsync(tcount, 0, ntiles * 4, s));
     int grid = (int)std::min<long long>(((long long)n + threads - 1) / threads, 148 * 16);
     render_bin_kernel<<<grid, threads, 0, s>>>(a, tiles_x, tile_of, tcount);
     render_scan_kernel<<<1, 1024, 0, s>>>(tcount, tstart, tcursor, (int)ntiles);
-    render_scatter_kernel<<<grid, threads, 0, s>>>((long long)n, tile_of, tcursor, order);
-    render_tiled_kernel<<<(unsigned)ntiles, 256, 0, s>>>(a, tiles_x, tstart, order);
+    render_scatter_kernel<<<grid, threads, 0, s>>>(a, tile_of, tcursor, sorted);
+    render_tiled_kernel<<<(unsigned)ntiles, 256, 0, s>>>(a, tiles_x, tstart, sorted);
     g_pb_launches += 4;
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
