@@ -266,6 +266,8 @@ def main():
     lib = _lib.load()
     _lib.require_gpu()
     if world > 1:
+        # keep stdout to the single JSON line (NCCL prints its version banner at INFO/VERSION)
+        os.environ["NCCL_DEBUG"] = os.environ.get("PB_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.spots
