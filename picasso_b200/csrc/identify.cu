@@ -75,7 +75,13 @@ template <typename T>
 __device__ __forceinline__ T pmax(T a, T b) { return a > b ? a : b; }
 
 // packed helpers: two uint16 pixels per 32-bit word (low half = even column)
-__device__ __forceinline__ unsigned pk_max(unsigned a, unsigned b) { return __vmaxu2(a, b); }
+// (PTX max.u16x2 is a native packed instruction on sm_90+; the __vmaxu2 / __vcmp*2
+//  SIMD-video intrinsics are emulated with long LOP3/SEL sequences)
+__device__ __forceinline__ unsigned pk_max(unsigned a, unsigned b) {
+    unsigned r;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
 // pixels (2k+1, 2k+2) from the words holding (2k, 2k+1) and (2k+2, 2k+3)
 __device__ __forceinline__ unsigned pk_odd(unsigned w0, unsigned w1) { return __byte_perm(w0, w1, 0x5432); }
 
@@ -144,6 +150,12 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
     // maxima of the last P rows (slot = tile row mod P).  Scan range of the reference:
     // i in [H, Ys-H-1), j in [H, Xs-H-1).
     unsigned long long cand0 = 0, cand1 = 0;   // bit u: (ty0+u, column) is a local maximum
+    // rows of this tile inside the reference's scan range: 0 <= u < kTY, H <= ty0+u < Ys-H-1
+    unsigned long long rowmask;
+    {
+        const int ulo = max(0, H - ty0), uhi = min(kTY, a.Ys - H - 1 - ty0);
+        rowmask = (uhi > ulo) ? ((uhi - ulo >= 64 ? ~0ull : ((1ull << (uhi - ulo)) - 1ull)) << ulo) : 0ull;
+    }
     if constexpr (!PACKED) {
         const int j = tx0 + tid;                 // image column of this thread
         const int tc = kHP + tid;                // tile column
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
         for (int k = 0; k < P; k++) { rm[k] = T(0); cc[k] = T(0); ll[k] = T(0); rr[k] = T(0); }
 #pragma unroll 1
         for (int t0 = 0; t0 < kTY + 2 * H; t0 += P) {
+            unsigned pm = 0;
 #pragma unroll
             for (int k = 0; k < P; k++) {
                 const int t = t0 + k;            // tile row t+1 <-> image row ty0 - H + t
@@ -171,14 +184,16 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
                     below = pmax(below, rm[(k + P - H + 1 + q) % P]);
                 }
                 const int cs = (k + P - H) % P;
-                const int u = t - 2 * H;         // output row within the tile
-                const int i = ty0 + u;           // image row of the window centre
                 const T c0 = cc[cs];
-                const bool is_max = (u >= 0) && col_ok && (i >= H) && (i < a.Ys - H - 1) &&
-                                    (c0 > above) && (c0 > ll[cs]) && (c0 >= rr[cs]) && (c0 >= below);
-                if (is_max) cand0 |= (1ull << u);
+                const bool is_max = (c0 > above) && (c0 > ll[cs]) && (c0 >= rr[cs]) && (c0 >= below);
+                pm |= (is_max ? 1u : 0u) << k;   // bit k <-> output row t0 + k - 2H
             }
+            // one variable shift per period instead of one per row
+            if (t0 >= 2 * H) cand0 |= (unsigned long long)pm << (t0 - 2 * H);
+            else cand0 |= (unsigned long long)pm >> (2 * H - t0);
         }
+        if (!col_ok) cand0 = 0;
+        cand0 &= rowmask;
     } else {
         // two adjacent columns per thread, packed uint16x2 SIMD: 2.5 shared loads per
         // pixel instead of 7 and half the compare/max instructions
@@ -193,6 +208,7 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
         for (int k = 0; k < P; k++) { rm[k] = 0; cc[k] = 0; ll[k] = 0; rr[k] = 0; }
 #pragma unroll 1
         for (int t0 = 0; t0 < kTY + 2 * H; t0 += P) {
+            unsigned pm0 = 0, pm1 = 0;
 #pragma unroll
             for (int k = 0; k < P; k++) {
                 const int t = t0 + k;
@@ -219,17 +235,30 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
                     below = pk_max(below, rm[(k + P - H + 1 + q) % P]);
                 }
                 const int cs = (k + P - H) % P;
-                const int u = t - 2 * H;
-                const int i = ty0 + u;
                 const unsigned c0 = cc[cs];
-                // per-half 0xffff masks: c0 > above, c0 > left, c0 >= right, c0 >= below
-                const unsigned m = __vcmpgtu2(c0, above) & __vcmpgtu2(c0, ll[cs]) &
-                                   __vcmpgeu2(c0, rr[cs]) & __vcmpgeu2(c0, below);
-                const bool row_ok = (u >= 0) && (i >= H) && (i < a.Ys - H - 1);
-                if (row_ok && ok0 && (m & 0x0000ffffu)) cand0 |= (1ull << u);
-                if (row_ok && ok1 && (m & 0xffff0000u)) cand1 |= (1ull << u);
+                // strict part: c0 > max(above, left)  <=>  max(c0, m1) != m1   (per half)
+                // weak part:   c0 >= max(right, below) <=> max(c0, m2) == c0   (per half)
+                const unsigned m1 = pk_max(above, ll[cs]);
+                const unsigned m2 = pk_max(rr[cs], below);
+                const unsigned sgt = pk_max(c0, m1) ^ m1;      // half != 0: strictly greater
+                const unsigned wge = pk_max(c0, m2) ^ c0;      // half == 0: greater or equal
+                const unsigned h0 = ((sgt & 0x0000ffffu) != 0) & ((wge & 0x0000ffffu) == 0);
+                const unsigned h1 = ((sgt & 0xffff0000u) != 0) & ((wge & 0xffff0000u) == 0);
+                pm0 |= h0 << k;                  // bit k <-> output row t0 + k - 2H
+                pm1 |= h1 << k;
+            }
+            if (t0 >= 2 * H) {
+                cand0 |= (unsigned long long)pm0 << (t0 - 2 * H);
+                cand1 |= (unsigned long long)pm1 << (t0 - 2 * H);
+            } else {
+                cand0 |= (unsigned long long)pm0 >> (2 * H - t0);
+                cand1 |= (unsigned long long)pm1 >> (2 * H - t0);
             }
         }
+        if (!ok0) cand0 = 0;
+        if (!ok1) cand1 = 0;
+        cand0 &= rowmask;
+        cand1 &= rowmask;
     }
 
     // ---- net gradient of the local maxima (localize.py:202-244) -------------------
