@@ -128,8 +128,11 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
             const int c = tx0 - kHP + tv * PV;
             T* dst = &tile[tr][tv * PV];
             if (r >= 0 && r < a.Ys && c >= 0 && c + PV <= a.Xs && vec_ok) {
-                *reinterpret_cast<V*>(dst) =
-                    __ldg(reinterpret_cast<const V*>(frame + (size_t)(a.y0 + r) * a.X + a.x0 + c));
+                // 16-byte asynchronous global->shared copy (LDGSTS): no register staging,
+                // all of a thread's vectors are in flight at once
+                const V* src = reinterpret_cast<const V*>(frame + (size_t)(a.y0 + r) * a.X + a.x0 + c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pb_smem_u32(dst)), "l"(src)
+                             : "memory");
             } else {
 #pragma unroll
                 for (int k = 0; k < PV; k++) {
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
             }
         }
     }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // Local maxima (localize.py:97-134) in separable form: the centre must be > every
