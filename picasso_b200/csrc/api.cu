@@ -69,8 +69,9 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
 };
+constexpr int kSlots = 3;
 struct DevWs {
-    Slot slots[2];
+    Slot slots[kSlots];
 };
 std::mutex g_ws_mutex;
 std::vector<DevWs> g_ws;   // indexed by device
@@ -120,8 +121,13 @@ extern "C" int pb_mle_fit(size_t n, int box, const float* spots, double eps, int
     }
     std::lock_guard<std::mutex> call_lk(g_host_call_mutex);
     const size_t pix = (size_t)box * box;
-    // chunk: ~64 MB of ROIs, a multiple of 4 spots (TMA tile)
-    size_t chunk = (64u << 20) / (pix * 4);
+    // chunk: ~64 MB of ROIs (PB_MLE_CHUNK_MB overrides), a multiple of 4096 spots
+    size_t chunk_mb = 64;
+    if (const char* e = getenv("PB_MLE_CHUNK_MB")) {
+        const long v = atol(e);
+        if (v >= 1 && v <= 4096) chunk_mb = (size_t)v;
+    }
+    size_t chunk = (chunk_mb << 20) / (pix * 4);
     chunk = chunk / 4096 * 4096;
     if (chunk < 4096) chunk = 4096;
     if (chunk > n) chunk = align_up(n, 4);
@@ -133,16 +139,18 @@ extern "C" int pb_mle_fit(size_t n, int box, const float* spots, double eps, int
     const size_t o_it = align_up(o_ll + chunk * 4, 256);
     const size_t o_st = align_up(o_it + chunk * 4, 256);
     const size_t total = align_up(o_st + chunk * 4, 256);
-    Slot* sl[2];
+    Slot* sl[kSlots];
     int rc;
-    if ((rc = ws_get(0, total, &sl[0])) != PB_OK) return rc;
-    if ((rc = ws_get(1, total, &sl[1])) != PB_OK) return rc;
+    for (int s = 0; s < kSlots; s++)
+        if ((rc = ws_get(s, total, &sl[s])) != PB_OK) return rc;
 
-    size_t done_spots[2] = {0, 0};
-    bool busy[2] = {false, false};
+    // kSlots chunks in flight: the H2D of chunk c+1/c+2 and the D2H of chunk c-1 overlap
+    // the kernel of chunk c (separate streams -> separate copy engines)
+    size_t done_spots[kSlots] = {0};
+    bool busy[kSlots] = {false};
     size_t c = 0;
     for (size_t first = 0; first < n; first += chunk, c++) {
-        const int s = (int)(c & 1);
+        const int s = (int)(c % kSlots);
         Slot* S = sl[s];
         if (busy[s]) {
             PB_CUDA_CHECK(cudaEventSynchronize(S->done));
@@ -174,7 +182,7 @@ extern "C" int pb_mle_fit(size_t n, int box, const float* spots, double eps, int
         busy[s] = true;
         done_spots[s] = first + m;
     }
-    for (int s = 0; s < 2; s++)
+    for (int s = 0; s < kSlots; s++)
         if (busy[s]) PB_CUDA_CHECK(cudaEventSynchronize(sl[s]->done));
     if (progress) *progress = (long long)n;
     return PB_OK;
