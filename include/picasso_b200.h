@@ -189,6 +189,17 @@ int pb_rcc_windows_dev(int n_pairs, const int* d_pair_i, const int* d_pair_j, in
                        const void* d_spectra, int Y0, int X0, int H, int W, float* d_windows,
                        int batch, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Fused front end of postprocess.undrift (picasso/postprocess.py:2903-2961 = segment
+ * :2846-2900 + imageprocess.rcc :160-217): segment images are rendered on the device
+ * (oversampling 1, full FOV, blur "gaussian", min_blur_width as given) from localisations
+ * grouped by segment -- segment i owns [seg_start[i], seg_start[i+1]) of x/y/lpx/lpy --
+ * and cross-correlated without leaving the GPU.  Outputs as pb_rcc_windows; segments_out
+ * (n_seg, Y, X) float32 is optional. */
+int pb_undrift_windows(int n_seg, const long long* seg_start, const float* x, const float* y,
+                       const float* lpx, const float* lpy, int Y, int X, double min_blur_width,
+                       int Y0, int X0, int H, int W, float* windows, double* sums,
+                       float* segments_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,8 +60,8 @@ extern "C" int pb_host_free(void* ptr) {
 }
 
 // ---- cached device workspaces (per device, per slot) ----------------------
-// The host-buffer entry points stream chunks through two slots; the device
-// buffers are kept between calls (cudaMalloc costs ~1 ms per 100 MB).
+// The host-buffer entry points stream chunks through kSlots slots (own stream each);
+// the device buffers are kept between calls (cudaMalloc costs ~1 ms per 100 MB).
 namespace {
 struct Slot {
     void* buf = nullptr;

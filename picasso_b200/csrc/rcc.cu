@@ -222,3 +222,81 @@ extern "C" int pb_rcc_windows(int n_seg, int Y, int X, const float* segments, in
     if (e != cudaSuccess) { pb_set_error("pb_rcc_windows: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
     return rc;
 }
+
+// Fused undrift front end (postprocess.undrift :2903-2961 = segment :2846-2900 + rcc
+// :160-217): the segment images are rendered ON THE DEVICE straight into the segment
+// stack (no host round trip of n_seg x Y x X images), then spectra and pair windows as in
+// pb_rcc_windows.  Localisations arrive grouped by segment: segment i owns
+// [seg_start[i], seg_start[i+1]) of x/y/lpx/lpy.  Rendering parameters are those of
+// postprocess.segment: oversampling 1, full field of view, blur "gaussian" (mode 1).
+extern "C" int pb_undrift_windows(int n_seg, const long long* seg_start, const float* x,
+                                  const float* y, const float* lpx, const float* lpy, int Y, int X,
+                                  double min_blur_width, int Y0, int X0, int H, int W,
+                                  float* windows, double* sums, float* segments_out /*nullable*/) {
+    if (n_seg < 1) return PB_OK;
+    if (!seg_start || !sums || (n_seg > 1 && !windows)) { pb_set_error("pb_undrift_windows: null pointer"); return PB_ERR_INVALID; }
+    if (Y < 1 || X < 1 || H < 1 || W < 1 || Y0 < 0 || X0 < 0 || Y0 + H > Y || X0 + W > X) {
+        pb_set_error("pb_undrift_windows: bad window");
+        return PB_ERR_INVALID;
+    }
+    const size_t n_locs = (size_t)seg_start[n_seg];
+    const size_t img = (size_t)Y * X, spec = (size_t)Y * (X / 2 + 1);
+    const int n_pairs = n_seg * (n_seg - 1) / 2;
+    int batch = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)1 << 30) / (spec * 8 + img * 4)));
+    batch = std::max(1, std::min(batch, std::max(n_pairs, 1)));
+    size_t max_seg = 0;
+    for (int i = 0; i < n_seg; i++) max_seg = std::max<size_t>(max_seg, (size_t)(seg_start[i + 1] - seg_start[i]));
+    const size_t rws = pb_render_workspace_bytes(max_seg, Y, X);
+    const size_t wsb = std::max((size_t)batch * (spec * 8 + img * 4), rws);
+    float *dseg = nullptr, *dwin = nullptr, *dx = nullptr, *dy = nullptr, *dlx = nullptr, *dly = nullptr;
+    void *dspec = nullptr, *dws = nullptr;
+    double* dsum = nullptr;
+    unsigned long long* dcnt = nullptr;
+    int *dpi = nullptr, *dpj = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t err) { if (err != cudaSuccess && e == cudaSuccess) e = err; };
+    const size_t nb = std::max<size_t>(n_locs, 1) * 4;
+    ok(cudaMalloc(&dseg, n_seg * img * 4));
+    ok(cudaMalloc(&dspec, n_seg * spec * 8));
+    ok(cudaMalloc(&dsum, n_seg * 8));
+    ok(cudaMalloc(&dcnt, 8));
+    ok(cudaMalloc(&dws, wsb));
+    ok(cudaMalloc(&dwin, std::max<size_t>(1, (size_t)n_pairs * H * W * 4)));
+    ok(cudaMalloc(&dpi, std::max(1, n_pairs) * 4));
+    ok(cudaMalloc(&dpj, std::max(1, n_pairs) * 4));
+    ok(cudaMalloc(&dx, nb)); ok(cudaMalloc(&dy, nb)); ok(cudaMalloc(&dlx, nb)); ok(cudaMalloc(&dly, nb));
+    int rc = PB_OK;
+    if (e == cudaSuccess) {
+        if (n_locs) {
+            ok(cudaMemcpy(dx, x, n_locs * 4, cudaMemcpyHostToDevice));
+            ok(cudaMemcpy(dy, y, n_locs * 4, cudaMemcpyHostToDevice));
+            ok(cudaMemcpy(dlx, lpx, n_locs * 4, cudaMemcpyHostToDevice));
+            ok(cudaMemcpy(dly, lpy, n_locs * 4, cudaMemcpyHostToDevice));
+        }
+        for (int i = 0; i < n_seg && rc == PB_OK && e == cudaSuccess; i++) {
+            const size_t a0 = (size_t)seg_start[i], m = (size_t)(seg_start[i + 1] - seg_start[i]);
+            rc = pb_render_dev(m, dx + a0, dy + a0, dlx + a0, dly + a0, 1.0, 0.0, 0.0, (double)Y,
+                               (double)X, min_blur_width, 1, dseg + (size_t)i * img, Y, X, dcnt, dws,
+                               wsb, nullptr);
+        }
+        std::vector<int> pi, pj;
+        for (int i = 0; i < n_seg - 1; i++)
+            for (int j = i + 1; j < n_seg; j++) { pi.push_back(i); pj.push_back(j); }
+        if (n_pairs) {
+            ok(cudaMemcpy(dpi, pi.data(), n_pairs * 4, cudaMemcpyHostToDevice));
+            ok(cudaMemcpy(dpj, pj.data(), n_pairs * 4, cudaMemcpyHostToDevice));
+        }
+        if (e == cudaSuccess && rc == PB_OK) rc = pb_rcc_spectra_dev(n_seg, Y, X, dseg, dspec, dsum, nullptr);
+        if (e == cudaSuccess && rc == PB_OK && n_pairs)
+            rc = pb_rcc_windows_dev(n_pairs, dpi, dpj, Y, X, dspec, Y0, X0, H, W, dwin, batch, dws, wsb, nullptr);
+        if (e == cudaSuccess && rc == PB_OK) {
+            ok(cudaMemcpy(sums, dsum, n_seg * 8, cudaMemcpyDeviceToHost));
+            if (n_pairs) ok(cudaMemcpy(windows, dwin, (size_t)n_pairs * H * W * 4, cudaMemcpyDeviceToHost));
+            if (segments_out) ok(cudaMemcpy(segments_out, dseg, n_seg * img * 4, cudaMemcpyDeviceToHost));
+        }
+    }
+    cudaFree(dseg); cudaFree(dspec); cudaFree(dsum); cudaFree(dcnt); cudaFree(dws); cudaFree(dwin);
+    cudaFree(dpi); cudaFree(dpj); cudaFree(dx); cudaFree(dy); cudaFree(dlx); cudaFree(dly);
+    if (e != cudaSuccess) { pb_set_error("pb_undrift_windows: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    return rc;
+}

@@ -21,6 +21,9 @@ def _declare(l):
     vp, i32 = C.c_void_p, C.c_int
     l.pb_rcc_windows.argtypes = [i32, i32, i32, vp, i32, i32, i32, i32, vp, vp]
     l.pb_rcc_windows.restype = i32
+    l.pb_undrift_windows.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, C.c_double, i32, i32, i32,
+                                     i32, vp, vp, vp]
+    l.pb_undrift_windows.restype = i32
     l._rcc_declared = True
 
 
@@ -110,38 +113,79 @@ def get_image_shift(imageA, imageB, box: int, roi: int | None = None, display: b
     return _shift_from_window(win[0].astype(np.float64), Y, X, Y_, X_, box)
 
 
+def _rcc_from_windows(win, sums, Y, X, Y_, X_, callback):
+    """Pairwise shifts from the correlation windows -> minimize_shifts (the loop body of the
+    reference's rcc, imageprocess.py:191-217)."""
+    n_segments = len(sums)
+    shifts_x = np.zeros((n_segments, n_segments))
+    shifts_y = np.zeros((n_segments, n_segments))
+    n_pairs = int(n_segments * (n_segments - 1) / 2)
+    bar = None
+    if callback is None:
+        from tqdm import tqdm
+
+        bar = tqdm(total=n_pairs, desc="Correlating image pairs", unit="pairs")
+    else:
+        callback(0)
+    flag = 0
+    for i in range(n_segments - 1):
+        for j in range(i + 1, n_segments):
+            if sums[i] == 0 or sums[j] == 0:
+                sy, sx = 0, 0
+            else:
+                sy, sx = _shift_from_window(win[flag].astype(np.float64), Y, X, Y_, X_, 5)
+            shifts_y[i, j], shifts_x[i, j] = sy, sx
+            flag += 1
+            if bar is not None:
+                bar.update()
+            else:
+                callback(flag)
+    if bar is not None:
+        bar.close()
+    return lib.minimize_shifts(shifts_x, shifts_y)
+
+
 def rcc(segments, max_shift: float | None = None, callback: Callable[[int], None] | None = None):
     """Redundant cross-correlation over all segment pairs (reference
     imageprocess.py:160-217); returns ``lib.minimize_shifts(shifts_x, shifts_y)`` =
     ``(shift_y, shift_x)`` per segment.  ``callback`` is called with 0..n_pairs."""
     segments = np.asarray(segments)
     n_segments = len(segments)
-    shifts_x = np.zeros((n_segments, n_segments))
-    shifts_y = np.zeros((n_segments, n_segments))
-    if callback is not None:
-        callback(0)
-    bar = None
-    n_pairs = int(n_segments * (n_segments - 1) / 2)
-    if callback is None:
-        from tqdm import tqdm
+    if n_segments < 2:
+        if callback is not None:
+            callback(0)
+        z = np.zeros(max(n_segments, 1))
+        return lib.minimize_shifts(np.zeros((n_segments, n_segments)), np.zeros((n_segments, n_segments))) \
+            if n_segments else (z[:0], z[:0])
+    win, sums, (Y_, X_) = _windows(segments, max_shift)
+    _, Y, X = segments.shape
+    return _rcc_from_windows(win, sums, Y, X, Y_, X_, callback)
 
-        bar = tqdm(total=n_pairs, desc="Correlating image pairs", unit="pairs")
-    if n_pairs:
-        win, sums, (Y_, X_) = _windows(segments, max_shift)
-        _, Y, X = segments.shape
-        flag = 0
-        for i in range(n_segments - 1):
-            for j in range(i + 1, n_segments):
-                if sums[i] == 0 or sums[j] == 0:
-                    sy, sx = 0, 0
-                else:
-                    sy, sx = _shift_from_window(win[flag].astype(np.float64), Y, X, Y_, X_, 5)
-                shifts_y[i, j], shifts_x[i, j] = sy, sx
-                flag += 1
-                if bar is not None:
-                    bar.update()
-                else:
-                    callback(flag)
-    if bar is not None:
-        bar.close()
-    return lib.minimize_shifts(shifts_x, shifts_y)
+
+def _rcc_of_locs(locs, info, bounds, min_blur_width, max_shift, callback):
+    """Fused device path used by postprocess.undrift: render the segment images on the GPU
+    and cross-correlate them there (same kernels as segment() + rcc(), no host round trip
+    of the (n_seg, Y, X) image stack)."""
+    l = _lib.load()
+    _declare(l)
+    _lib.require_gpu()
+    Y, X = info[0]["Height"], info[0]["Width"]
+    n_seg = len(bounds) - 1
+    frames = locs["frame"].to_numpy()
+    # stable grouping by segment; frames outside [bounds[0], bounds[-1]) are dropped
+    seg_of = np.searchsorted(bounds, frames, side="right") - 1
+    keep = (frames >= bounds[0]) & (frames < bounds[-1])
+    idx = np.flatnonzero(keep)
+    idx = idx[np.argsort(seg_of[idx], kind="stable")]
+    counts = np.bincount(seg_of[idx], minlength=n_seg)[:n_seg]
+    seg_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    take = lambda c: np.ascontiguousarray(locs[c].to_numpy()[idx], dtype=np.float32)
+    x, y, lpx, lpy = take("x"), take("y"), take("lpx"), take("lpy")
+    Y_, X_, H, W = _crop_geometry(Y, X, max_shift)
+    n_pairs = n_seg * (n_seg - 1) // 2
+    win = np.zeros((n_pairs, H, W), dtype=np.float32)
+    sums = np.zeros(n_seg, dtype=np.float64)
+    _lib.check(l.pb_undrift_windows(n_seg, _lib.ptr(seg_start), _lib.ptr(x), _lib.ptr(y),
+                                    _lib.ptr(lpx), _lib.ptr(lpy), Y, X, float(min_blur_width),
+                                    Y_, X_, H, W, _lib.ptr(win), _lib.ptr(sums), None))
+    return _rcc_from_windows(win, sums, Y, X, Y_, X_, callback)

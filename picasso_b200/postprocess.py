@@ -93,10 +93,17 @@ def undrift(locs: pd.DataFrame, info, segmentation: int, display: bool = True,
     from scipy import interpolate
 
     locs = locs.copy()
-    bounds, segments = segment(locs, info, segmentation,
-                               {"blur_method": "gaussian", "min_blur_width": 1},
-                               segmentation_callback)
-    shift_y, shift_x = imageprocess.rcc(segments, 32, rcc_callback)
+    # same work as segment(..., blur_method="gaussian", min_blur_width=1) followed by
+    # imageprocess.rcc(segments, 32), but the segment images never leave the GPU
+    n_frames = info[0]["Frames"]
+    n_seg = n_segments(info, segmentation)
+    bounds = np.linspace(0, n_frames - 1, n_seg + 1, dtype=np.uint32)
+    if segmentation_callback is not None:
+        for i in range(n_seg + 1):
+            segmentation_callback(i)
+    if rcc_callback is None:
+        rcc_callback = lambda _i: None
+    shift_y, shift_x = imageprocess._rcc_of_locs(locs, info, bounds, 1, 32, rcc_callback)
     t = (bounds[1:] + bounds[:-1]) / 2
     drift_x_pol = interpolate.InterpolatedUnivariateSpline(t, shift_x, k=3)
     drift_y_pol = interpolate.InterpolatedUnivariateSpline(t, shift_y, k=3)

@@ -112,3 +112,19 @@ def test_apply_drift_and_minimize_shifts():
             sx[i, j] = true[j] - true[i]
     y, x = lib.minimize_shifts(sx, sy)
     np.testing.assert_allclose(x, true, atol=1e-9)
+
+
+def test_fused_undrift_equals_segment_plus_rcc(problem):
+    """postprocess.undrift renders the segments on the device; the public two-step path
+    (segment() -> rcc()) must give the same shifts."""
+    locs, info = problem
+    bounds, segs = postprocess.segment(locs, info, 100, {"blur_method": "gaussian",
+                                                         "min_blur_width": 1}, lambda i: None)
+    sy, sx = imageprocess.rcc(segs, 32, lambda i: None)
+    fy, fx = imageprocess._rcc_of_locs(locs, info, bounds, 1, 32, lambda i: None)
+    np.testing.assert_allclose(fy, sy, atol=2e-4)
+    np.testing.assert_allclose(fx, sx, atol=2e-4)
+    seg_cb, rcc_cb = [], []
+    postprocess.undrift(locs, info, 100, display=False, segmentation_callback=seg_cb.append,
+                        rcc_callback=rcc_cb.append)
+    assert seg_cb == list(range(9)) and rcc_cb == list(range(29))
