@@ -84,13 +84,103 @@ def _gauss_peak_fit(window):
     return popt[1], popt[2]
 
 
-def _shift_from_window(XCorr, Y, X, Y_, X_, box):
-    """arg-max, fit-window cut-out and peak fit (reference imageprocess.py:103-157)."""
+def _gauss_peak_fit_batch(windows, max_iter: int = 60):
+    """Vectorised Levenberg-Marquardt fit of the same model / start values / bounds as
+    ``_gauss_peak_fit`` for a stack of (P, k, k) windows at once (RCC fits n(n-1)/2 peaks;
+    19 900 scipy ``curve_fit`` calls would cost more than all the FFTs on the GPU).
+
+    Returns ``(xc, yc, ok)``; ``ok[p]`` is False where the batched solver did not converge
+    to an interior optimum (a bound active, singular normal equations, no convergence) --
+    the caller re-fits those windows with scipy's bounded ``curve_fit`` exactly like the
+    reference.  Both solvers minimise the same convex-near-the-peak least-squares problem
+    to ~1e-8, so converged fits agree far below the 1e-3 px parity bar (tests/test_peakfit_cpu.py).
+    """
+    w = np.asarray(windows, dtype=np.float64)
+    P, k, _ = w.shape
+    h = k // 2
+    yy, xx = np.mgrid[-h:h + 1, -h:h + 1]
+    xx = xx.ravel()[None, :].astype(np.float64)
+    yy = yy.ravel()[None, :].astype(np.float64)
+    d = w.reshape(P, k * k)
+    p = np.stack([d.max(1), np.zeros(P), np.zeros(P), np.ones(P), d.min(1)], 1)   # a xc yc s b
+    lam = np.full(P, 1e-3)
+
+    def model_jac(p):
+        a, xc, yc, s, b = (p[:, i:i + 1] for i in range(5))
+        dx, dy = xx - xc, yy - yc
+        r2 = dx * dx + dy * dy
+        E = np.exp(-0.5 * r2 / (s * s))
+        m = a * E + b
+        J = np.stack([E, a * E * dx / (s * s), a * E * dy / (s * s), a * E * r2 / (s ** 3),
+                      np.ones_like(E)], 2)
+        return m, J
+
+    m, J = model_jac(p)
+    res = d - m
+    cost = (res * res).sum(1)
+    active = np.ones(P, bool)
+    converged = np.zeros(P, bool)
+    eye = np.eye(5)[None]
+    for _ in range(max_iter):
+        if not active.any():
+            break
+        idx = np.flatnonzero(active)
+        Ja, ra = J[idx], res[idx]
+        JTJ = np.einsum("pij,pik->pjk", Ja, Ja)
+        g = np.einsum("pij,pi->pj", Ja, ra)
+        A = JTJ + lam[idx, None, None] * (eye * np.maximum(np.einsum("pjj->pj", JTJ), 1e-300)[:, None, :])
+        try:
+            step = np.linalg.solve(A, g[:, :, None])[:, :, 0]
+        except np.linalg.LinAlgError:
+            step = np.zeros_like(g)
+            for q in range(len(idx)):
+                try:
+                    step[q] = np.linalg.solve(A[q], g[q])
+                except np.linalg.LinAlgError:
+                    active[idx[q]] = False
+        trial = p[idx] + step
+        trial[:, 0] = np.maximum(trial[:, 0], 0.0)      # bounds of the reference's curve_fit
+        trial[:, 3] = np.maximum(trial[:, 3], 1e-12)
+        trial[:, 4] = np.maximum(trial[:, 4], 0.0)
+        with np.errstate(over="ignore", invalid="ignore"):
+            mt, Jt = model_jac(trial)
+            rt = d[idx] - mt
+            ct = (rt * rt).sum(1)
+        better = np.isfinite(ct) & (ct <= cost[idx])
+        bi = idx[better]
+        small = np.abs(step[better]).max(1) < 1e-10 * (1.0 + np.abs(p[bi]).max(1))
+        flat = (cost[bi] - ct[better]) <= 1e-14 * (cost[bi] + 1e-300)
+        p[bi] = trial[better]
+        J[bi], res[bi], cost[bi] = Jt[better], rt[better], ct[better]
+        lam[bi] = np.maximum(lam[bi] * 0.3, 1e-12)
+        done = bi[small | flat]
+        converged[done] = True
+        active[done] = False
+        wi = idx[~better]
+        lam[wi] *= 10.0
+        stuck = wi[lam[wi] > 1e12]
+        active[stuck] = False
+    interior = (p[:, 0] > 0) & (p[:, 4] > 0) & (p[:, 3] > 1e-6)
+    ok = converged & interior & np.isfinite(p).all(1)
+    return p[:, 1], p[:, 2], ok
+
+
+def _window_geometry(XCorr, box):
+    """arg-max and fit-window cut-out of one correlation image (imageprocess.py:103-116):
+    returns (y_max, x_max, FitROI or None when the window touches the crop edge)."""
     fit_X = int(box / 2)
     y_max_, x_max_ = np.unravel_index(XCorr.argmax(), XCorr.shape)
     FitROI = XCorr[y_max_ - fit_X: y_max_ + fit_X + 1, x_max_ - fit_X: x_max_ + fit_X + 1]
     dims = FitROI.shape
     if 0 in dims or dims[0] != dims[1]:
+        return y_max_, x_max_, None
+    return y_max_, x_max_, FitROI
+
+
+def _shift_from_window(XCorr, Y, X, Y_, X_, box):
+    """arg-max, fit-window cut-out and peak fit (reference imageprocess.py:103-157)."""
+    y_max_, x_max_, FitROI = _window_geometry(XCorr, box)
+    if FitROI is None:
         xc, yc = 0, 0
     else:
         xc, yc = _gauss_peak_fit(FitROI)
@@ -115,7 +205,8 @@ def get_image_shift(imageA, imageB, box: int, roi: int | None = None, display: b
 
 def _rcc_from_windows(win, sums, Y, X, Y_, X_, callback):
     """Pairwise shifts from the correlation windows -> minimize_shifts (the loop body of the
-    reference's rcc, imageprocess.py:191-217)."""
+    reference's rcc, imageprocess.py:191-217).  The 5x5 peak fits of all pairs are done in
+    one vectorised pass; windows it cannot settle go through scipy's ``curve_fit``."""
     n_segments = len(sums)
     shifts_x = np.zeros((n_segments, n_segments))
     shifts_y = np.zeros((n_segments, n_segments))
@@ -127,19 +218,39 @@ def _rcc_from_windows(win, sums, Y, X, Y_, X_, callback):
         bar = tqdm(total=n_pairs, desc="Correlating image pairs", unit="pairs")
     else:
         callback(0)
-    flag = 0
-    for i in range(n_segments - 1):
-        for j in range(i + 1, n_segments):
-            if sums[i] == 0 or sums[j] == 0:
-                sy, sx = 0, 0
-            else:
-                sy, sx = _shift_from_window(win[flag].astype(np.float64), Y, X, Y_, X_, 5)
-            shifts_y[i, j], shifts_x[i, j] = sy, sx
-            flag += 1
-            if bar is not None:
-                bar.update()
-            else:
-                callback(flag)
+    pairs = [(i, j) for i in range(n_segments - 1) for j in range(i + 1, n_segments)]
+    geo, rois, which = [], [], []
+    for flag, (i, j) in enumerate(pairs):
+        if sums[i] == 0 or sums[j] == 0:
+            geo.append(None)
+            continue
+        ym, xm, roi = _window_geometry(win[flag].astype(np.float64), 5)
+        geo.append((ym, xm, roi is not None))
+        if roi is not None:
+            rois.append(roi)
+            which.append(flag)
+    if rois and rois[0].shape == (5, 5):
+        bx, by, ok = _gauss_peak_fit_batch(np.stack(rois))
+    else:
+        bx = by = np.zeros(len(rois))
+        ok = np.zeros(len(rois), bool)
+    fitted = {}
+    for q, flag in enumerate(which):
+        fitted[flag] = (bx[q], by[q]) if ok[q] else _gauss_peak_fit(rois[q])
+    for flag, (i, j) in enumerate(pairs):
+        g = geo[flag]
+        if g is None or not g[2]:
+            sy, sx = 0, 0
+        else:
+            xc, yc = fitted[flag]
+            xc = xc + X_ + g[1] - np.floor(X / 2)
+            yc = yc + Y_ + g[0] - np.floor(Y / 2)
+            sy, sx = -yc, -xc
+        shifts_y[i, j], shifts_x[i, j] = sy, sx
+        if bar is not None:
+            bar.update()
+        else:
+            callback(flag + 1)
     if bar is not None:
         bar.close()
     return lib.minimize_shifts(shifts_x, shifts_y)

@@ -270,6 +270,37 @@ def stage_rcc(torch, small):
         "window_peak": float(ref.max())}), flush=True)
 
 
+def stage_undrift(torch, small):
+    """End-to-end postprocess.undrift through the Python API (host locs DataFrame in, drift
+    out): device-rendered segments + cuFFT RCC + batched host peak fits + spline."""
+    import warnings
+
+    from picasso_b200 import postprocess, testing
+
+    n_frames, Y, X, seg = (4000, 1024, 1024, 100) if small else (12000, 2048, 2048, 100)
+    locs, info, truth = testing.synthetic_drift_locs(n_frames, Y, X, n_clusters=3000,
+                                                     locs_per_frame=500, seed=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        postprocess.undrift(locs.iloc[:20000], [{**info[0], "Frames": 400}], 100, display=False,
+                            segmentation_callback=lambda i: None, rcc_callback=lambda i: None)
+        t0 = time.perf_counter()
+        drift, und = postprocess.undrift(locs, info, seg, display=False,
+                                         segmentation_callback=lambda i: None,
+                                         rcc_callback=lambda i: None)
+        t1 = time.perf_counter()
+    n_seg = postprocess.n_segments(info, seg)
+    err = []
+    for k, col in enumerate(("x", "y")):
+        est = drift[col].to_numpy() - drift[col].mean()
+        tru = truth[:, k] - truth[:, k].mean()
+        err.append(float(np.abs(est - tru).max()))
+    print(json.dumps({"stage": "postprocess.undrift end to end (Python API)", "frames": n_frames,
+                      "image": [Y, X], "n_locs": len(locs), "n_segments": n_seg,
+                      "n_pairs": n_seg * (n_seg - 1) // 2, "seconds": t1 - t0,
+                      "max_abs_drift_error_px_vs_injected": err}), flush=True)
+
+
 KERNEL_ONLY = "--kernel-only" in sys.argv
 
 if __name__ == "__main__":
@@ -279,4 +310,5 @@ if __name__ == "__main__":
     small = "--small" in sys.argv
     which = args or ["identify", "render", "rcc"]
     for w in which:
-        {"identify": stage_identify, "render": stage_render, "rcc": stage_rcc}[w](torch, small)
+        {"identify": stage_identify, "render": stage_render, "rcc": stage_rcc,
+         "undrift": stage_undrift}[w](torch, small)
