@@ -48,6 +48,9 @@ constexpr int kRedStride = 23;     // doubles per lane in the reduction scratch 
 #ifndef PB_MLE_LIBM_ERF
 #define PB_MLE_LIBM_ERF 0      // 1: CUDA libdevice erf(); 0: erf_from_gauss (shares the exp)
 #endif
+#ifndef PB_MLE_F32_PIXELS
+#define PB_MLE_F32_PIXELS 0    // 1: float32 per-pixel Newton sums (experiment, not the default:
+#endif                         //    trades ~0.1 % iteration-count parity for FP32-pipe throughput)
 #define PB_STR2(x) #x
 #define PB_STR(x) PB_STR2(x)
 #define PB_PIX_UNROLL _Pragma(PB_STR(unroll PB_MLE_PIX_UNROLL))
@@ -73,11 +76,12 @@ struct MleSmem {
     static constexpr int kRoiBytes = 2 * kTileSpots * PIX * 4;          // 2 TMA stages (f32)
     static constexpr int kDataBytes = ((S * PIX * 8 + 15) / 16) * 16;    // current spots as f64
     static constexpr int kFxBytes = ((S * kNFx * BOX * 8 + 15) / 16) * 16;
+    static constexpr int kFxfBytes = PB_MLE_F32_PIXELS ? S * 12 * BOX * 4 : 0;
     static constexpr int kRedBytes = 32 * kRedStride * 8;
     static constexpr int kSumBytes = S * 24 * 8;
     static constexpr int kBarBytes = 16;
     static constexpr int kPerWarp =
-        ((kRoiBytes + kDataBytes + kFxBytes + kRedBytes + kSumBytes + kBarBytes + 127) / 128) * 128;
+        ((kRoiBytes + kDataBytes + kFxBytes + kFxfBytes + kRedBytes + kSumBytes + kBarBytes + 127) / 128) * 128;
     static constexpr int kTotal = kPerWarp * kWarpsPerBlock;
 };
 
@@ -258,13 +262,14 @@ mle_fit_kernel(const MleArgs a) {
     float* roi = reinterpret_cast<float*>(wbase);                                   // [2][4*PIX]
     double* dspot = reinterpret_cast<double*>(wbase + SM::kRoiBytes) + grp * PIX;    // [PIX] f64
     double* fx = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kDataBytes) +
-                 grp * kNFx * BOX;                                                  // [13][BOX]
-    double* red = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kDataBytes +
-                                            SM::kFxBytes);                          // [32][23]
-    double* sums = reinterpret_cast<double*>(wbase + SM::kRoiBytes + SM::kDataBytes +
-                                             SM::kFxBytes + SM::kRedBytes) + grp * 24;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + SM::kRoiBytes + SM::kDataBytes +
-                                                 SM::kFxBytes + SM::kRedBytes + SM::kSumBytes);
+                 grp * kNFx * BOX;                                                  // [BOX][14]
+    constexpr int kOffF = SM::kRoiBytes + SM::kDataBytes + SM::kFxBytes;
+    float* fxf = reinterpret_cast<float*>(wbase + kOffF) + grp * 12 * BOX;          // [BOX][12]
+    constexpr int kOffR = kOffF + SM::kFxfBytes;
+    double* red = reinterpret_cast<double*>(wbase + kOffR);                         // [32][23]
+    double* sums = reinterpret_cast<double*>(wbase + kOffR + SM::kRedBytes) + grp * 24;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + kOffR + SM::kRedBytes + SM::kSumBytes);
+    (void)fxf;
 
     const long long n = a.n;
     const long long ntiles = (n + kTileSpots - 1) / kTileSpots;
@@ -499,6 +504,14 @@ mle_fit_kernel(const MleArgs a) {
                         c[F_G1PX] = gx1 * PSFx;
                         c[F_C1PX] = cx1 * PSFx;
                         c[F_C1G1] = cx1 * gx1;
+#if PB_MLE_F32_PIXELS
+                        float* cf32 = fxf + g * 12;
+                        cf32[0] = (float)((double)th[2] * PSFx); cf32[1] = (float)PSFx;
+                        cf32[2] = (float)cx1; cf32[3] = (float)cx2;
+                        cf32[4] = (float)gx1; cf32[5] = (float)gx2;
+                        cf32[6] = (float)(PSFx * PSFx); cf32[7] = (float)(cx1 * cx1);
+                        cf32[8] = (float)(gx1 * gx1); cf32[9] = (float)(gx1 * PSFx);
+#endif
                     }
                     __syncwarp();
                 }
@@ -513,6 +526,43 @@ mle_fit_kernel(const MleArgs a) {
                     // over its row and applies the row factors once per row. =====
                     double c0 = 0, cpx = 0, cc1 = 0, cc2 = 0, cg1 = 0, cg2 = 0;
                     double d0 = 0, dpx2 = 0, dc1 = 0, dg1 = 0, dgp = 0;
+#if PB_MLE_F32_PIXELS
+                    if (g < BOX) {
+                        const float* frow = sp + g * BOX;
+                        const float4* col = reinterpret_cast<const float4*>(fxf);
+                        const float PSFy_f = (float)PSFy, bg_f = (float)bg;
+                        float c0f = 0, cpxf = 0, cc1f = 0, cc2f = 0, cg1f = 0, cg2f = 0;
+                        float d0f = 0, dpx2f = 0, dc1f = 0, dg1f = 0, dgpf = 0;
+                        PB_PIX_UNROLL
+                        for (int i = 0; i < BOX; i++, col += 3) {
+                            const float4 f0 = col[0];    // N*px, px, c1, c2
+                            const float4 f1 = col[1];    // g1, g2, px^2, c1^2
+                            const float4 f2 = col[2];    // g1^2, g1*px, -, -
+                            const float model = fmaf(f0.x, PSFy_f, bg_f);
+                            const bool okm = model > 10e-3f;
+                            const float inv = __frcp_rn(model);
+                            const float t = frow[i] * inv;
+                            float cf = t - 1.0f, df = t * inv;
+                            cf = cf > 10e4f ? 10e4f : cf;
+                            df = df > 10e4f ? 10e4f : df;
+                            cf = okm ? cf : 0.0f;
+                            df = okm ? df : 0.0f;
+                            c0f += cf;
+                            cpxf = fmaf(cf, f0.y, cpxf);
+                            cc1f = fmaf(cf, f0.z, cc1f);
+                            cc2f = fmaf(cf, f0.w, cc2f);
+                            cg1f = fmaf(cf, f1.x, cg1f);
+                            cg2f = fmaf(cf, f1.y, cg2f);
+                            d0f += df;
+                            dpx2f = fmaf(df, f1.z, dpx2f);
+                            dc1f = fmaf(df, f1.w, dc1f);
+                            dg1f = fmaf(df, f2.x, dg1f);
+                            if constexpr (METHOD == 0) dgpf = fmaf(df, f2.y, dgpf);
+                        }
+                        c0 = c0f; cpx = cpxf; cc1 = cc1f; cc2 = cc2f; cg1 = cg1f; cg2 = cg2f;
+                        d0 = d0f; dpx2 = dpx2f; dc1 = dc1f; dg1 = dg1f; dgp = dgpf;
+                    }
+#else
                     if (g < BOX) {
                         const double* drow = dspot + g * BOX;
                         const double2* col = reinterpret_cast<const double2*>(fx);
@@ -549,6 +599,7 @@ mle_fit_kernel(const MleArgs a) {
                             if constexpr (METHOD == 0) dgp = fma(df, f4.y, dgp);
                         }
                     }
+#endif
                     const double Ncy1 = N * cy1, Ncy2 = N * cy2;
                     myred[0] = NPy * cc1;            myred[6] = NPy * cc2 - NPy * NPy * dc1;
                     myred[1] = Ncy1 * cpx;           myred[7] = Ncy2 * cpx - Ncy1 * Ncy1 * dpx2;

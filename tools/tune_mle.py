@@ -15,10 +15,12 @@ VDIR = os.path.join(ROOT, "picasso_b200", "_variants")
 CSRC = os.path.join(ROOT, "picasso_b200", "csrc")
 NVCC = "/usr/local/cuda/bin/nvcc"
 
-VARIANTS = {}
-for erf, unroll in itertools.product((0, 1), (1, 8)):
-    VARIANTS[f"b4_u{unroll}_{'libm' if erf else 'gauss'}erf"] = [
-        "-DPB_MLE_MINB=4", f"-DPB_MLE_PIX_UNROLL={unroll}", f"-DPB_MLE_LIBM_ERF={erf}"]
+VARIANTS = {
+    "default": [],
+    "b5": ["-DPB_MLE_MINB=5"],
+    "f32pixels": ["-DPB_MLE_F32_PIXELS=1"],
+    "f32pixels_b5": ["-DPB_MLE_F32_PIXELS=1", "-DPB_MLE_MINB=5"],
+}
 
 
 def build():
@@ -54,7 +56,7 @@ def run():
     n = 2_000_000
     dev = torch.device("cuda", 0)
     spots = bench.gen_spots_device(torch, n, 7, 1234, dev)
-    par = testing.synthetic_spots(20000, 7, seed=3)
+    par = testing.synthetic_spots(100000, 7, seed=3)
     oth, ocr, oll, oit = oracle.gaussmle(par, 0.001, 100, "sigmaxy", nthreads=os.cpu_count())
     dpar = torch.from_numpy(par).to(dev)
     for name in VARIANTS:
@@ -84,8 +86,9 @@ def run():
         pit = it[:len(par)].cpu().numpy(); pth = th[:len(par)].cpu().numpy()
         match = float((pit == oit).mean())
         rms = float(np.sqrt(((pth[:, :2] - oth[:, :2]).astype(np.float64) ** 2).mean()))
+        bit = float((pth.view(np.uint32) == oth.view(np.uint32)).all(1).mean())
         print(json.dumps({"variant": name, "ms": ms, "Mfits_per_s": n / ms / 1e3,
-                          "iter_match": match, "xy_rms": rms}), flush=True)
+                          "iter_match": match, "xy_rms": rms, "theta_bit_identical": bit}), flush=True)
 
 
 if __name__ == "__main__":
