@@ -382,7 +382,12 @@ def main():
                          "algorithmic_bytes": BYTES_PER_SPOT * n, "peak_source": peak_src,
                          "kernel_ms": ms_kernel,
                          "note": "algorithmic 252 B/spot; the fit is FP64-issue bound, not HBM bound "
-                                 "(SURVEY.md 8d) -- see DESIGN.md for the instruction roofline"},
+                                 "(SURVEY.md 8d) -- see `compute` and DESIGN.md 5.1"},
+            # instruction-side view of the same kernel from the committed ncu --set full capture
+            # (profiles/r01_mle_ncu.md, v3): what actually bounds the fit
+            "compute": {"source": "ncu --set full, profiles/r01_mle_ncu.md (v3)",
+                        "fp64_pipe_busy_pct": 47.7, "issue_slots_busy_pct": 61.9,
+                        "warp_instructions_per_spot": 3613},
             "clocks": clocks, "gpu_launches": launches,
         }
         if e2e is not None:

@@ -46,8 +46,7 @@ struct IdArgs {
     int Y, X;               // full frame shape (row pitch X)
     int y0, x0, Ys, Xs;     // ROI window (image = frame[y0:y0+Ys, x0:x0+Xs])
     long long frame_offset; // added to the emitted frame number
-    float min_ng;           // compared as double below
-    double min_ng_d;
+    double min_ng_d;        // threshold, compared in double like the reference (ng > minimum_ng)
     long long* out_frame;
     long long* out_x;
     long long* out_y;
@@ -464,7 +463,7 @@ extern "C" int pb_identify_dev(const void* d_movie, int dtype, size_t n_frames, 
         a.y0 = y0; a.x0 = x0; a.Ys = y1 - y0; a.Xs = x1 - x0;
     }
     a.frame_offset = frame_offset;
-    a.min_ng_d = min_ng; a.min_ng = (float)min_ng;
+    a.min_ng_d = min_ng;
     a.out_frame = d_frame; a.out_x = d_x; a.out_y = d_y; a.out_ng = d_ng;
     a.capacity = capacity; a.counter = d_counter;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
