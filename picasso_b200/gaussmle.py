@@ -164,3 +164,12 @@ def locs_from_fits(
     else:
         locs.sort_values(by=["frame"], kind="quicksort", inplace=True)
     return locs
+
+
+def sigma_uncertainty(sigma, sigma_orth, photons, bg):
+    """Standard error of the fitted sigma for the MLE Gaussian/Poisson model (Rieger &
+    Stallinga 2014 approximation; reference gaussmle.py:1040-1074)."""
+    sa2 = sigma ** 2 + 1 / 12
+    tau = (2 * np.pi * sa2 * bg) / photons
+    var = (sigma ** 2 / (4 * photons)) * (1 + 8 * tau + np.sqrt((8 * tau) / (1 + 2 * tau)))
+    return np.sqrt(var)

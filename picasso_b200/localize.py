@@ -240,6 +240,56 @@ def identify(movie, minimum_ng: float, box: int, *, roi=None, frame_bounds=None,
     return ids
 
 
+def identify_async(movie, minimum_ng: float, box: int, *, roi=None, frame_bounds=None):
+    """Start identification in the background (reference ``identify_async``,
+    localize.py:482-558): returns ``(current, futures)`` immediately; ``current[0]`` counts
+    the frames processed so far and reaches ``len(movie)`` when done;
+    ``identifications_from_futures(futures)`` gives the final table.  The reference fans
+    frames out to a thread pool; here one worker thread streams frame chunks through the
+    GPU."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    lib = _lib_ready()
+    N = len(movie)
+    lo, hi = _frame_range(N, frame_bounds)
+    roi_arr = _roi_array(roi)
+    current = [0]
+
+    def _work():
+        out = []
+        step = _frames_per_chunk(movie) if N else 1
+        f = 0
+        while f < N:
+            f1 = min(N, f + step)
+            a, b = max(f, lo), min(f1, hi + 1)
+            if a < b:
+                fr, xs, ys, ng = _identify_chunk(lib, _movie_chunk(movie, a, b), a, minimum_ng, box,
+                                                 roi_arr)
+                out.append(pd.DataFrame({"frame": fr.astype(int), "x": xs.astype(int),
+                                         "y": ys.astype(int),
+                                         "net_gradient": ng.astype(np.float32)}))
+            current[0] = f1
+            f = f1
+        if not out:
+            out.append(_empty_ids())
+        return out
+
+    executor = ThreadPoolExecutor(1)
+    futures = [executor.submit(_work)]
+    executor.shutdown(wait=False)
+    return current, futures
+
+
+def identifications_from_futures(futures) -> pd.DataFrame:
+    """Combine the results of ``identify_async`` (reference localize.py:457-479)."""
+    from itertools import chain
+
+    ids_list = list(chain(*[f.result() for f in futures]))
+    ids = pd.concat(ids_list, ignore_index=True)
+    ids.sort_values(by="frame", kind="quicksort", inplace=True)
+    return ids
+
+
 def get_spots(movie, identifications: pd.DataFrame, box: int, camera_info: dict):
     """Cut ``box x box`` ROIs around the identifications and convert to photons.
 

@@ -169,3 +169,19 @@ def test_fit2d_argument_contract():
     assert localize.fit2D(movie, [], cam, ids, 7, abort_callback=lambda: True)[0] is None
     with pytest.raises(NotImplementedError):
         localize.fit2D(movie, [], cam, ids, 7, fitting_method="avg")
+
+
+def test_identify_async_matches_identify():
+    import time
+
+    movie = testing.synthetic_movie(9, 64, 64, emitters_per_frame=5, seed=8)
+    ids = localize.identify(movie, 5000, 7, return_info=False)
+    current, futures = localize.identify_async(movie, 5000, 7)
+    t0 = time.time()
+    while current[0] < len(movie) and time.time() - t0 < 60:
+        time.sleep(0.01)
+    assert current[0] == len(movie)
+    ids2 = localize.identifications_from_futures(futures)
+    a = sorted(zip(ids["frame"], ids["y"], ids["x"]))
+    b = sorted(zip(ids2["frame"], ids2["y"], ids2["x"]))
+    assert a == b and len(a) > 10
