@@ -24,6 +24,8 @@
 //
 // No tensor cores: 2*n_par sums over box^2 pixels is not a dense contraction.
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "pb_common.cuh"
 
@@ -65,6 +67,7 @@ struct MleArgs {
     float* logliks;       // (n,)
     int* iterations;      // (n,)
     int* status;          // (n,) nullable
+    unsigned long long* tile_counter;   // dynamic tile scheduler (zeroed before launch)
 };
 
 constexpr int kNFx = 14;          // per-column x-factors kept in shared memory (12 used)
@@ -273,8 +276,17 @@ mle_fit_kernel(const MleArgs a) {
 
     const long long n = a.n;
     const long long ntiles = (n + kTileSpots - 1) / kTileSpots;
-    const long long wstride = (long long)gridDim.x * kWarpsPerBlock;
-    long long tile = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    // Dynamic tile scheduler: every warp claims its next 4-spot tile with one atomic (one
+    // per ~100 us of work).  CTAs that become resident late -- e.g. because a concurrent NCCL
+    // all-gather of the previous step's outputs holds a few SMs -- simply claim fewer tiles,
+    // so collectives overlap the fit without stretching its tail.
+    auto claim = [&]() -> long long {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
+        return (long long)__shfl_sync(0xffffffffu, t, 0);
+    };
+    long long tile = claim();
+    long long next_tile = (tile < ntiles) ? claim() : ntiles;
     const bool tma_ok = ((reinterpret_cast<uintptr_t>(a.spots) & 15) == 0);
     constexpr unsigned kTileBytes = kTileSpots * PIX * 4;
 
@@ -309,11 +321,11 @@ mle_fit_kernel(const MleArgs a) {
     if (tile < ntiles) cur_tma = issue(tile, 0);
     int stage = 0;
 
-    for (; tile < ntiles; tile += wstride, stage ^= 1) {
+    for (; tile < ntiles; stage ^= 1) {
         // prefetch the next tile into the other stage (it was fully consumed
         // before the __syncwarp at the end of the previous trip)
         bool next_tma = false;
-        if (tile + wstride < ntiles) next_tma = issue(tile + wstride, stage ^ 1);
+        if (next_tile < ntiles) next_tma = issue(next_tile, stage ^ 1);
         if (cur_tma) {
             if (stage == 0) { pb_mbar_wait(&bars[0], phase0); phase0 ^= 1; }
             else            { pb_mbar_wait(&bars[1], phase1); phase1 ^= 1; }
@@ -793,7 +805,26 @@ mle_fit_kernel(const MleArgs a) {
         }   // sub
         __syncwarp();   // everyone is done reading this stage before it is refilled
         cur_tma = next_tma;
+        tile = next_tile;
+        next_tile = (tile < ntiles) ? claim() : ntiles;
     }
+}
+
+// A ring of zero-initialised tile counters per device: launches on different streams may be
+// in flight together (the host pipeline keeps three), so each launch takes the next slot and
+// clears it on its own stream.
+constexpr int kCounterSlots = 64;
+int next_tile_counter(int dev, cudaStream_t stream, unsigned long long** out) {
+    static std::mutex mu;
+    static std::vector<unsigned long long*> rings;
+    static std::vector<unsigned> cursor;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)rings.size() <= dev) { rings.resize(dev + 1, nullptr); cursor.resize(dev + 1, 0); }
+    if (!rings[dev]) PB_CUDA_CHECK(cudaMalloc(&rings[dev], kCounterSlots * sizeof(unsigned long long)));
+    unsigned long long* slot = rings[dev] + (cursor[dev]++ % kCounterSlots);
+    PB_CUDA_CHECK(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), stream));
+    *out = slot;
+    return PB_OK;
 }
 
 template <int BOX, int G, int METHOD>
@@ -811,12 +842,17 @@ int launch_mle(const MleArgs& a, cudaStream_t stream) {
         pb_set_error("mle kernel does not fit on an SM (box=%d)", BOX);
         return PB_ERR_CUDA;
     }
+    MleArgs args = a;
+    {
+        int rc = next_tile_counter(dev, stream, &args.tile_counter);
+        if (rc != PB_OK) return rc;
+    }
     const long long ntiles = (a.n + kTileSpots - 1) / kTileSpots;
     long long want = (ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
     long long cap = (long long)num_sms * blocks_per_sm;   // persistent: one wave
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, kWarpsPerBlock * 32, SM::kTotal, stream>>>(a);
+    kern<<<grid, kWarpsPerBlock * 32, SM::kTotal, stream>>>(args);
     g_pb_launches++;
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
@@ -858,7 +894,7 @@ extern "C" int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double ep
     }
     if (max_it < 0) max_it = 0;
     MleArgs a{d_spots, (long long)n, eps, max_it, d_thetas, d_crlbs, d_logliks, d_iterations,
-              d_status};
+              d_status, nullptr};
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     return method == 1 ? dispatch_box<1>(box, a, s) : dispatch_box<0>(box, a, s);
 }
