@@ -158,6 +158,17 @@ def gen_testdata(ref):
                lq_thetas=lq)
     for c in locs.columns:
         out[f"locs_{c}"] = locs[c].to_numpy()
+    for em in (False, True):
+        lqlocs = glq.locs_from_fits(ids, lq, 7, em)
+        for c in lqlocs.columns:
+            out[f"lqlocs_em{int(em)}_{c}"] = lqlocs[c].to_numpy()
+    gp = np.stack([lq[:, 2], lq[:, 0] + 3, lq[:, 1] + 3, lq[:, 4], lq[:, 5], lq[:, 3]], 1)
+    gplocs = glq.locs_from_fits_gpufit(ids, gp, 7, False)
+    for c in gplocs.columns:
+        out[f"gplocs_{c}"] = gplocs[c].to_numpy()
+    ids_nid = ids.copy(); ids_nid["n_id"] = np.arange(len(ids))[::-1].astype(np.int64)
+    nlocs = gm.locs_from_fits(ids_nid, th, cr, ll, it, 7)
+    out["nidlocs_n_id"] = nlocs["n_id"].to_numpy(); out["nidlocs_x"] = nlocs["x"].to_numpy()
     for bm in (None, "gaussian", "gaussian_iso"):
         n, img = rnd.render(locs, info, oversampling=20, blur_method=bm)
         out[f"render_{bm}_n"] = np.array(n); out[f"render_{bm}_image"] = img
