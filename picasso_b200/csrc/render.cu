@@ -158,6 +158,7 @@ __global__ void render_splat_kernel(const RenderArgs a) {
 
 // ---- tiled path ---------------------------------------------------------------
 constexpr int kTile = 64;                 // tile edge in image pixels (16 KB of smem)
+constexpr int kSizeClasses = 4;           // bins per tile: by blur width (window size)
 
 // pass 1: tile id per localisation (-1 = not in view) + histogram of tile sizes
 __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restrict__ tile_of,
@@ -173,7 +174,11 @@ __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restri
             int px = (int)(a.os * (xv - a.x_min)), py = (int)(a.os * (yv - a.y_min));
             px = min(max(px, 0), a.npx - 1);
             py = min(max(py, 0), a.npy - 1);
-            t = (py / kTile) * tiles_x + (px / kTile);
+            // bin = (tile, window-size class): threads of a warp then splat windows of similar
+            // size (a warp runs as long as its widest window: 3..11 px across at config 4)
+            const float sg = __fmul_rn(a.osf, fmaxf(fmaxf(a.lpx[k], a.lpy[k]), a.mbw));
+            const int cls = sg < 0.75f ? 0 : sg < 1.05f ? 1 : sg < 1.4f ? 2 : 3;
+            t = ((py / kTile) * tiles_x + (px / kTile)) * kSizeClasses + cls;
             atomicAdd(tile_count + t, 1u);
         }
         tile_of[k] = t;
@@ -247,7 +252,8 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
     __shared__ float acc[kTile * kTile];
     __shared__ float gxs[kMaxWin][256];
     const int tile = blockIdx.x;
-    const unsigned int first = start[tile], last = start[tile + 1];
+    // the tile's localisations: its kSizeClasses consecutive bins, narrow windows first
+    const unsigned int first = start[tile * kSizeClasses], last = start[(tile + 1) * kSizeClasses];
     if (first == last) return;
     const int ty0 = (tile / tiles_x) * kTile, tx0 = (tile % tiles_x) * kTile;
     for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) acc[q] = 0.0f;
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
 // Workspace (bytes) pb_render_dev needs for the tiled path; 0 => use the direct path.
 extern "C" size_t pb_render_workspace_bytes(size_t n, int n_pixel_y, int n_pixel_x) {
     const size_t tiles = (size_t)((n_pixel_y + kTile - 1) / kTile) * ((n_pixel_x + kTile - 1) / kTile);
-    return n * 20 + (tiles + 1) * 12 + 256;   // tile_of (4 B) + sorted float4 (16 B) per loc
+    return n * 20 + (tiles * kSizeClasses + 1) * 12 + 256;   // tile_of (4 B) + sorted float4 (16 B) per loc
 }
 
 extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
@@ -367,12 +373,13 @@ extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const
     float4* sorted = reinterpret_cast<float4*>(w);
     int* tile_of = reinterpret_cast<int*>(w + n * 16);
     unsigned int* tcount = reinterpret_cast<unsigned int*>(w + n * 20);
-    unsigned int* tstart = tcount + ntiles;
-    unsigned int* tcursor = tstart + ntiles + 1;
-    PB_CUDA_CHECK(cudaMemsetAsync(tcount, 0, ntiles * 4, s));
+    const long long nbins = ntiles * kSizeClasses;
+    unsigned int* tstart = tcount + nbins;
+    unsigned int* tcursor = tstart + nbins + 1;
+    PB_CUDA_CHECK(cudaMemsetAsync(tcount, 0, nbins * 4, s));
     int grid = (int)std::min<long long>(((long long)n + threads - 1) / threads, 148 * 16);
     render_bin_kernel<<<grid, threads, 0, s>>>(a, tiles_x, tile_of, tcount);
-    render_scan_kernel<<<1, 1024, 0, s>>>(tcount, tstart, tcursor, (int)ntiles);
+    render_scan_kernel<<<1, 1024, 0, s>>>(tcount, tstart, tcursor, (int)nbins);
     render_scatter_kernel<<<grid, threads, 0, s>>>(a, tile_of, tcursor, sorted);
     render_tiled_kernel<<<(unsigned)ntiles, 256, 0, s>>>(a, tiles_x, tstart, sorted);
     g_pb_launches += 4;
