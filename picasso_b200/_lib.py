@@ -32,8 +32,9 @@ def _declare(lib):
     lib.pb_host_free.argtypes = [vp]
     lib.pb_mle_fit.argtypes = [sz, i32, vp, f64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.pb_mle_fit_dev.argtypes = [sz, i32, vp, f64, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.pb_mle_set_impl.argtypes = [i32]
     for name in ("pb_set_device", "pb_synchronize", "pb_host_alloc", "pb_host_free",
-                 "pb_mle_fit", "pb_mle_fit_dev"):
+                 "pb_mle_fit", "pb_mle_fit_dev", "pb_mle_set_impl", "pb_mle_get_impl"):
         getattr(lib, name).restype = i32
 
 

@@ -25,6 +25,7 @@
 // No tensor cores: 2*n_par sums over box^2 pixels is not a dense contraction.
 #include <atomic>
 #include <mutex>
+#include <stdlib.h>
 #include <vector>
 
 #include "pb_common.cuh"
@@ -878,6 +879,38 @@ int dispatch_box(int box, const MleArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+// thread-per-spot path (mle_tps.cu)
+bool pb_mle_tps_supports(int box);
+int pb_mle_tps_fit(size_t n, int box, const float* d_spots, double eps, int max_it, int method,
+                   float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
+                   int* d_status, cudaStream_t stream, int pixel_f32);
+
+// Implementation selector: 0 = lane-group kernel (this file), 1 = thread-per-spot with float64
+// per-pixel sums, 2 = thread-per-spot with float32 per-pixel sums (default for box <= 13).
+// PB_MLE_IMPL in the environment sets the initial value.
+static std::atomic<int> g_mle_impl{-1};
+static int mle_impl() {
+    int v = g_mle_impl.load();
+    if (v < 0) {
+        v = 2;
+        if (const char* e = getenv("PB_MLE_IMPL")) {
+            const int w = atoi(e);
+            if (w >= 0 && w <= 2) v = w;
+        }
+        g_mle_impl.store(v);
+    }
+    return v;
+}
+extern "C" int pb_mle_set_impl(int impl) {
+    if (impl < 0 || impl > 2) {
+        pb_set_error("pb_mle_set_impl: impl must be 0, 1 or 2");
+        return PB_ERR_INVALID;
+    }
+    g_mle_impl.store(impl);
+    return PB_OK;
+}
+extern "C" int pb_mle_get_impl(void) { return mle_impl(); }
+
 // Device-pointer entry point, asynchronous on `stream`.  Declared in
 // include/picasso_b200.h.
 extern "C" int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double eps, int max_it,
@@ -896,5 +929,9 @@ extern "C" int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double ep
     MleArgs a{d_spots, (long long)n, eps, max_it, d_thetas, d_crlbs, d_logliks, d_iterations,
               d_status, nullptr};
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int impl = mle_impl();
+    if (impl != 0 && pb_mle_tps_supports(box))
+        return pb_mle_tps_fit(n, box, d_spots, eps, max_it, method, d_thetas, d_crlbs, d_logliks,
+                              d_iterations, d_status, s, impl == 2);
     return method == 1 ? dispatch_box<1>(box, a, s) : dispatch_box<0>(box, a, s);
 }

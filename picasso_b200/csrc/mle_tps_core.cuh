@@ -1,0 +1,671 @@
+// picasso_b200/csrc/mle_tps_core.cuh
+//
+// Per-spot arithmetic of the thread-per-spot MLE path (mle_tps.cu): start values,
+// one Newton iteration, CRLB + log-likelihood.  Everything here is scalar code that
+// one thread runs for one spot, written once for the device (nvcc, sm_100a) and for
+// the host (g++): tests/host_sim compiles the same functions on the CPU so the
+// arithmetic is checked against the oracle before a kernel ever runs.  The host
+// build is test scaffolding only -- the product has no CPU path.
+//
+// Reference: picasso/gaussmle.py (jungmannlab/picasso @ 96e0da51):
+//   _initial_parameters :28-168, _gaussian_integral :268-280,
+//   _derivative_gaussian_integral :283-303, _G / _derivative_gaussian_integral_sigma
+//   :306-336, _derivative_gaussian_integral_iso_sigma :339-383, _mlefit_sigma :533-644,
+//   _update_theta_sigma :647-670, _mlefit_sigma_crlb :673-742, _mlefit_sigmaxy :745-857,
+//   _update_theta_sigmaxy :860-884, _mlefit_sigmaxy_crlb :887-954.
+//
+// The model is separable: all transcendentals are evaluated per pixel EDGE
+// (box+1 edges per axis: 1 exp + 1 erf polynomial each), every derivative is
+// (column factor) x (row factor), and the Newton sums are accumulated as
+// column-weighted row sums to which the row factors are applied once per row.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+// Under nvcc these are DEVICE functions (tables live in __constant__ memory, so the FP64
+// instructions take their coefficients straight from the constant bank); under g++ they
+// are plain inline functions with ordinary const tables.
+#ifdef __CUDACC__
+#define PB_HD __device__ __forceinline__
+#define PB_HD_NOINLINE __device__ __noinline__
+#define PB_TABLE static __constant__
+#else
+#define PB_HD inline
+#define PB_HD_NOINLINE
+#define PB_TABLE static const
+#endif
+
+namespace tps {
+
+constexpr double kInvSqrt2Pi = 0.3989422804014326779;   // 1/sqrt(2*pi)
+constexpr double kInvSqrt2 = 0.70710678118654757;        // gaussmle.py:276
+constexpr double kInvSqrtPi = 0.5641895835477562869;     // 1/sqrt(pi)
+
+// ---- small math helpers ----------------------------------------------------
+// 1/x for x in the normal range (MUFU seed + two Newton steps on the device).
+PB_HD double rcp64(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    r = fma(r, fma(e, e, e), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+PB_HD float rcp32(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+PB_HD double rsqrt64(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+template <typename T> PB_HD T tfma(T a, T b, T c);
+template <> PB_HD float tfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> PB_HD double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
+template <typename T> PB_HD T trcp(T x);
+template <> PB_HD float trcp<float>(float x) { return rcp32(x); }
+template <> PB_HD double trcp<double>(double x) { return rcp64(x); }
+
+// exp(-q) for q >= 0 (tools/gen_exp_coeffs.py): n = rint(-q log2 e), r = -q - n ln2 (hi/lo),
+// exp(r) by a degree-11 near-minimax polynomial (4e-18 relative before rounding) split into
+// even and odd Horner chains, scaled by 2^n through the exponent field.  q is clamped to 700
+// (exp(-700) ~ 1e-304 stands in for the underflowed tail), so the result stays normal and no
+// special-case branch is needed.
+PB_TABLE double kExpPoly[12] = {
+    1.0, 1.0, 0.5000000000000019, 0.1666666666666668, 0.04166666666648738,
+    0.008333333333319546, 0.0013888888952505406, 0.00019841269890193705,
+    2.4801485278370062e-05, 2.7557240761739257e-06, 2.7632715071632255e-07,
+    2.5110095611886237e-08,
+};
+PB_HD double exp_neg(double q) {
+    q = q > 700.0 ? 700.0 : q;
+    const double x = -q;
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);   // 1.5 * 2^52: n in the low word
+    const double n = t - 6755399441055744.0;
+    double r = fma(n, -0.6931471805598903, x);                          // ln2_hi (11 trailing zero bits)
+    r = fma(n, -5.497923018708371e-14, r);                              // ln2_lo
+    const double r2 = r * r;
+    double pe = kExpPoly[10], po = kExpPoly[11];
+#pragma unroll
+    for (int k = 4; k >= 0; k--) {
+        pe = fma(pe, r2, kExpPoly[2 * k]);
+        po = fma(po, r2, kExpPoly[2 * k + 1]);
+    }
+    const double p = fma(po, r, pe);
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
+#else
+    return ldexp(p, (int)n);
+#endif
+}
+
+// erf(z) from the Gaussian term A = exp(-z^2) the fit needs anyway:
+//   erf(z) = sign(z) (1 - A P(x)),  t = 1/(1 + |z|/2),  x = (8 t - 5)/3,
+// P = degree-16 fit of erfcx on [0, 6] (tools/gen_erf_coeffs.py: max abs error 2.2e-15;
+// beyond |z| = 6, A < 3e-16), evaluated as two Horner chains in x^2.
+PB_TABLE double kErfcxPoly[17] = {
+    0.3785374169292369,      0.4221875836134109,     0.16940759095488894,
+    0.03299342947957943,     -0.0016702444148986467, -0.001665364388974453,
+    0.00013358437327083263,  0.00010054202594586505, -2.2700690081718415e-05,
+    -4.271484393949245e-06,  2.839667893118267e-06,  -2.8180849640529505e-07,
+    -2.0096403079505821e-07, 8.619074557878024e-08,  -3.971810944694673e-09,
+    -7.52808888456569e-09,   2.015803325273065e-09,
+};
+PB_HD double erf_from_gauss(double z, double A) {
+    double a = fabs(z);
+    a = a > 6.0 ? 6.0 : a;
+    const double t = rcp64(fma(0.5, a, 1.0));
+    const double x = fma(t, 2.6666666666666665, -1.6666666666666667);
+    const double x2 = x * x;
+    double pe = kErfcxPoly[16], po = kErfcxPoly[15];
+    pe = fma(pe, x2, kErfcxPoly[14]);
+#pragma unroll
+    for (int k = 6; k >= 0; k--) {
+        po = fma(po, x2, kErfcxPoly[2 * k + 1]);
+        pe = fma(pe, x2, kErfcxPoly[2 * k]);
+    }
+    const double p = fma(po, x, pe);
+    return copysign(fma(-A, p, 1.0), z);
+}
+
+// ---- per-axis constants of one iteration ------------------------------------
+// Reciprocals of sigma, f32(sigma^2), f32(sigma^3), f32(sigma^5): `float32 ** int`
+// stays float32 in the reference (binary powering), so the powers are rounded first.
+struct Axis {
+    double rs, r2, r3, r5;   // 1/sigma, 1/f32(sigma^2), 1/f32(sigma^3), 1/f32(sigma^5)
+    double rho;              // sigma^2 / f32(sigma^2) - 1   (for _G's exponent, :306-316)
+    double rinvf;            // (double) f32(1/sigma)        (iso-sigma d2, :380-382)
+};
+PB_HD Axis make_axis(float sig) {
+    Axis a;
+    const float s2f = sig * sig;
+    const float s3f = sig * s2f;
+    const float s5f = sig * (s2f * s2f);
+    const double sd = (double)sig;
+    a.rs = rcp64(sd);
+    a.r2 = rcp64((double)s2f);
+    a.r3 = rcp64((double)s3f);
+    a.r5 = rcp64((double)s5f);
+    a.rho = fma(sd * sd, a.r2, -1.0);
+    a.rinvf = (double)(1.0f / sig);
+    return a;
+}
+
+// Everything the two pixels sharing an edge need from it.  Edge g of an axis sits at
+// e = (g - mu) - 1/2: the minus edge of pixel g and (exactly, in f64) the plus edge of g-1.
+template <int METHOD>
+struct Edge {
+    double E;    // erf(e / (sqrt2 sigma))
+    double A;    // exp(-e^2 / (2 sigma^2))
+    double eA;   // e * A
+    double u;    // METHOD 1: e * AG  (AG = exp(-e^2 / (2 f32(sigma^2))));  METHOD 0: am * A
+    double v;    // METHOD 1: e^3 * AG;                                     METHOD 0: am A (1 - 2 am^2)
+};
+template <int METHOD>
+PB_HD Edge<METHOD> eval_edge(int g, float mu, const Axis& ax) {
+    Edge<METHOD> r;
+    const double e = ((double)g - (double)mu) - 0.5;
+    const double t = e * ax.rs;
+    const double q = 0.5 * t * t;
+    const double A = exp_neg(q);
+    r.A = A;
+    r.E = erf_from_gauss(e * (kInvSqrt2 * ax.rs), A);
+    r.eA = e * A;
+    if (METHOD == 1) {
+        const double z = -q * ax.rho;
+        const double AG = fma(A, fma(0.5 * z, z, z), A);
+        r.u = e * AG;
+        r.v = e * e * r.u;
+    } else {
+        const double am = e * (ax.rs * kInvSqrt2);
+        r.u = am * A;
+        r.v = r.u * (1.0 - 2.0 * am * am);
+    }
+    return r;
+}
+
+// Factors of one pixel column (or row) from its two edges:
+//   f[0] = PSF (integrated Gaussian), f[1], f[2] = d/dmu, d2/dmu2 (per photon, per other-axis PSF),
+//   f[3], f[4] = d/dsigma, d2/dsigma2 parts.
+template <int METHOD>
+PB_HD void pixel_factors(const Edge<METHOD>& lo, const Edge<METHOD>& hi, const Axis& ax, double f[5]) {
+    f[0] = 0.5 * (hi.E - lo.E);
+    f[1] = (lo.A - hi.A) * ax.rs * kInvSqrt2Pi;
+    f[2] = (lo.eA - hi.eA) * ax.r3 * kInvSqrt2Pi;
+    if (METHOD == 1) {
+        const double w1 = lo.u - hi.u, w3 = lo.v - hi.v;
+        f[3] = w1 * ax.r2 * kInvSqrt2Pi;
+        f[4] = (w3 * ax.r5 - 2.0 * w1 * ax.r3) * kInvSqrt2Pi;
+    } else {
+        const double F = lo.u - hi.u;
+        const double dF = (hi.v - lo.v) * ax.rs;
+        f[3] = F * ax.rs * kInvSqrtPi;
+        f[4] = kInvSqrtPi * (-F * ax.r2 + ax.rinvf * dF);
+    }
+}
+
+// ---- start values (gaussmle.py:28-168) ---------------------------------------
+// roi(p) returns pixel p = row * BOX + col as float.  Returns status flags
+// (bit 0: a centre-row/column sum was exactly 0 -- the reference raises there).
+template <int BOX, int METHOD, class Roi>
+PB_HD int initial_theta(const Roi& roi, float th[6]) {
+    constexpr int H = BOX / 2;
+    int st = 0;
+    // sum and centre of mass, f64, row-major like the reference (:28-48)
+    double s = 0.0, ys = 0.0, xs = 0.0;
+    // 3x3 edge-truncated mean filter minimum (:61-91, :135).  f32(S / N) is monotone in S,
+    // so the minimum is taken over the window sums per window size and divided once.
+    double m4 = INFINITY, m6 = INFINITY, m9 = INFINITY;
+    double h[3][BOX];   // horizontal 3-sums of the last three rows (rotating, fully unrolled)
+#pragma unroll
+    for (int m = 0; m <= BOX; m++) {
+        if (m < BOX) {
+            float v[BOX];
+#pragma unroll
+            for (int j = 0; j < BOX; j++) {
+                v[j] = roi(m * BOX + j);
+                const double d = (double)v[j];
+                ys += d * (double)m;
+                xs += d * (double)j;
+                s += d;
+            }
+#pragma unroll
+            for (int j = 0; j < BOX; j++) {
+                double a = (double)v[j];
+                if (j > 0) a = (double)v[j - 1] + a;
+                if (j + 1 < BOX) a += (double)v[j + 1];
+                h[m % 3][j] = a;
+            }
+        }
+        // window sums of row k = m - 1 are complete once row m is in
+        const int k = m - 1;
+        if (k >= 0) {
+#pragma unroll
+            for (int j = 0; j < BOX; j++) {
+                double S = h[k % 3][j];
+                if (k > 0) S = h[(k - 1) % 3][j] + S;
+                if (k + 1 < BOX) S += h[(k + 1) % 3][j];
+                const bool er = (k == 0 || k == BOX - 1), ec = (j == 0 || j == BOX - 1);
+                if (er && ec) m4 = S < m4 ? S : m4;
+                else if (er || ec) m6 = S < m6 ? S : m6;
+                else m9 = S < m9 ? S : m9;
+            }
+        }
+    }
+    double xc, yc;
+    if (s <= 0.0) { s = 0.01; yc = (BOX - 1) / 2.0; xc = (BOX - 1) / 2.0; }
+    else { yc = ys / s; xc = xs / s; }
+    const float b4 = (float)(m4 / 4.0), b6 = (float)(m6 / 6.0), b9 = (float)(m9 / 9.0);
+    float bg = b4 < b6 ? b4 : b6;
+    bg = b9 < bg ? b9 : bg;
+    double ph = s - (double)(BOX * BOX) * (double)bg;
+    ph = ph > 1.0 ? ph : 1.0;
+    // sigmas from the centre column / row of (spot - bg) (:94-124)
+    double sdy = 0.0, sy_ = 0.0, sdx = 0.0, sx_ = 0.0;
+#pragma unroll
+    for (int i = 0; i < BOX; i++) {
+        const float vy = roi(i * BOX + H) - bg;
+        const float vx = roi(H * BOX + i) - bg;
+        const double d2 = (double)((i - H) * (i - H));
+        sdy += (double)vy * d2; sdx += (double)vx * d2;
+        sy_ += (double)vy;      sx_ += (double)vx;
+    }
+    double sy0, sx0;
+    if (sy_ == 0.0) { sy0 = 0.01; st |= 1; } else sy0 = sqrt(sdy / sy_);
+    if (sx_ == 0.0) { sx0 = 0.01; st |= 1; } else sx0 = sqrt(sdx / sx_);
+    if (!isfinite(sy0) || sy0 == 0.0) sy0 = 0.01;
+    if (!isfinite(sx0) || sx0 == 0.0) sx0 = 0.01;
+    th[0] = (float)xc; th[1] = (float)yc; th[2] = (float)ph; th[3] = bg;
+    if (METHOD == 1) { th[4] = (float)sx0; th[5] = (float)sy0; }
+    else { th[4] = (float)((sx0 + sy0) / 2.0); th[5] = th[4]; }
+    return st;
+}
+
+// max_step from the start values (gaussmle.py:558-561, 770-773)
+PB_HD void max_steps(const float th0[6], float ms[6]) {
+    ms[0] = th0[4]; ms[1] = th0[4];
+    ms[2] = (float)(0.1 * (double)th0[2]);
+    ms[3] = (float)(0.1 * (double)th0[3]);
+    ms[4] = (float)(0.2 * (double)th0[4]);
+    ms[5] = (float)(0.2 * (double)th0[5]);
+}
+
+// ---- one Newton iteration ------------------------------------------------------
+// Column factors of the x axis are written to `xf` (T = float or double; shared memory on
+// the device) by stage 1 and read back per pixel by stage 2; the y factors are formed on
+// the fly, one row at a time.  Xf concept: void put(int col, const double f[5]);
+// void get(int col, T f[5]) const.
+template <int BOX, int METHOD, typename T, class Xf>
+PB_HD void column_stage(const float th[6], Xf& xf) {
+    const Axis ax = make_axis(th[4]);
+    // edges are evaluated in pairs into two fixed register sets (A: even edges, B: odd edges):
+    // no loop-carried copies, and the two evaluations of a trip are independent (ILP)
+    Edge<METHOD> A, B = {};
+#pragma unroll 1
+    for (int k = 0; k < (BOX + 1) / 2; k++) {
+        double f[5];
+        A = eval_edge<METHOD>(2 * k, th[0], ax);
+        if (k > 0) {
+            pixel_factors<METHOD>(B, A, ax, f);
+            xf.put(2 * k - 1, f);
+        }
+        B = eval_edge<METHOD>(2 * k + 1, th[0], ax);
+        pixel_factors<METHOD>(A, B, ax, f);
+        xf.put(2 * k, f);
+    }
+}
+
+// One pixel row: column-weighted sums of cf = data/model - 1 and df = data/model^2 over the
+// row (type T), then the row factors fy applied in f64.
+template <int BOX, int METHOD, typename T, class Roi, class Xf>
+PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& xf, double N, double bg,
+                          double num[6], double den[6]) {
+    const double PSFy = fy[0];
+    const double NPy = N * PSFy;
+    const T NPy_t = (T)NPy, bg_t = (T)bg;
+    T c0 = 0, cpx = 0, cc1 = 0, cc2 = 0, cg1 = 0, cg2 = 0;
+    T d0 = 0, dpx2 = 0, dc1 = 0, dg1 = 0, dgp = 0;
+#pragma unroll
+    for (int i = 0; i < BOX; i++) {
+        T f[5];
+        xf.get(i, f);
+        const T model = tfma<T>(f[0], NPy_t, bg_t);
+        // guards (gaussmle.py:829-835): model > 0.01, cf, df <= 1e5; NaN / inf from a
+        // non-positive model are discarded by the select
+        const bool okm = model > (T)10e-3;
+        const T inv = trcp<T>(model);
+        const T t = (T)roi(j * BOX + i) * inv;
+        T cf = t - (T)1, df = t * inv;
+        cf = cf > (T)10e4 ? (T)10e4 : cf;
+        df = df > (T)10e4 ? (T)10e4 : df;
+        cf = okm ? cf : (T)0;
+        df = okm ? df : (T)0;
+        c0 += cf;
+        cpx = tfma<T>(cf, f[0], cpx);
+        cc1 = tfma<T>(cf, f[1], cc1);
+        cc2 = tfma<T>(cf, f[2], cc2);
+        cg1 = tfma<T>(cf, f[3], cg1);
+        cg2 = tfma<T>(cf, f[4], cg2);
+        d0 += df;
+        dpx2 = tfma<T>(df, f[0] * f[0], dpx2);
+        dc1 = tfma<T>(df, f[1] * f[1], dc1);
+        dg1 = tfma<T>(df, f[3] * f[3], dg1);
+        if (METHOD == 0) dgp = tfma<T>(df, f[3] * f[0], dgp);
+    }
+    const double Ncy1 = N * fy[1], Ncy2 = N * fy[2];
+    const double cpx_d = (double)cpx, dpx2_d = (double)dpx2;
+    num[0] = fma(NPy, (double)cc1, num[0]);
+    den[0] += NPy * (double)cc2 - NPy * NPy * (double)dc1;
+    num[1] = fma(Ncy1, cpx_d, num[1]);
+    den[1] += Ncy2 * cpx_d - Ncy1 * Ncy1 * dpx2_d;
+    num[2] = fma(PSFy, cpx_d, num[2]);
+    den[2] -= PSFy * PSFy * dpx2_d;
+    num[3] += (double)c0;
+    den[3] -= (double)d0;
+    if (METHOD == 1) {
+        const double Ngy1 = N * fy[3], Ngy2 = N * fy[4];
+        num[4] = fma(NPy, (double)cg1, num[4]);
+        den[4] += NPy * (double)cg2 - NPy * NPy * (double)dg1;
+        num[5] = fma(Ngy1, cpx_d, num[5]);
+        den[5] += Ngy2 * cpx_d - Ngy1 * Ngy1 * dpx2_d;
+    } else {
+        // dudt = N (PSFy dPx + PSFx dPy); the reference's d2udt2 has photons on the
+        // first term only (gaussmle.py:380-382)
+        const double gy1 = fy[3], gy2 = fy[4];
+        num[4] += N * (PSFy * (double)cg1 + gy1 * cpx_d);
+        den[4] += (NPy * (double)cg2 + 2.0 * gy1 * (double)cg1 + gy2 * cpx_d) -
+                  N * N * (PSFy * PSFy * (double)dg1 + 2.0 * PSFy * gy1 * (double)dgp +
+                           gy1 * gy1 * dpx2_d);
+    }
+}
+
+template <int BOX, int METHOD, typename T, class Roi, class Xf>
+PB_HD void newton_sums(const Roi& roi, const float th[6], const Xf& xf, double num[6], double den[6]) {
+    const double N = (double)th[2], bg = (double)th[3];
+    const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
+#pragma unroll
+    for (int l = 0; l < 6; l++) { num[l] = 0.0; den[l] = 0.0; }
+    Edge<METHOD> A, B = {};
+#pragma unroll 1
+    for (int k = 0; k < (BOX + 1) / 2; k++) {
+        double fy[5];
+        A = eval_edge<METHOD>(2 * k, th[1], ay);
+        if (k > 0) {
+            pixel_factors<METHOD>(B, A, ay, fy);
+            accumulate_row<BOX, METHOD, T>(2 * k - 1, fy, roi, xf, N, bg, num, den);
+        }
+        B = eval_edge<METHOD>(2 * k + 1, th[1], ay);
+        pixel_factors<METHOD>(A, B, ay, fy);
+        accumulate_row<BOX, METHOD, T>(2 * k, fy, roi, xf, N, bg, num, den);
+    }
+}
+
+// Clamped per-parameter Newton step in float32 (gaussmle.py:647-670, 860-884).
+// Returns true when the stopping rule is met (:632-638, :844-852).
+template <int BOX, int METHOD>
+PB_HD bool update_theta(float th[6], const float ms[6], const double num[6], const double den[6],
+                        double eps) {
+    constexpr int NP = METHOD == 1 ? 6 : 5;
+    float tn[6];
+#pragma unroll
+    for (int l = 0; l < NP; l++) {
+        const float nu = (float)num[l], de = (float)den[l];
+        float upd;
+        if (de == 0.0f) {
+            if (METHOD == 1) {
+                const float sg = nu > 0.f ? 1.f : (nu < 0.f ? -1.f : nu);
+                upd = sg * ms[l];
+            } else {
+                const float pr = nu * ms[l];
+                upd = pr > 0.f ? 1.f : (pr < 0.f ? -1.f : pr);
+            }
+        } else {
+            upd = fminf(fmaxf(nu / de, -ms[l]), ms[l]);
+        }
+        float v = th[l] - upd;
+        if (l == 2) v = fmaxf(v, 1.0f);
+        if (l >= 3) v = fmaxf(v, 0.01f);
+        if (METHOD == 0 && l == 4) v = fminf(v, (float)BOX);
+        tn[l] = v;
+    }
+    if (METHOD == 0) tn[5] = tn[4];
+    bool conv = ((double)fabsf(th[0] - tn[0]) < eps) && ((double)fabsf(th[1] - tn[1]) < eps);
+    if (METHOD == 1)
+        conv = conv && ((double)fabsf(th[4] - tn[4]) < eps) && ((double)fabsf(th[5] - tn[5]) < eps);
+#pragma unroll
+    for (int l = 0; l < 6; l++) th[l] = tn[l];
+    return conv;
+}
+
+// ---- CRLB: diagonal of the (pseudo-)inverse Fisher matrix --------------------------
+// Jacobi eigen pseudo-inverse diagonal (rare fallback; np.linalg.pinv, rcond 1e-15)
+template <int NP>
+PB_HD_NOINLINE void pinv_diag_jacobi(const double* Msym /*NP*NP*/, double* diag) {
+    double A[NP * NP], V[NP * NP];
+    bool finite = true;
+    for (int i = 0; i < NP * NP; i++) {
+        A[i] = Msym[i];
+        finite = finite && isfinite(A[i]);
+    }
+    if (!finite) {
+        for (int i = 0; i < NP; i++) diag[i] = NAN;
+        return;
+    }
+    for (int i = 0; i < NP; i++)
+        for (int j = 0; j < NP; j++) V[i * NP + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0, dsum = 0.0;
+        for (int i = 0; i < NP; i++)
+            for (int j = 0; j < NP; j++) {
+                double v = A[i * NP + j] * A[i * NP + j];
+                if (i != j) off += v; else dsum += v;
+            }
+        if (off <= 1e-60 || off <= 1e-34 * dsum) break;
+        for (int p = 0; p < NP - 1; p++)
+            for (int q = p + 1; q < NP; q++) {
+                double apq = A[p * NP + q];
+                if (apq == 0.0) continue;
+                double th = (A[q * NP + q] - A[p * NP + p]) / (2.0 * apq);
+                double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                if (!isfinite(th)) t = 0.0;
+                double c = rsqrt64(t * t + 1.0), s = t * c;
+                for (int k = 0; k < NP; k++) {
+                    double akp = A[k * NP + p], akq = A[k * NP + q];
+                    A[k * NP + p] = c * akp - s * akq;
+                    A[k * NP + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < NP; k++) {
+                    double apk = A[p * NP + k], aqk = A[q * NP + k];
+                    A[p * NP + k] = c * apk - s * aqk;
+                    A[q * NP + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < NP; k++) {
+                    double vkp = V[k * NP + p], vkq = V[k * NP + q];
+                    V[k * NP + p] = c * vkp - s * vkq;
+                    V[k * NP + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double smax = 0.0;
+    for (int i = 0; i < NP; i++) smax = fmax(smax, fabs(A[i * NP + i]));
+    double cutoff = 1e-15 * smax;
+    for (int i = 0; i < NP; i++) {
+        double acc = 0.0;
+        for (int k = 0; k < NP; k++) {
+            double lam = A[k * NP + k];
+            if (fabs(lam) > cutoff) acc += V[i * NP + k] * V[i * NP + k] / lam;
+        }
+        diag[i] = acc;
+    }
+}
+
+// Diagonal of inv(M), M symmetric positive definite, packed upper triangle m[idx(k,l)], k <= l.
+// false when the diagonally scaled Cholesky meets a non-positive / tiny pivot.
+template <int NP>
+PB_HD bool inv_diag_cholesky(const double* m, double* diag) {
+#define PB_TRI(k, l) ((k) * NP - ((k) * ((k) - 1)) / 2 + ((l) - (k)))
+    double d[NP];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        double mii = m[PB_TRI(i, i)];
+        ok = ok && (mii > 0.0) && isfinite(mii);
+        d[i] = rsqrt64(mii);
+    }
+    if (!ok) return false;
+    double L[NP][NP];
+    double rl[NP];
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        double s = 1.0;
+#pragma unroll
+        for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+        ok = ok && (s > 1e-12);
+        rl[j] = rsqrt64(s);
+        L[j][j] = s * rl[j];
+#pragma unroll
+        for (int i = j + 1; i < NP; i++) {
+            double c = m[PB_TRI(j, i)] * d[i] * d[j];
+#pragma unroll
+            for (int k = 0; k < j; k++) c -= L[i][k] * L[j][k];
+            L[i][j] = c * rl[j];
+        }
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        double X[NP];
+        double acc = 0.0;
+#pragma unroll
+        for (int i = j; i < NP; i++) {
+            double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = j; k < i; k++) s -= L[i][k] * X[k];
+            X[i] = s * rl[i];
+            acc += X[i] * X[i];
+        }
+        diag[j] = acc * d[j] * d[j];
+    }
+#undef PB_TRI
+    return true;
+}
+
+// CRLB + log-likelihood at theta (gaussmle.py:673-742, 887-954).  Xf3 concept: put(col, f[5])
+// keeps (PSF, d/dmu, d/dsigma) of the column; get(col, double f[3]).
+// Returns status flags (bit 1: pseudo-inverse fallback, bit 2: non-finite CRLB).
+template <int BOX, int METHOD, class Roi, class Xf3>
+PB_HD int crlb_loglik(const Roi& roi, const float th[6], Xf3& xf, float crlb[6], float* loglik) {
+    constexpr int NP = METHOD == 1 ? 6 : 5;
+    constexpr int NF = NP * (NP + 1) / 2;
+    int st = 0;
+    const double N = (double)th[2], bg = (double)th[3];
+    {
+        const Axis ax = make_axis(th[4]);
+        Edge<METHOD> lo = {};
+#pragma unroll 1
+        for (int g = 0; g <= BOX; g++) {
+            const Edge<METHOD> hi = eval_edge<METHOD>(g, th[0], ax);
+            if (g > 0) {
+                double f[5];
+                pixel_factors<METHOD>(lo, hi, ax, f);
+                xf.put(g - 1, f);
+            }
+            lo = hi;
+        }
+    }
+    double M[NF];
+#pragma unroll
+    for (int q = 0; q < NF; q++) M[q] = 0.0;
+    double ll = 0.0;
+    const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
+    Edge<METHOD> lo = {};
+#pragma unroll 1
+    for (int g = 0; g <= BOX; g++) {
+        const Edge<METHOD> hi = eval_edge<METHOD>(g, th[1], ay);
+        const Edge<METHOD> lo_ = lo;
+        lo = hi;
+        if (g == 0) continue;
+        const int j = g - 1;
+        double fy[5];
+        pixel_factors<METHOD>(lo_, hi, ay, fy);
+        const double PSFy = fy[0], NPy = N * fy[0], Ncy1 = N * fy[1], Ngy1 = N * fy[3];
+#pragma unroll 1
+        for (int i = 0; i < BOX; i++) {
+            double f[3];   // px, c1, g1
+            xf.get(i, f);
+            const double model = fma(N * f[0], PSFy, bg);
+            const double w = 1.0 / model;
+            double du[NP];
+            du[0] = NPy * f[1];
+            du[1] = Ncy1 * f[0];
+            du[2] = PSFy * f[0];
+            du[3] = 1.0;
+            if (METHOD == 1) { du[4] = NPy * f[2]; du[5] = Ngy1 * f[0]; }
+            else du[4] = NPy * f[2] + Ngy1 * f[0];
+            int q = 0;
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                const double dw = du[k] * w;
+#pragma unroll
+                for (int l = k; l < NP; l++) { M[q] = fma(dw, du[l], M[q]); q++; }
+            }
+            const float dataf = roi(j * BOX + i);
+            if (model > 0.0) {
+                if (dataf > 0.0f)
+                    ll += (double)dataf * log(model) - model - (double)(dataf * logf(dataf)) +
+                          (double)dataf;
+                else
+                    ll -= model;
+            }
+        }
+    }
+    *loglik = (float)ll;
+    double dg[NP];
+    // np.linalg.pinv drops singular values below 1e-15 * max: a tiny diagonal entry means a
+    // (numerically) null direction -> pseudo-inverse
+    double dmin = INFINITY, dmax = 0.0;
+    {
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            dmin = fmin(dmin, M[q]); dmax = fmax(dmax, M[q]);
+            q += NP - k;
+        }
+    }
+    bool ok = (dmin > 1e-13 * dmax) && inv_diag_cholesky<NP>(M, dg);
+    if (!ok) {
+        st |= 2;
+        double Mfull[NP * NP];
+        int q = 0;
+        for (int k = 0; k < NP; k++)
+            for (int l = k; l < NP; l++) {
+                Mfull[k * NP + l] = M[q];
+                Mfull[l * NP + k] = M[q];
+                q++;
+            }
+        pinv_diag_jacobi<NP>(Mfull, dg);
+    }
+    bool bad = false;
+#pragma unroll
+    for (int l = 0; l < NP; l++) {
+        crlb[l] = (float)dg[l];
+        bad = bad || !isfinite(crlb[l]);
+    }
+    if (METHOD == 0) crlb[5] = crlb[4];
+    if (bad) st |= 4;
+    return st;
+}
+
+}  // namespace tps

@@ -1,0 +1,81 @@
+// tests/host_sim/mle_tps_sim.cpp -- TEST SCAFFOLDING, NOT PRODUCT CODE.
+//
+// Compiles the per-spot arithmetic of the thread-per-spot CUDA MLE path
+// (picasso_b200/csrc/mle_tps_core.cuh, the very functions the kernels call) with g++ and
+// runs it spot by spot on the CPU, so tests can compare it with the oracle without a GPU.
+// glibc's exp/log stand in for libdevice's; everything else is the same code.
+#include "../../picasso_b200/csrc/mle_tps_core.cuh"
+
+namespace {
+
+struct RoiPtr {
+    const float* p;
+    float operator()(int k) const { return p[k]; }
+};
+template <int BOX, typename T>
+struct XfHost {
+    T a[BOX][5];
+    void put(int c, const double f[5]) { for (int k = 0; k < 5; k++) a[c][k] = (T)f[k]; }
+    void get(int c, T f[5]) const { for (int k = 0; k < 5; k++) f[k] = a[c][k]; }
+};
+template <int BOX>
+struct Xf3Host {
+    double a[BOX][3];
+    void put(int c, const double f[5]) { a[c][0] = f[0]; a[c][1] = f[1]; a[c][2] = f[3]; }
+    void get(int c, double f[3]) const { f[0] = a[c][0]; f[1] = a[c][1]; f[2] = a[c][2]; }
+};
+
+template <int BOX, int METHOD, typename T>
+void fit_range(const float* spots, long long n, double eps, int max_it, float* thetas, float* crlbs,
+               float* logliks, int* iterations, int* status) {
+    for (long long s = 0; s < n; s++) {
+        RoiPtr roi{spots + s * BOX * BOX};
+        float th[6], ms[6];
+        int st = tps::initial_theta<BOX, METHOD>(roi, th);
+        tps::max_steps(th, ms);
+        int kk = 0;
+        while (kk < max_it) {
+            kk++;
+            XfHost<BOX, T> xf;
+            tps::column_stage<BOX, METHOD, T>(th, xf);
+            double num[6], den[6];
+            tps::newton_sums<BOX, METHOD, T>(roi, th, xf, num, den);
+            if (tps::update_theta<BOX, METHOD>(th, ms, num, den, eps)) break;
+        }
+        Xf3Host<BOX> x3;
+        float cr[6], ll;
+        st |= tps::crlb_loglik<BOX, METHOD>(roi, th, x3, cr, &ll);
+        for (int l = 0; l < 6; l++) { thetas[s * 6 + l] = th[l]; crlbs[s * 6 + l] = cr[l]; }
+        logliks[s] = ll;
+        iterations[s] = kk;
+        if (status) status[s] = st;
+    }
+}
+
+template <int BOX>
+int dispatch(const float* spots, long long n, double eps, int max_it, int method, int f32,
+             float* th, float* cr, float* ll, int* it, int* st) {
+    if (method == 1) {
+        if (f32) fit_range<BOX, 1, float>(spots, n, eps, max_it, th, cr, ll, it, st);
+        else fit_range<BOX, 1, double>(spots, n, eps, max_it, th, cr, ll, it, st);
+    } else {
+        if (f32) fit_range<BOX, 0, float>(spots, n, eps, max_it, th, cr, ll, it, st);
+        else fit_range<BOX, 0, double>(spots, n, eps, max_it, th, cr, ll, it, st);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int sim_mle_tps(const float* spots, long long n, int box, double eps, int max_it,
+                           int method, int f32_pixels, float* thetas, float* crlbs, float* logliks,
+                           int* iterations, int* status) {
+    switch (box) {
+        case 5: return dispatch<5>(spots, n, eps, max_it, method, f32_pixels, thetas, crlbs, logliks, iterations, status);
+        case 7: return dispatch<7>(spots, n, eps, max_it, method, f32_pixels, thetas, crlbs, logliks, iterations, status);
+        case 9: return dispatch<9>(spots, n, eps, max_it, method, f32_pixels, thetas, crlbs, logliks, iterations, status);
+        case 11: return dispatch<11>(spots, n, eps, max_it, method, f32_pixels, thetas, crlbs, logliks, iterations, status);
+        case 13: return dispatch<13>(spots, n, eps, max_it, method, f32_pixels, thetas, crlbs, logliks, iterations, status);
+        default: return -1;
+    }
+}

@@ -22,10 +22,30 @@ def _compare(spots, method, oracle, eps=0.001, max_it=100):
                 oll=oll, it=it, oit=oit)
 
 
+@pytest.fixture
+def mle_impl():
+    """Select the MLE kernel family for one test and restore the default afterwards
+    (0 = lane-group kernel, 1 = thread-per-spot f64 pixel sums, 2 = thread-per-spot f32)."""
+    from picasso_b200 import _lib
+
+    lib = _lib.load()
+    default = lib.pb_mle_get_impl()
+
+    def select(impl):
+        _lib.check(lib.pb_mle_set_impl(impl))
+
+    yield select
+    lib.pb_mle_set_impl(default)
+
+
+@pytest.mark.parametrize("impl", [2, 1, 0])
 @pytest.mark.parametrize("method", ["sigmaxy", "sigma"])
 @pytest.mark.parametrize("box", [5, 7, 9, 11, 13, 15, 17])
-def test_mle_matches_oracle(box, method, oracle):
-    n = 10_000 if box == 7 else 1_003   # 1003: ragged tail tile (not a multiple of 4)
+def test_mle_matches_oracle(box, method, impl, oracle, mle_impl):
+    if box > 13 and impl != 0:
+        pytest.skip("boxes above 13 always run the lane-group kernel")
+    mle_impl(impl)
+    n = 10_000 if box == 7 else 1_003   # 1003: ragged tail (not a multiple of 4 / 32 / 128)
     spots = testing.synthetic_spots(n, box, seed=box)
     r = _compare(spots, method, oracle)
     assert r["same_it"] >= 0.99, r["same_it"]
