@@ -67,15 +67,17 @@ struct RoiSlot {   // one spot's pixels, contiguous floats in shared memory
 // column factors of the x axis for the lane's spot; column stride = 32 lanes (one warp)
 struct XfF32 {
     float4* a;   // (PSF, d/dmu, d2/dmu2, d/dsigma)
-    float* b;    // d2/dsigma2
+    float2* b;   // (d2/dsigma2, low word of PSF for the float-float residual)
     __host__ __device__ __forceinline__ void put(int c, const double f[5]) {
-        a[c * 32] = make_float4((float)f[0], (float)f[1], (float)f[2], (float)f[3]);
-        b[c * 32] = (float)f[4];
+        const float px = (float)f[0];
+        a[c * 32] = make_float4(px, (float)f[1], (float)f[2], (float)f[3]);
+        b[c * 32] = make_float2((float)f[4], (float)(f[0] - (double)px));
     }
-    __host__ __device__ __forceinline__ void get(int c, float f[5]) const {
+    __host__ __device__ __forceinline__ void get(int c, float f[6]) const {
         const float4 v = a[c * 32];
+        const float2 w = b[c * 32];
         f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-        f[4] = b[c * 32];
+        f[4] = w.x; f[5] = w.y;
     }
 };
 struct XfF64 {
@@ -87,10 +89,11 @@ struct XfF64 {
         b[col * 32] = make_double2(f[2], f[3]);
         c[col * 32] = f[4];
     }
-    __host__ __device__ __forceinline__ void get(int col, double f[5]) const {
+    __host__ __device__ __forceinline__ void get(int col, double f[6]) const {
         const double2 u = a[col * 32], v = b[col * 32];
         f[0] = u.x; f[1] = u.y; f[2] = v.x; f[3] = v.y;
         f[4] = c[col * 32];
+        f[5] = 0.0;
     }
 };
 // CRLB pass: (PSF, d/dmu, d/dsigma) per column; column stride = kThreads
@@ -111,7 +114,7 @@ struct Xf3 {
 template <typename T> struct XfSel;
 template <> struct XfSel<float> {
     using type = XfF32;
-    static constexpr int kBytesPerLaneCol = 20;
+    static constexpr int kBytesPerLaneCol = 24;
 };
 template <> struct XfSel<double> {
     using type = XfF64;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, PB_TPS_MINB) tps_iter_kernel(const T
     typename XfSel<T>::type xf;
     if constexpr (sizeof(T) == 4) {
         xf.a = reinterpret_cast<float4*>(xf_raw) + lane;
-        xf.b = reinterpret_cast<float*>(xf_raw + 32 * BOX * 16) + lane;
+        xf.b = reinterpret_cast<float2*>(xf_raw + 32 * BOX * 16) + lane;
     } else {
         xf.a = reinterpret_cast<double2*>(xf_raw) + lane;
         xf.b = reinterpret_cast<double2*>(xf_raw + 32 * BOX * 16) + lane;
@@ -206,53 +209,100 @@ __global__ void __launch_bounds__(kThreads, PB_TPS_MINB) tps_iter_kernel(const T
     const long long seg_end = seg_first + seg_n;
 
     long long idx = -1;            // spot owned by this lane (-1: none)
-    long long wnext = 0, wend = 0; // indices claimed by the warp, not yet handed out (uniform)
-    bool exhausted = false;        // nothing left to claim (uniform)
+    // Two claimed blocks of up to 32 spot indices per warp (warp-uniform): `cur` is being handed
+    // out, `nxt` was claimed one block ahead and its ROIs / start values prefetched into L2, so
+    // the refill loads below do not wait for DRAM.
+    long long wnext = 0, wend = 0, nnext = 0, nend = 0;
+    bool exhausted = false;        // the claim counter ran past the end (uniform)
     float th[6] = {0.f, 0.f, 1.f, 1.f, 1.f, 1.f};
     int kk = 0;
+
+    auto claim = [&](long long& b, long long& e) {
+        b = e = 0;
+        if (exhausted) return;
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(a.counter, 32ull);
+        v = __shfl_sync(kFull, v, 0);
+        const long long first = seg_first + (long long)v;
+        if (first >= seg_end) { exhausted = true; return; }
+        b = first;
+        e = first + 32 < seg_end ? first + 32 : seg_end;
+        const char* p0 = reinterpret_cast<const char*>(a.spots + b * PIX);
+        const long long nbytes = (e - b) * PIX * 4;
+        for (long long off = (long long)lane * 128; off < nbytes + 127; off += 32 * 128) {
+            const char* q = p0 + (off < nbytes ? off : nbytes - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+        const char* t0 = reinterpret_cast<const char*>(a.thetas + b * 6);
+        const long long tbytes = (e - b) * 24;
+        if ((long long)lane * 128 < tbytes + 127) {
+            const long long off = (long long)lane * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(t0 + (off < tbytes ? off : tbytes - 1)));
+        }
+    };
+    claim(wnext, wend);
+    claim(nnext, nend);
 
     // (the trip bound is a watchdog only: a warp makes ~ spots/warp * iterations / 32 trips)
     for (unsigned trip = 0; trip < (1u << 24); trip++) {
         // ---- lanes without a spot take the next unclaimed ones ------------------------
         const bool idle = idx < 0;
         const unsigned need = __ballot_sync(kFull, idle);
-        if (need != 0u && (!exhausted || wnext < wend)) {
+        if (need != 0u && (wnext < wend || nnext < nend)) {
             const int cnt = __popc(need);
-            const long long left = wend - wnext;
-            long long nb = 0, ne = 0;          // freshly claimed block [nb, ne)
-            if (cnt > left && !exhausted) {
-                unsigned long long b = 0;
-                if (lane == 0) b = atomicAdd(a.counter, 32ull);
-                b = __shfl_sync(kFull, b, 0);
-                nb = seg_first + (long long)b;
-                if (nb >= seg_end) { exhausted = true; nb = ne = 0; }
-                else ne = nb + 32 < seg_end ? nb + 32 : seg_end;
-            }
+            const long long leftc = wend - wnext, leftn = nend - nnext;
             const int rank = __popc(need & ((1u << lane) - 1u));
             if (idle) {
-                if (rank < left) idx = wnext + rank;
-                else if (nb + (rank - left) < ne) idx = nb + (rank - left);
+                if (rank < leftc) idx = wnext + rank;
+                else if (rank - leftc < leftn) idx = nnext + (rank - leftc);
             }
-            if (cnt <= left) wnext += cnt;
+            if (cnt <= leftc) wnext += cnt;
             else {
-                const long long used = cnt - left;        // taken from the new block
-                wnext = nb + (used < ne - nb ? used : ne - nb);
-                wend = ne;
+                const long long used = cnt - leftc < leftn ? cnt - leftc : leftn;
+                wnext = nnext + used;
+                wend = nend;
+                claim(nnext, nend);
             }
-            // the whole warp copies each new spot's ROI into its lane's slot (coalesced)
-            unsigned got = __ballot_sync(kFull, idle && idx >= 0);
-            while (got) {
-                const int t = __ffs(got) - 1;
-                got &= got - 1;
-                const long long sidx = __shfl_sync(kFull, idx, t);
-                const float* src = a.spots + sidx * PIX;
-                float* dst = roi_w + t * PIX;
-#pragma unroll
-                for (int p = lane; p < PIX; p += 32) dst[p] = src[p];
-            }
-            if (idle && idx >= 0) {
+            const bool fresh = idle && idx >= 0;
+            // start values of the new spots (per-lane loads, in flight during the ROI copy)
+            float2 v0 = make_float2(0.f, 0.f), v1 = v0, v2 = v0;
+            if (fresh) {
                 const float2* in = reinterpret_cast<const float2*>(a.thetas + idx * 6);
-                const float2 v0 = in[0], v1 = in[1], v2 = in[2];
+                v0 = in[0]; v1 = in[1]; v2 = in[2];
+            }
+            // the whole warp copies each new spot's ROI into its lane's slot (coalesced),
+            // four spots per round so that their loads are in flight together
+            constexpr int NCH = (PIX + 31) / 32;
+            unsigned got = __ballot_sync(kFull, fresh);
+            while (got) {
+                int t[4];
+                float v[4][NCH];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    t[u] = got ? __ffs(got) - 1 : -1;
+                    got &= got - 1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (t[u] >= 0) {
+                        const long long sidx = __shfl_sync(kFull, idx, t[u]);
+                        const float* src = a.spots + sidx * PIX;
+#pragma unroll
+                        for (int c = 0; c < NCH; c++)
+                            v[u][c] = (lane + 32 * c < PIX) ? src[lane + 32 * c] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (t[u] >= 0) {
+                        float* dst = roi_w + t[u] * PIX;
+#pragma unroll
+                        for (int c = 0; c < NCH; c++)
+                            if (lane + 32 * c < PIX) dst[lane + 32 * c] = v[u][c];
+                    }
+                }
+            }
+            if (fresh) {
                 th[0] = v0.x; th[1] = v0.y; th[2] = v1.x; th[3] = v1.y; th[4] = v2.x; th[5] = v2.y;
                 float ms[6];
                 tps::max_steps(th, ms);
@@ -267,12 +317,12 @@ __global__ void __launch_bounds__(kThreads, PB_TPS_MINB) tps_iter_kernel(const T
         // ---- one Newton iteration on every lane that owns a spot -------------------------
         if (idx >= 0) {
             tps::column_stage<BOX, METHOD, T>(th, xf);
-            double num[6], den[6];
-            tps::newton_sums<BOX, METHOD, T>(roi, th, xf, num, den);
+            T num[6], den[6];   // float32 pixel sums also run the row stage in float32
+            tps::newton_sums<BOX, METHOD, T, T>(roi, th, xf, num, den);
             float ms[6];
 #pragma unroll
             for (int l = 0; l < 6; l++) ms[l] = ms_s[l * 32 + lane];
-            const bool conv = tps::update_theta<BOX, METHOD>(th, ms, num, den, a.eps);
+            const bool conv = tps::update_theta<BOX, METHOD, T>(th, ms, num, den, a.eps);
             kk++;
             if (conv || kk >= a.max_it) {
                 float2* out = reinterpret_cast<float2*>(a.thetas + idx * 6);

@@ -140,6 +140,37 @@ PB_HD double erf_from_gauss(double z, double A) {
     return copysign(fma(-A, p, 1.0), z);
 }
 
+// ln(x) for a positive, finite, normal x (|relative error| < 1e-15): x = m 2^e with
+// m in [sqrt(1/2), sqrt(2)), ln m = 2 atanh(s), s = (m - 1)/(m + 1), nine odd terms.
+// Coefficients come from the constant bank and there is no special-case branch (libdevice's
+// log spends a third of its instructions on immediates and on denormal / inf / nan paths).
+PB_TABLE double kLogPoly[9] = {
+    2.0, 0.66666666666666663, 0.40000000000000002, 0.2857142857142857, 0.22222222222222221,
+    0.18181818181818182, 0.15384615384615385, 0.13333333333333333, 0.11764705882352941,
+};
+PB_HD double log_pos(double x) {
+#ifdef __CUDA_ARCH__
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                    // m in [1, 2)
+    if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }     // m >= ~sqrt(2): halve
+    const double m = __hiloint2double(hi, lo);
+#else
+    int e;
+    double m = 2.0 * frexp(x, &e);
+    e -= 1;
+    if (m >= 1.4142141342163086) { m *= 0.5; e += 1; }     // same threshold: high word 0x3ff6a09f
+#endif
+    const double s = (m - 1.0) * rcp64(m + 1.0);
+    const double s2 = s * s;
+    double p = kLogPoly[8];
+#pragma unroll
+    for (int k = 7; k >= 0; k--) p = fma(p, s2, kLogPoly[k]);
+    const double de = (double)e;
+    return fma(de, 0.6931471805598903, fma(s, p, de * 5.497923018708371e-14));
+}
+
 // ---- per-axis constants of one iteration ------------------------------------
 // Reciprocals of sigma, f32(sigma^2), f32(sigma^3), f32(sigma^5): `float32 ** int`
 // stays float32 in the reference (binary powering), so the powers are rounded first.
@@ -328,26 +359,48 @@ PB_HD void column_stage(const float th[6], Xf& xf) {
 }
 
 // One pixel row: column-weighted sums of cf = data/model - 1 and df = data/model^2 over the
-// row (type T), then the row factors fy applied in f64.
-template <int BOX, int METHOD, typename T, class Roi, class Xf>
-PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& xf, double N, double bg,
-                          double num[6], double den[6]) {
-    const double PSFy = fy[0];
-    const double NPy = N * PSFy;
-    const T NPy_t = (T)NPy, bg_t = (T)bg;
+// row in type T, then the row factors fy applied and accumulated over rows in type A
+// (A = double: f64 row stage; A = float: everything after the edge terms runs on the FP32
+// pipe -- the reference itself accumulates all b*b terms in float32, gaussmle.py:836-839).
+template <int BOX, int METHOD, typename T, typename A, class Roi, class Xf>
+PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& xf, float Nf, float bgf,
+                          A num[6], A den[6]) {
+    const A N = (A)Nf;
+    const A PSFy = (A)fy[0];
+    const A NPy = N * PSFy;
+    const T NPy_t = (T)NPy, bg_t = (T)bgf;
+    // float32 pixels: the residual data - model cancels to ~sqrt(model), so it is formed in
+    // float-float arithmetic (N PSFy and PSFx carry a low word); everything downstream of the
+    // residual is well conditioned and stays plain float32
+    const float NPy_lo = (sizeof(T) == 4) ? (float)((double)Nf * fy[0] - (double)(float)NPy_t) : 0.f;
     T c0 = 0, cpx = 0, cc1 = 0, cc2 = 0, cg1 = 0, cg2 = 0;
     T d0 = 0, dpx2 = 0, dc1 = 0, dg1 = 0, dgp = 0;
 #pragma unroll
     for (int i = 0; i < BOX; i++) {
-        T f[5];
+        T f[6];
         xf.get(i, f);
-        const T model = tfma<T>(f[0], NPy_t, bg_t);
+        const T data = (T)roi(j * BOX + i);
+        T model, inv, cf, df;
+        if (sizeof(T) == 4) {
+            const float p = (float)f[0] * (float)NPy_t;                    // hi part of N PSFx PSFy
+            const float pe = fmaf((float)f[0], (float)NPy_t, -p);           // its rounding error
+            const float cross = fmaf((float)f[0], NPy_lo, (float)f[5] * (float)NPy_t);
+            model = (T)(p + (float)bg_t);
+            inv = trcp<T>(model);
+            const float a = (float)data - p;          // exact when data and p are within 2x
+            const float r = (a - (float)bg_t) - (pe + cross);
+            cf = (T)(r * (float)inv);
+            df = data * inv * inv;
+        } else {
+            model = tfma<T>(f[0], NPy_t, bg_t);
+            inv = trcp<T>(model);
+            const T t = data * inv;
+            cf = t - (T)1;
+            df = t * inv;
+        }
         // guards (gaussmle.py:829-835): model > 0.01, cf, df <= 1e5; NaN / inf from a
         // non-positive model are discarded by the select
         const bool okm = model > (T)10e-3;
-        const T inv = trcp<T>(model);
-        const T t = (T)roi(j * BOX + i) * inv;
-        T cf = t - (T)1, df = t * inv;
         cf = cf > (T)10e4 ? (T)10e4 : cf;
         df = df > (T)10e4 ? (T)10e4 : df;
         cf = okm ? cf : (T)0;
@@ -364,58 +417,57 @@ PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& x
         dg1 = tfma<T>(df, f[3] * f[3], dg1);
         if (METHOD == 0) dgp = tfma<T>(df, f[3] * f[0], dgp);
     }
-    const double Ncy1 = N * fy[1], Ncy2 = N * fy[2];
-    const double cpx_d = (double)cpx, dpx2_d = (double)dpx2;
-    num[0] = fma(NPy, (double)cc1, num[0]);
-    den[0] += NPy * (double)cc2 - NPy * NPy * (double)dc1;
-    num[1] = fma(Ncy1, cpx_d, num[1]);
-    den[1] += Ncy2 * cpx_d - Ncy1 * Ncy1 * dpx2_d;
-    num[2] = fma(PSFy, cpx_d, num[2]);
-    den[2] -= PSFy * PSFy * dpx2_d;
-    num[3] += (double)c0;
-    den[3] -= (double)d0;
+    const A Ncy1 = N * (A)fy[1], Ncy2 = N * (A)fy[2];
+    const A cpx_a = (A)cpx, dpx2_a = (A)dpx2;
+    num[0] = tfma<A>(NPy, (A)cc1, num[0]);
+    den[0] += NPy * (A)cc2 - NPy * NPy * (A)dc1;
+    num[1] = tfma<A>(Ncy1, cpx_a, num[1]);
+    den[1] += Ncy2 * cpx_a - Ncy1 * Ncy1 * dpx2_a;
+    num[2] = tfma<A>(PSFy, cpx_a, num[2]);
+    den[2] -= PSFy * PSFy * dpx2_a;
+    num[3] += (A)c0;
+    den[3] -= (A)d0;
     if (METHOD == 1) {
-        const double Ngy1 = N * fy[3], Ngy2 = N * fy[4];
-        num[4] = fma(NPy, (double)cg1, num[4]);
-        den[4] += NPy * (double)cg2 - NPy * NPy * (double)dg1;
-        num[5] = fma(Ngy1, cpx_d, num[5]);
-        den[5] += Ngy2 * cpx_d - Ngy1 * Ngy1 * dpx2_d;
+        const A Ngy1 = N * (A)fy[3], Ngy2 = N * (A)fy[4];
+        num[4] = tfma<A>(NPy, (A)cg1, num[4]);
+        den[4] += NPy * (A)cg2 - NPy * NPy * (A)dg1;
+        num[5] = tfma<A>(Ngy1, cpx_a, num[5]);
+        den[5] += Ngy2 * cpx_a - Ngy1 * Ngy1 * dpx2_a;
     } else {
         // dudt = N (PSFy dPx + PSFx dPy); the reference's d2udt2 has photons on the
         // first term only (gaussmle.py:380-382)
-        const double gy1 = fy[3], gy2 = fy[4];
-        num[4] += N * (PSFy * (double)cg1 + gy1 * cpx_d);
-        den[4] += (NPy * (double)cg2 + 2.0 * gy1 * (double)cg1 + gy2 * cpx_d) -
-                  N * N * (PSFy * PSFy * (double)dg1 + 2.0 * PSFy * gy1 * (double)dgp +
-                           gy1 * gy1 * dpx2_d);
+        const A gy1 = (A)fy[3], gy2 = (A)fy[4];
+        num[4] += N * (PSFy * (A)cg1 + gy1 * cpx_a);
+        den[4] += (NPy * (A)cg2 + (A)2 * gy1 * (A)cg1 + gy2 * cpx_a) -
+                  N * N * (PSFy * PSFy * (A)dg1 + (A)2 * PSFy * gy1 * (A)dgp +
+                           gy1 * gy1 * dpx2_a);
     }
 }
 
-template <int BOX, int METHOD, typename T, class Roi, class Xf>
-PB_HD void newton_sums(const Roi& roi, const float th[6], const Xf& xf, double num[6], double den[6]) {
-    const double N = (double)th[2], bg = (double)th[3];
+template <int BOX, int METHOD, typename T, typename A, class Roi, class Xf>
+PB_HD void newton_sums(const Roi& roi, const float th[6], const Xf& xf, A num[6], A den[6]) {
     const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
 #pragma unroll
-    for (int l = 0; l < 6; l++) { num[l] = 0.0; den[l] = 0.0; }
-    Edge<METHOD> A, B = {};
+    for (int l = 0; l < 6; l++) { num[l] = 0; den[l] = 0; }
+    Edge<METHOD> EA, EB = {};
 #pragma unroll 1
     for (int k = 0; k < (BOX + 1) / 2; k++) {
         double fy[5];
-        A = eval_edge<METHOD>(2 * k, th[1], ay);
+        EA = eval_edge<METHOD>(2 * k, th[1], ay);
         if (k > 0) {
-            pixel_factors<METHOD>(B, A, ay, fy);
-            accumulate_row<BOX, METHOD, T>(2 * k - 1, fy, roi, xf, N, bg, num, den);
+            pixel_factors<METHOD>(EB, EA, ay, fy);
+            accumulate_row<BOX, METHOD, T, A>(2 * k - 1, fy, roi, xf, th[2], th[3], num, den);
         }
-        B = eval_edge<METHOD>(2 * k + 1, th[1], ay);
-        pixel_factors<METHOD>(A, B, ay, fy);
-        accumulate_row<BOX, METHOD, T>(2 * k, fy, roi, xf, N, bg, num, den);
+        EB = eval_edge<METHOD>(2 * k + 1, th[1], ay);
+        pixel_factors<METHOD>(EA, EB, ay, fy);
+        accumulate_row<BOX, METHOD, T, A>(2 * k, fy, roi, xf, th[2], th[3], num, den);
     }
 }
 
 // Clamped per-parameter Newton step in float32 (gaussmle.py:647-670, 860-884).
 // Returns true when the stopping rule is met (:632-638, :844-852).
-template <int BOX, int METHOD>
-PB_HD bool update_theta(float th[6], const float ms[6], const double num[6], const double den[6],
+template <int BOX, int METHOD, typename A>
+PB_HD bool update_theta(float th[6], const float ms[6], const A num[6], const A den[6],
                         double eps) {
     constexpr int NP = METHOD == 1 ? 6 : 5;
     float tn[6];
@@ -562,6 +614,80 @@ PB_HD bool inv_diag_cholesky(const double* m, double* diag) {
     return true;
 }
 
+// One pixel row of the Fisher matrix and the log-likelihood.  dudt_k = (row factor) x (column
+// factor of kind c1 / px / 1 / g1), so the row accumulates the ten 1/model-weighted products of
+// column-factor pairs and the row factors are applied once per row.
+template <int BOX, int METHOD, int NF, class Roi, class Xf3>
+PB_HD void crlb_row(int j, const double fy[5], const Roi& roi, const Xf3& xf, double N, double bg,
+                    double M[NF], double& ll) {
+    constexpr int NP = METHOD == 1 ? 6 : 5;
+    const double PSFy = fy[0], NPy = N * fy[0];
+    double ac[10];
+#pragma unroll
+    for (int q = 0; q < 10; q++) ac[q] = 0.0;
+#pragma unroll
+    for (int i = 0; i < BOX; i++) {
+        double f[3];   // px, c1, g1
+        xf.get(i, f);
+        const double model = fma(f[0], NPy, bg);
+        const double w = rcp64(model);
+        const double c1w = f[1] * w, pxw = f[0] * w, g1w = f[2] * w;
+        ac[0] = fma(c1w, f[1], ac[0]);   // c1 c1
+        ac[1] = fma(c1w, f[0], ac[1]);   // c1 px
+        ac[2] += c1w;                    // c1 1
+        ac[3] = fma(c1w, f[2], ac[3]);   // c1 g1
+        ac[4] = fma(pxw, f[0], ac[4]);   // px px
+        ac[5] += pxw;                    // px 1
+        ac[6] = fma(pxw, f[2], ac[6]);   // px g1
+        ac[7] += w;                      // 1 1
+        ac[8] += g1w;                    // 1 g1
+        ac[9] = fma(g1w, f[2], ac[9]);   // g1 g1
+        const float dataf = roi(j * BOX + i);
+        if (model > 0.0) {
+            // d ln(model) - model - f32(d logf(d)) + d  (gaussmle.py:935-945)
+            if (dataf > 0.0f)
+                ll += (double)dataf * log_pos(model) - model - (double)(dataf * logf(dataf)) +
+                      (double)dataf;
+            else
+                ll -= model;
+        }
+    }
+    // pair index of column-factor kinds: 0 = c1, 1 = px, 2 = one, 3 = g1
+#define PB_PR(p, q) ac[((p) < (q) ? (p) : (q)) * 4 - (((p) < (q) ? (p) : (q)) * (((p) < (q) ? (p) : (q)) - 1)) / 2 + \
+                       (((p) < (q) ? (q) : (p)) - ((p) < (q) ? (p) : (q)))]
+    if (METHOD == 1) {
+        const double arow[6] = {NPy, N * fy[1], PSFy, 1.0, NPy, N * fy[3]};
+        constexpr int kind[6] = {0, 1, 1, 2, 3, 1};
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+#pragma unroll
+            for (int l = k; l < 6; l++) {
+                M[q] = fma(arow[k] * arow[l], PB_PR(kind[k], kind[l]), M[q]);
+                q++;
+            }
+    } else {
+        // dudt_4 = N PSFy g1(i) + N gy1 px(i)
+        const double arow[4] = {NPy, N * fy[1], PSFy, 1.0};
+        constexpr int kind[4] = {0, 1, 1, 2};
+        const double u = NPy, v = N * fy[3];
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int l = k; l < 4; l++) {
+                M[q] = fma(arow[k] * arow[l], PB_PR(kind[k], kind[l]), M[q]);
+                q++;
+            }
+            M[q] = fma(arow[k], u * PB_PR(kind[k], 3) + v * PB_PR(kind[k], 1), M[q]);
+            q++;
+        }
+        M[q] += u * u * PB_PR(3, 3) + 2.0 * u * v * PB_PR(3, 1) + v * v * PB_PR(1, 1);
+    }
+#undef PB_PR
+    (void)NP;
+}
+
 // CRLB + log-likelihood at theta (gaussmle.py:673-742, 887-954).  Xf3 concept: put(col, f[5])
 // keeps (PSF, d/dmu, d/dsigma) of the column; get(col, double f[3]).
 // Returns status flags (bit 1: pseudo-inverse fallback, bit 2: non-finite CRLB).
@@ -573,62 +699,38 @@ PB_HD int crlb_loglik(const Roi& roi, const float th[6], Xf3& xf, float crlb[6],
     const double N = (double)th[2], bg = (double)th[3];
     {
         const Axis ax = make_axis(th[4]);
-        Edge<METHOD> lo = {};
+        Edge<METHOD> EA, EB = {};
 #pragma unroll 1
-        for (int g = 0; g <= BOX; g++) {
-            const Edge<METHOD> hi = eval_edge<METHOD>(g, th[0], ax);
-            if (g > 0) {
-                double f[5];
-                pixel_factors<METHOD>(lo, hi, ax, f);
-                xf.put(g - 1, f);
+        for (int k = 0; k < (BOX + 1) / 2; k++) {
+            double f[5];
+            EA = eval_edge<METHOD>(2 * k, th[0], ax);
+            if (k > 0) {
+                pixel_factors<METHOD>(EB, EA, ax, f);
+                xf.put(2 * k - 1, f);
             }
-            lo = hi;
+            EB = eval_edge<METHOD>(2 * k + 1, th[0], ax);
+            pixel_factors<METHOD>(EA, EB, ax, f);
+            xf.put(2 * k, f);
         }
     }
     double M[NF];
 #pragma unroll
     for (int q = 0; q < NF; q++) M[q] = 0.0;
     double ll = 0.0;
-    const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
-    Edge<METHOD> lo = {};
+    {
+        const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
+        Edge<METHOD> EA, EB = {};
 #pragma unroll 1
-    for (int g = 0; g <= BOX; g++) {
-        const Edge<METHOD> hi = eval_edge<METHOD>(g, th[1], ay);
-        const Edge<METHOD> lo_ = lo;
-        lo = hi;
-        if (g == 0) continue;
-        const int j = g - 1;
-        double fy[5];
-        pixel_factors<METHOD>(lo_, hi, ay, fy);
-        const double PSFy = fy[0], NPy = N * fy[0], Ncy1 = N * fy[1], Ngy1 = N * fy[3];
-#pragma unroll 1
-        for (int i = 0; i < BOX; i++) {
-            double f[3];   // px, c1, g1
-            xf.get(i, f);
-            const double model = fma(N * f[0], PSFy, bg);
-            const double w = 1.0 / model;
-            double du[NP];
-            du[0] = NPy * f[1];
-            du[1] = Ncy1 * f[0];
-            du[2] = PSFy * f[0];
-            du[3] = 1.0;
-            if (METHOD == 1) { du[4] = NPy * f[2]; du[5] = Ngy1 * f[0]; }
-            else du[4] = NPy * f[2] + Ngy1 * f[0];
-            int q = 0;
-#pragma unroll
-            for (int k = 0; k < NP; k++) {
-                const double dw = du[k] * w;
-#pragma unroll
-                for (int l = k; l < NP; l++) { M[q] = fma(dw, du[l], M[q]); q++; }
+        for (int k = 0; k < (BOX + 1) / 2; k++) {
+            double fy[5];
+            EA = eval_edge<METHOD>(2 * k, th[1], ay);
+            if (k > 0) {
+                pixel_factors<METHOD>(EB, EA, ay, fy);
+                crlb_row<BOX, METHOD, NF>(2 * k - 1, fy, roi, xf, N, bg, M, ll);
             }
-            const float dataf = roi(j * BOX + i);
-            if (model > 0.0) {
-                if (dataf > 0.0f)
-                    ll += (double)dataf * log(model) - model - (double)(dataf * logf(dataf)) +
-                          (double)dataf;
-                else
-                    ll -= model;
-            }
+            EB = eval_edge<METHOD>(2 * k + 1, th[1], ay);
+            pixel_factors<METHOD>(EA, EB, ay, fy);
+            crlb_row<BOX, METHOD, NF>(2 * k, fy, roi, xf, N, bg, M, ll);
         }
     }
     *loglik = (float)ll;

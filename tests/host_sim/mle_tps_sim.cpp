@@ -14,9 +14,12 @@ struct RoiPtr {
 };
 template <int BOX, typename T>
 struct XfHost {
-    T a[BOX][5];
-    void put(int c, const double f[5]) { for (int k = 0; k < 5; k++) a[c][k] = (T)f[k]; }
-    void get(int c, T f[5]) const { for (int k = 0; k < 5; k++) f[k] = a[c][k]; }
+    T a[BOX][6];
+    void put(int c, const double f[5]) {
+        for (int k = 0; k < 5; k++) a[c][k] = (T)f[k];
+        a[c][5] = (T)(f[0] - (double)a[c][0]);     // low word of PSFx (0 for T = double)
+    }
+    void get(int c, T f[6]) const { for (int k = 0; k < 6; k++) f[k] = a[c][k]; }
 };
 template <int BOX>
 struct Xf3Host {
@@ -25,7 +28,7 @@ struct Xf3Host {
     void get(int c, double f[3]) const { f[0] = a[c][0]; f[1] = a[c][1]; f[2] = a[c][2]; }
 };
 
-template <int BOX, int METHOD, typename T>
+template <int BOX, int METHOD, typename T, typename A>
 void fit_range(const float* spots, long long n, double eps, int max_it, float* thetas, float* crlbs,
                float* logliks, int* iterations, int* status) {
     for (long long s = 0; s < n; s++) {
@@ -38,9 +41,9 @@ void fit_range(const float* spots, long long n, double eps, int max_it, float* t
             kk++;
             XfHost<BOX, T> xf;
             tps::column_stage<BOX, METHOD, T>(th, xf);
-            double num[6], den[6];
-            tps::newton_sums<BOX, METHOD, T>(roi, th, xf, num, den);
-            if (tps::update_theta<BOX, METHOD>(th, ms, num, den, eps)) break;
+            A num[6], den[6];
+            tps::newton_sums<BOX, METHOD, T, A>(roi, th, xf, num, den);
+            if (tps::update_theta<BOX, METHOD, A>(th, ms, num, den, eps)) break;
         }
         Xf3Host<BOX> x3;
         float cr[6], ll;
@@ -55,12 +58,16 @@ void fit_range(const float* spots, long long n, double eps, int max_it, float* t
 template <int BOX>
 int dispatch(const float* spots, long long n, double eps, int max_it, int method, int f32,
              float* th, float* cr, float* ll, int* it, int* st) {
+    // f32: 0 = float64 pixel sums and row stage, 1 = float32 pixel sums / float64 row stage,
+    //      2 = float32 pixel sums and row stage
     if (method == 1) {
-        if (f32) fit_range<BOX, 1, float>(spots, n, eps, max_it, th, cr, ll, it, st);
-        else fit_range<BOX, 1, double>(spots, n, eps, max_it, th, cr, ll, it, st);
+        if (f32 == 2) fit_range<BOX, 1, float, float>(spots, n, eps, max_it, th, cr, ll, it, st);
+        else if (f32) fit_range<BOX, 1, float, double>(spots, n, eps, max_it, th, cr, ll, it, st);
+        else fit_range<BOX, 1, double, double>(spots, n, eps, max_it, th, cr, ll, it, st);
     } else {
-        if (f32) fit_range<BOX, 0, float>(spots, n, eps, max_it, th, cr, ll, it, st);
-        else fit_range<BOX, 0, double>(spots, n, eps, max_it, th, cr, ll, it, st);
+        if (f32 == 2) fit_range<BOX, 0, float, float>(spots, n, eps, max_it, th, cr, ll, it, st);
+        else if (f32) fit_range<BOX, 0, float, double>(spots, n, eps, max_it, th, cr, ll, it, st);
+        else fit_range<BOX, 0, double, double>(spots, n, eps, max_it, th, cr, ll, it, st);
     }
     return 0;
 }

@@ -48,7 +48,7 @@ def _check(sim, spots, gold, prefix, method, f32, eps=0.001, max_it=100, min_sam
     return th, gth
 
 
-@pytest.mark.parametrize("f32", [0, 1])
+@pytest.mark.parametrize("f32", [0, 1, 2])
 @pytest.mark.parametrize("method", ["sigmaxy", "sigma"])
 def test_sim_config1(sim, golden_dir, method, f32):
     g = np.load(os.path.join(golden_dir, "mle_config1.npz"))
@@ -60,7 +60,7 @@ def test_sim_config1(sim, golden_dir, method, f32):
         assert bit >= 0.7, bit
 
 
-@pytest.mark.parametrize("f32", [0, 1])
+@pytest.mark.parametrize("f32", [0, 1, 2])
 @pytest.mark.parametrize("method", ["sigmaxy", "sigma"])
 @pytest.mark.parametrize("box", [5, 9, 11, 13])
 def test_sim_boxes(sim, golden_dir, box, method, f32):
@@ -69,7 +69,7 @@ def test_sim_boxes(sim, golden_dir, box, method, f32):
     _check(sim, spots, g, f"b{box}_", method, f32)
 
 
-@pytest.mark.parametrize("f32", [0, 1])
+@pytest.mark.parametrize("f32", [0, 1, 2])
 @pytest.mark.parametrize("method", ["sigmaxy", "sigma"])
 @pytest.mark.parametrize("tag,eps,max_it", [("e3", 1e-3, 100), ("e6", 1e-6, 100),
                                             ("it3", 1e-3, 3), ("it0", 1e-3, 0)])
