@@ -43,9 +43,21 @@ EPS = 0.001
 MAX_IT = 100
 METHOD = "sigmaxy"
 BYTES_PER_SPOT = BOX * BOX * 4 + 56   # 196 B ROI read + 56 B results written
-# dram__bytes_read.sum + dram__bytes_write.sum of mle_fit_kernel<7,8,1> for 1 M spots from the
-# committed `ncu --set full` capture (profiles/r01_mle_ncu.md): 197.5 MB + 41.1 MB
-NCU_DRAM_BYTES_PER_SPOT = 238.6
+# The fit runs as three kernels (csrc/mle_tps.cu): start values, Newton iterations (dominant,
+# ~75 % of the step), CRLB + log-likelihood.  Algorithmic bytes of the dominant kernel per spot:
+# ROI 196 + start theta 24 read, theta 24 + iterations 4 written.
+ITER_BYTES_PER_SPOT = BOX * BOX * 4 + 24 + 28
+# dram__bytes_read.sum + dram__bytes_write.sum of tps_iter_kernel<7,1,float> for 4 M spots from
+# the committed `ncu --set full` capture (profiles/r01_mle_tps_ncu.md): 881.9 MB + 104.2 MB
+NCU_ITER_DRAM_BYTES_PER_SPOT = 246.5
+# all three kernels: 3 ROI reads + 2 theta reads + theta x2, iterations x2, crlb, logL written
+PIPELINE_DRAM_BYTES_PER_SPOT = 3 * BOX * BOX * 4 + 2 * 24 + (24 + 4) * 2 + 28
+
+
+# from profiles/r01_mle_tps_ncu.md (tps_iter_kernel<7,1,float>, 4 M spots)
+COMPUTE_NCU = {"source": "ncu --set full, profiles/r01_mle_tps_ncu.md",
+               "issue_slots_busy_pct": 66.6, "fp64_pipe_busy_pct": 50.2, "xu_pipe_busy_pct": 38.0,
+               "warp_instructions_per_spot": 1004}
 
 
 def parse():
@@ -313,6 +325,7 @@ def main():
         step(i)
     drain()
     barrier()
+    _lib.check(lib.pb_mle_profile(1))     # CUDA events around the three kernels of each call
     launches0 = _lib.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -342,10 +355,14 @@ def main():
     launches = _lib.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
-    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
+    k3 = np.zeros(3, np.float32)          # {start values, iterations, CRLB} of the last step
+    if lib.pb_mle_get_impl() != 0:
+        _lib.check(lib.pb_mle_profile_read(k3.ctypes.data))
+    _lib.check(lib.pb_mle_profile(0))
+    t = torch.tensor([ms_total, ms_kernel, *k3.tolist()], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_kernel = t.tolist()
+    ms_total, ms_kernel, ms_init, ms_iter, ms_crlb = t.tolist()
     th, cr, ll, it = views(flats[0])
     mean_it = float(it.float().mean().item())
     value = n * world * args.steps / (ms_total * 1e-3)
@@ -388,31 +405,49 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        ach = BYTES_PER_SPOT * n / (ms_kernel * 1e-3) / 1e9
+        tps = ms_iter > 0
+        if tps:
+            ach = ITER_BYTES_PER_SPOT * n / (ms_iter * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "tps_iter_kernel<7,1,float> (Newton iterations)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": NCU_ITER_DRAM_BYTES_PER_SPOT * n,
+                    "traffic_source": "ncu --set full, profiles/r01_mle_tps_ncu.md (bytes/spot x spots per launch)",
+                    "algorithmic_bytes": ITER_BYTES_PER_SPOT * n, "peak_source": peak_src,
+                    "kernel_ms": ms_iter,
+                    "step_kernels_ms": {"tps_init_kernel": ms_init, "tps_iter_kernel": ms_iter,
+                                        "tps_crlb_kernel": ms_crlb, "step": ms_kernel},
+                    "step_algorithmic_GBs": BYTES_PER_SPOT * n / (ms_kernel * 1e-3) / 1e9,
+                    "step_dram_bytes": PIPELINE_DRAM_BYTES_PER_SPOT * n,
+                    "note": "algorithmic 248 B/spot for the iteration kernel (252 B/spot for the "
+                            "whole fit; the three kernels together move 720 B/spot = "
+                            f"{PIPELINE_DRAM_BYTES_PER_SPOT * n / (ms_kernel * 1e-3) / 1e9 / peak:.1%} of "
+                            "HBM peak). The fit is instruction-issue / FP64-pipe bound, not HBM "
+                            "bound (SURVEY.md 8d) -- see `compute` and DESIGN.md 5.1"}
+        else:
+            ach = BYTES_PER_SPOT * n / (ms_kernel * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "mle_fit_kernel<7,8,1> (lane-group)", "achieved": ach,
+                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 238.6 * n,
+                    "algorithmic_bytes": BYTES_PER_SPOT * n, "peak_source": peak_src,
+                    "kernel_ms": ms_kernel}
         line = {
             "metric": "MLE spot-fits/sec (7x7 ROI)", "value": value, "unit": "fits/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64 math / f32 state", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": "f64 edge terms / f32 pixel sums with float-float residual / f32 state",
+            "data": "synthetic",
             "config": {"workload": "configs[1]: 10M synthetic 7x7 spots/GPU, gaussmle sigmaxy "
                                    "eps=1e-3 max_it=100", "box": BOX, "method": METHOD,
                        "spots_per_gpu": n, "mean_iterations": mean_it,
+                       "mle_impl": int(lib.pb_mle_get_impl()),
                        "l2": "input 1.96 GB per step >> 126 MB L2 (no flush needed)",
                        "parallelism": f"spots sharded by index over {world} GPU(s)"
                                       + ("; one NCCL all-gather of the packed outputs per step, "
                                          "overlapped with the next step's fit" if world > 1 else "")},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_SPOT * n,
-                         "traffic_source": "ncu --set full, profiles/r01_mle_ncu.md (bytes/spot x spots per launch)",
-                         "algorithmic_bytes": BYTES_PER_SPOT * n, "peak_source": peak_src,
-                         "kernel_ms": ms_kernel,
-                         "note": "algorithmic 252 B/spot; the fit is FP64-issue bound, not HBM bound "
-                                 "(SURVEY.md 8d) -- see `compute` and DESIGN.md 5.1"},
-            # instruction-side view of the same kernel from the committed ncu --set full capture
-            # (profiles/r01_mle_ncu.md, v3): what actually bounds the fit
-            "compute": {"source": "ncu --set full, profiles/r01_mle_ncu.md (v3)",
-                        "fp64_pipe_busy_pct": 47.7, "issue_slots_busy_pct": 61.9,
-                        "warp_instructions_per_spot": 3613},
+            "roofline": roof,
+            # instruction-side view of the dominant kernel from the committed ncu --set full
+            # capture (profiles/r01_mle_tps_ncu.md): what actually bounds the fit
+            "compute": COMPUTE_NCU,
             "clocks": clocks, "gpu_launches": launches,
         }
         if e2e is not None:

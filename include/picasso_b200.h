@@ -85,6 +85,12 @@ int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double eps, int max_
 int pb_mle_set_impl(int impl);
 int pb_mle_get_impl(void);
 
+/* Measurement hook for bench.py: when enabled, the thread-per-spot path records CUDA events on
+ * the launch stream around its three kernels; pb_mle_profile_read waits for the most recent
+ * call and returns their durations in ms: {start values, Newton iterations, CRLB + logL}. */
+int pb_mle_profile(int enable);
+int pb_mle_profile_read(float* ms3);
+
 /* ---- spot identification ------------------------------------------------
  * Replaces localize.identify_in_image / identify_in_frame / identify_by_frame_number
  * and the frame loops _identify_serial / identify_async

@@ -410,6 +410,15 @@ long long segment_spots(int pix) {
     return env > 0 ? env : (1ll << 40);
 }
 
+// Optional per-kernel timing (pb_mle_profile / pb_mle_profile_read): CUDA events recorded on
+// the launch stream around the three kernels of the most recent call.
+struct TpsProfile {
+    std::atomic<bool> on{false};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool recorded = false;
+};
+TpsProfile g_prof;
+
 template <int BOX, int METHOD, typename T>
 int launch_tps(const TpsArgs& a0, cudaStream_t stream) {
     constexpr int PIX = BOX * BOX;
@@ -419,34 +428,57 @@ int launch_tps(const TpsArgs& a0, cudaStream_t stream) {
     auto k_iter = tps_iter_kernel<BOX, METHOD, T>;
     auto k_crlb = tps_crlb_kernel<BOX, METHOD>;
     constexpr int init_smem = kThreads * PIX * 4 + 16;
-    int dev = 0, num_sms = 0, per_sm = 0;
+    int dev = 0;
     PB_CUDA_CHECK(cudaGetDevice(&dev));
-    PB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    PB_CUDA_CHECK(cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, init_smem));
-    PB_CUDA_CHECK(cudaFuncSetAttribute(k_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, ISM::kTotal));
-    PB_CUDA_CHECK(cudaFuncSetAttribute(k_crlb, cudaFuncAttributeMaxDynamicSharedMemorySize, CSM::kTotal));
-    PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_iter, kThreads, ISM::kTotal));
-    if (per_sm < 1) {
-        pb_set_error("mle iteration kernel does not fit on an SM (box=%d)", BOX);
-        return PB_ERR_CUDA;
+    // per-device launch configuration of this instantiation, set up once
+    struct Cfg { int num_sms = 0, per_sm = 0; };
+    static std::mutex cfg_mu;
+    static std::vector<Cfg> cfgs;
+    Cfg cfg;
+    {
+        std::lock_guard<std::mutex> lk(cfg_mu);
+        if ((int)cfgs.size() <= dev) cfgs.resize(dev + 1);
+        if (cfgs[dev].per_sm == 0) {
+            Cfg c;
+            PB_CUDA_CHECK(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
+            PB_CUDA_CHECK(cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, init_smem));
+            PB_CUDA_CHECK(cudaFuncSetAttribute(k_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, ISM::kTotal));
+            PB_CUDA_CHECK(cudaFuncSetAttribute(k_crlb, cudaFuncAttributeMaxDynamicSharedMemorySize, CSM::kTotal));
+            PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, k_iter, kThreads, ISM::kTotal));
+            if (c.per_sm < 1) {
+                pb_set_error("mle iteration kernel does not fit on an SM (box=%d)", BOX);
+                return PB_ERR_CUDA;
+            }
+            cfgs[dev] = c;
+        }
+        cfg = cfgs[dev];
     }
+    const int num_sms = cfg.num_sms, per_sm = cfg.per_sm;
+    const bool prof = g_prof.on.load() && g_prof.ev[0] != nullptr;
     const long long seg = segment_spots(PIX);
     for (long long first = 0; first < a0.n; first += seg) {
         const long long m = a0.n - first < seg ? a0.n - first : seg;
         TpsArgs a = a0;
         const int chunks = (int)((m + kThreads - 1) / kThreads);
-        k_init<<<chunks, kThreads, init_smem, stream>>>(a, first, m);
-        g_pb_launches++;
         if (a.max_it > 0) {
             int rc = next_counter(dev, stream, &a.counter);
             if (rc != PB_OK) return rc;
+        }
+        const bool p = prof && first == 0;
+        if (p) cudaEventRecord(g_prof.ev[0], stream);
+        k_init<<<chunks, kThreads, init_smem, stream>>>(a, first, m);
+        g_pb_launches++;
+        if (p) cudaEventRecord(g_prof.ev[1], stream);
+        if (a.max_it > 0) {
             long long cap = (long long)num_sms * per_sm;
             int grid = (int)(chunks < cap ? chunks : cap);
             k_iter<<<grid, kThreads, ISM::kTotal, stream>>>(a, first, m);
             g_pb_launches++;
         }
+        if (p) cudaEventRecord(g_prof.ev[2], stream);
         k_crlb<<<chunks, kThreads, CSM::kTotal, stream>>>(a, first, m);
         g_pb_launches++;
+        if (p) { cudaEventRecord(g_prof.ev[3], stream); g_prof.recorded = true; }
     }
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;
@@ -479,4 +511,22 @@ int pb_mle_tps_fit(size_t n, int box, const float* d_spots, double eps, int max_
     if (method == 1)
         return pixel_f32 ? dispatch_tps<1, float>(box, a, stream) : dispatch_tps<1, double>(box, a, stream);
     return pixel_f32 ? dispatch_tps<0, float>(box, a, stream) : dispatch_tps<0, double>(box, a, stream);
+}
+
+// Measurement hooks (include/picasso_b200.h): time the three kernels of the next
+// thread-per-spot calls with CUDA events on their launch stream.
+extern "C" int pb_mle_profile(int enable) {
+    if (enable && g_prof.ev[0] == nullptr)
+        for (int i = 0; i < 4; i++) PB_CUDA_CHECK(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.on.store(enable != 0);
+    return PB_OK;
+}
+extern "C" int pb_mle_profile_read(float* ms3) {
+    if (!ms3 || !g_prof.recorded) {
+        pb_set_error("pb_mle_profile_read: nothing recorded (enable pb_mle_profile and run a fit)");
+        return PB_ERR_INVALID;
+    }
+    PB_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[3]));
+    for (int i = 0; i < 3; i++) PB_CUDA_CHECK(cudaEventElapsedTime(&ms3[i], g_prof.ev[i], g_prof.ev[i + 1]));
+    return PB_OK;
 }
