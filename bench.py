@@ -225,7 +225,7 @@ def run_reference(args, rank, world):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def gen_spots_device(torch, n, box, seed, device):
@@ -257,8 +257,27 @@ def gen_spots_device(torch, n, box, seed, device):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, library
+    chatter) was redirected to stderr for the whole run."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # keep stdout to the single JSON line: fd 1 -> stderr until the line is emitted
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -278,8 +297,8 @@ def main():
     lib = _lib.load()
     _lib.require_gpu()
     if world > 1:
-        # keep stdout to the single JSON line (NCCL prints its version banner at INFO/VERSION)
-        os.environ["NCCL_DEBUG"] = os.environ.get("PB_NCCL_DEBUG", "WARN")
+        if "PB_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["PB_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.spots
@@ -460,7 +479,7 @@ def main():
                 "value": r, "unit": "fits/s", "cores": used, "kind": "port", "host": cpu,
                 "sample": f"{d} spots in {el:.1f} s (same distribution), oracle C port of "
                           "picasso.gaussmle._mlefit_sigmaxy, bit-identical to the numba reference"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

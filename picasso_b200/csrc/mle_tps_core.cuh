@@ -382,29 +382,35 @@ PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& x
         const T data = (T)roi(j * BOX + i);
         T model, inv, cf, df;
         if (sizeof(T) == 4) {
-            const float p = (float)f[0] * (float)NPy_t;                    // hi part of N PSFx PSFy
-            const float pe = fmaf((float)f[0], (float)NPy_t, -p);           // its rounding error
-            const float cross = fmaf((float)f[0], NPy_lo, (float)f[5] * (float)NPy_t);
+            const float px = (float)f[0], NPh = (float)NPy_t;
+            const float p = px * NPh;                                   // hi part of N PSFx PSFy
+            // rounding error of p plus the low-word cross terms, three fused steps
+            float pc = fmaf(px, NPy_lo, fmaf(px, NPh, -p));
+            pc = fmaf((float)f[5], NPh, pc);
             model = (T)(p + (float)bg_t);
-            inv = trcp<T>(model);
             const float a = (float)data - p;          // exact when data and p are within 2x
-            const float r = (a - (float)bg_t) - (pe + cross);
-            cf = (T)(r * (float)inv);
+            const float r = (a - (float)bg_t) - pc;
+            // guard (gaussmle.py:829-835): model > 0.01, else cf = df = 0 -- folded into 1/model
+            const float iv = model > (T)10e-3 ? rcp32((float)model) : 0.0f;
+            inv = (T)iv;
+            cf = (T)(r * iv);
             df = data * inv * inv;
+            cf = cf > (T)10e4 ? (T)10e4 : cf;          // cf, df <= 1e5
+            df = df > (T)10e4 ? (T)10e4 : df;
         } else {
             model = tfma<T>(f[0], NPy_t, bg_t);
+            // guards (gaussmle.py:829-835): model > 0.01, cf, df <= 1e5; NaN / inf from a
+            // non-positive model are discarded by the select
+            const bool okm = model > (T)10e-3;
             inv = trcp<T>(model);
             const T t = data * inv;
             cf = t - (T)1;
             df = t * inv;
+            cf = cf > (T)10e4 ? (T)10e4 : cf;
+            df = df > (T)10e4 ? (T)10e4 : df;
+            cf = okm ? cf : (T)0;
+            df = okm ? df : (T)0;
         }
-        // guards (gaussmle.py:829-835): model > 0.01, cf, df <= 1e5; NaN / inf from a
-        // non-positive model are discarded by the select
-        const bool okm = model > (T)10e-3;
-        cf = cf > (T)10e4 ? (T)10e4 : cf;
-        df = df > (T)10e4 ? (T)10e4 : df;
-        cf = okm ? cf : (T)0;
-        df = okm ? df : (T)0;
         c0 += cf;
         cpx = tfma<T>(cf, f[0], cpx);
         cc1 = tfma<T>(cf, f[1], cc1);
