@@ -48,16 +48,16 @@ BYTES_PER_SPOT = BOX * BOX * 4 + 56   # 196 B ROI read + 56 B results written (S
 # ROI 196 + start theta 24 read, theta 24 + iterations 4 written.
 ITER_BYTES_PER_SPOT = BOX * BOX * 4 + 24 + 28
 # dram__bytes_read.sum + dram__bytes_write.sum of tps_iter_kernel<7,1,float> for 4 M spots from
-# the committed `ncu --set full` capture (profiles/r01_mle_tps_ncu.md): 881.9 MB + 104.2 MB
-NCU_ITER_DRAM_BYTES_PER_SPOT = 246.5
+# the committed `ncu --set full` capture (profiles/r01_mle_tps_ncu.md, v4): 881.3 MB + 103.7 MB
+NCU_ITER_DRAM_BYTES_PER_SPOT = 246.3
 # all three kernels: 3 ROI reads + 2 theta reads + theta x2, iterations x2, crlb, logL written
 PIPELINE_DRAM_BYTES_PER_SPOT = 3 * BOX * BOX * 4 + 2 * 24 + (24 + 4) * 2 + 28
 
 
 # from profiles/r01_mle_tps_ncu.md (tps_iter_kernel<7,1,float>, 4 M spots)
 COMPUTE_NCU = {"source": "ncu --set full, profiles/r01_mle_tps_ncu.md",
-               "issue_slots_busy_pct": 66.6, "fp64_pipe_busy_pct": 50.2, "xu_pipe_busy_pct": 38.0,
-               "warp_instructions_per_spot": 1004}
+               "issue_slots_busy_pct": 71.4, "fp64_pipe_busy_pct": 41.9, "fma_pipe_busy_pct": 27.7,
+               "xu_pipe_busy_pct": 33.6, "warp_instructions_per_spot": 1119}
 
 
 def parse():
