@@ -196,6 +196,11 @@ int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_l
  * The arg-max / 5x5 peak fit / minimize_shifts stay on the host. */
 int pb_rcc_windows(int n_seg, int Y, int X, const float* segments, int Y0, int X0, int H, int W,
                    float* windows, double* sums);
+/* Inverse-transform strategy of the pair stage: -1 = auto (default: pruned inverse DFT of the
+ * window rows / columns only when the window covers at most a quarter of the image, else cuFFT
+ * C2R + crop), 0 = always cuFFT, 1 = always pruned.  PB_RCC_PRUNED=0/1 in the environment sets
+ * the initial value. */
+int pb_rcc_set_mode(int mode);
 /* building blocks with device pointers (multi-GPU callers shard pairs across ranks) */
 int pb_rcc_spectra_dev(int n_seg, int Y, int X, const float* d_segments, void* d_spectra,
                        double* d_sums, void* stream);

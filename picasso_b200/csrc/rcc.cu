@@ -8,10 +8,15 @@
 // The reference recomputes fft2(A), fft2(B) and one ifft2 for EVERY pair in
 // float64 on the CPU (3 FFTs x n(n-1)/2 pairs).  Here:
 //   * one batched cuFFT R2C per SEGMENT (half-spectra kept resident in HBM),
-//   * per pair: a fused conj-multiply kernel -> batched cuFFT C2R -> a crop
-//     kernel that applies fftshift + the 1/(N*sqrt(N)) normalisation and copies
-//     only the central `roi` window (the reference crops it after the fact,
-//     imageprocess.py:88-101) -- 4 KB per pair go back to the host,
+//   * per pair, when only a small centre window of the correlation is read (the reference
+//     crops `roi` x `roi` pixels after the fact, imageprocess.py:88-101): a PRUNED inverse
+//     transform -- stage 1 multiplies the two half-spectra and evaluates the inverse DFT
+//     along y for the window rows only (each spectrum is read once, nothing is written
+//     back but H x (X/2+1) coefficients), stage 2 evaluates the real inverse DFT along x
+//     for the window columns with fftshift + the 1/(N*sqrt(N)) normalisation folded in,
+//   * otherwise (full-size windows): a fused conj-multiply kernel -> batched cuFFT C2R ->
+//     a crop kernel,
+//   * 4 KB per pair go back to the host,
 //   * the arg-max + 5x5 peak fit stay on the host (picasso_b200/imageprocess.py).
 // float32 transforms: the peak is fitted from a 5x5 window of O(1)-relative
 // values; cuFFT's 1e-6 relative error moves the fitted shift by << 1e-3 px.
@@ -19,6 +24,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cufft.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "pb_common.cuh"
@@ -87,13 +93,170 @@ __global__ void rcc_sum_kernel(const float* __restrict__ img, size_t elems, doub
     }
 }
 
+// ---- pruned inverse transform (window rows / columns only) -----------------------------
+// corr[y][x] = sum_ky sum_kx w_kx Re(P[ky][kx] e^{2 pi i (ky y / Y + kx x / X)}) over the half
+// spectrum (w = 1 for kx = 0 and the Nyquist column, else 2), P = F_i conj(F_j).
+//
+// Stage 1: T[pair][r][kx] = sum_ky P[ky][kx] e^{2 pi i ky y_r / Y} for the window rows y_r.
+// Block = 64 kx columns x 4 ky groups (each group owns a quarter of the rows; partial sums are
+// combined through shared memory at the end -- also keeps the float32 sums short).  A warp is
+// 32 adjacent columns of one group: 256-byte coalesced spectrum loads, twiddles broadcast from
+// shared memory, 32 complex accumulators per thread in registers (128 FFMA per spectrum pair).
+constexpr int kPR = 32;        // window rows per pass
+constexpr int kKC = 16;        // ky per twiddle chunk
+constexpr int kS1Cols = 64;
+constexpr int kS1Groups = 4;
+
+__global__ void __launch_bounds__(kS1Cols * kS1Groups, 2)
+rcc_pruned_rows_kernel(const float2* __restrict__ spectra, size_t spec_elems,
+                       const int* __restrict__ pi, const int* __restrict__ pj, int Y, int XH,
+                       int ywin0, int row0, int nrows, int H, float2* __restrict__ T) {
+    extern __shared__ __align__(16) unsigned char rcc_smem[];
+    float2* tw = reinterpret_cast<float2*>(rcc_smem);            // [groups][kKC][kPR]
+    float2* red = reinterpret_cast<float2*>(rcc_smem);           // [2][kPR][kS1Cols] (aliases tw)
+    const int tx = threadIdx.x & (kS1Cols - 1);
+    const int g = threadIdx.x / kS1Cols;
+    const int kx = blockIdx.x * kS1Cols + tx;
+    const bool col_ok = kx < XH;
+    const int pair = blockIdx.y;
+    const float2* A = spectra + (size_t)pi[pair] * spec_elems;
+    const float2* B = spectra + (size_t)pj[pair] * spec_elems;
+    const int per = (Y + kS1Groups - 1) / kS1Groups;
+    const int k0 = g * per;
+    const int k1 = k0 + per < Y ? k0 + per : Y;
+    float accr[kPR], acci[kPR];
+#pragma unroll
+    for (int r = 0; r < kPR; r++) { accr[r] = 0.f; acci[r] = 0.f; }
+    const float invY = 1.0f / (float)Y;
+    for (int kb = 0; kb < per; kb += kKC) {
+        __syncthreads();
+        // twiddles of this chunk: e^{2 pi i ky y_r / Y}, argument reduced exactly in integers
+        for (int e = tx; e < kKC * kPR; e += kS1Cols) {
+            const int kc = e / kPR, r = e % kPR;
+            const long long ky = k0 + kb + kc;
+            const long long yy = (ywin0 + row0 + r) % Y;
+            const int m = (int)((ky * yy) % Y);
+            float sn, cs;
+            sincospif(2.0f * (float)m * invY, &sn, &cs);
+            tw[(g * kKC + kc) * kPR + r] = make_float2(cs, sn);
+        }
+        __syncthreads();
+        if (col_ok) {
+            const float2* twg = tw + g * kKC * kPR;
+#pragma unroll 4
+            for (int kc = 0; kc < kKC; kc++) {
+                const int ky = k0 + kb + kc;
+                if (ky < k1) {
+                    const float2 a = __ldg(A + (size_t)ky * XH + kx);
+                    const float2 b = __ldg(B + (size_t)ky * XH + kx);
+                    const float px = fmaf(a.x, b.x, a.y * b.y);      // a * conj(b)
+                    const float py = fmaf(a.y, b.x, -a.x * b.y);
+                    const float4* t4 = reinterpret_cast<const float4*>(twg + kc * kPR);
+#pragma unroll
+                    for (int r = 0; r < kPR; r += 2) {
+                        const float4 t = t4[r >> 1];               // (cos, sin) of rows r, r+1
+                        accr[r] = fmaf(px, t.x, fmaf(-py, t.y, accr[r]));
+                        acci[r] = fmaf(px, t.y, fmaf(py, t.x, acci[r]));
+                        accr[r + 1] = fmaf(px, t.z, fmaf(-py, t.w, accr[r + 1]));
+                        acci[r + 1] = fmaf(px, t.w, fmaf(py, t.z, acci[r + 1]));
+                    }
+                }
+            }
+        }
+    }
+    // combine the four ky groups: (2,3) -> scratch, (0,1) add; 1 -> scratch, 0 adds and stores
+    __syncthreads();
+    if (g >= 2) {
+#pragma unroll
+        for (int r = 0; r < kPR; r++)
+            red[((g - 2) * kPR + r) * kS1Cols + tx] = make_float2(accr[r], acci[r]);
+    }
+    __syncthreads();
+    if (g < 2) {
+#pragma unroll
+        for (int r = 0; r < kPR; r++) {
+            const float2 v = red[(g * kPR + r) * kS1Cols + tx];
+            accr[r] += v.x;
+            acci[r] += v.y;
+        }
+    }
+    __syncthreads();
+    if (g == 1) {
+#pragma unroll
+        for (int r = 0; r < kPR; r++) red[r * kS1Cols + tx] = make_float2(accr[r], acci[r]);
+    }
+    __syncthreads();
+    if (g == 0 && col_ok) {
+        float2* out = T + ((size_t)pair * H + row0) * XH + kx;
+#pragma unroll
+        for (int r = 0; r < kPR; r++) {
+            if (r < nrows) {
+                const float2 v = red[r * kS1Cols + tx];
+                out[(size_t)r * XH] = make_float2(accr[r] + v.x, acci[r] + v.y);
+            }
+        }
+    }
+}
+
+// Stage 2: out[pair][r][c] = scale * sum_kx w_kx Re(T[pair][r][kx] e^{2 pi i kx x_c / X}).
+// One block per (window row, pair): 32 columns x 8 kx slices, float64 accumulation.
+__global__ void __launch_bounds__(256)
+rcc_pruned_cols_kernel(const float2* __restrict__ T, int H, int W, int XH, int X, int xwin0,
+                       double scale, float* __restrict__ out) {
+    __shared__ double part[8][33];
+    const int row = blockIdx.x, pair = blockIdx.y;
+    const int c = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const float2* Trow = T + ((size_t)pair * H + row) * XH;
+    const float invX = 1.0f / (float)X;
+    for (int c0 = 0; c0 < W; c0 += 32) {
+        const int cc = c0 + c;
+        const long long xx = (xwin0 + (cc < W ? cc : 0)) % X;
+        double sum = 0.0;
+        for (int kx = sl; kx < XH; kx += 8) {
+            const float2 t = __ldg(Trow + kx);
+            const int m = (int)(((long long)kx * xx) % X);
+            float sn, cs;
+            sincospif(2.0f * (float)m * invX, &sn, &cs);
+            const float wgt = (kx == 0 || ((X & 1) == 0 && kx == X / 2)) ? 1.0f : 2.0f;
+            sum += (double)(wgt * (t.x * cs - t.y * sn));
+        }
+        part[sl][c] = sum;
+        __syncthreads();
+        if (sl == 0 && cc < W) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) s += part[q][c];
+            out[((size_t)pair * H + row) * W + cc] = (float)(s * scale);
+        }
+        __syncthreads();
+    }
+}
+
 struct CufftPlan {
     cufftHandle h = 0;
     bool ok = false;
     ~CufftPlan() { if (ok) cufftDestroy(h); }
 };
 
+// -1 auto (pruned when the window covers at most a quarter of the image), 0 cuFFT, 1 pruned
+std::atomic<int> g_rcc_mode{-2};
+int rcc_mode() {
+    int v = g_rcc_mode.load();
+    if (v == -2) {
+        v = -1;
+        if (const char* e = getenv("PB_RCC_PRUNED")) v = atoi(e) ? 1 : 0;
+        g_rcc_mode.store(v);
+    }
+    return v;
+}
+
 }  // namespace
+
+extern "C" int pb_rcc_set_mode(int mode) {
+    if (mode < -1 || mode > 1) { pb_set_error("pb_rcc_set_mode: mode must be -1, 0 or 1"); return PB_ERR_INVALID; }
+    g_rcc_mode.store(mode);
+    return PB_OK;
+}
 
 // Forward transforms of all segments: d_spectra[s] = rfft2(d_segments[s]) (unnormalised),
 // plus per-segment sums.  d_spectra holds n_seg * Y * (X/2+1) float2.
@@ -136,6 +299,38 @@ extern "C" int pb_rcc_windows_dev(int n_pairs, const int* d_pair_i, const int* d
         return PB_ERR_INVALID;
     }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int mode = rcc_mode();
+    if (mode == 1 || (mode == -1 && (size_t)H * W * 4 <= (size_t)Y * X)) {
+        // pruned inverse transform: only the H x W window is evaluated
+        const int XH = X / 2 + 1;
+        const size_t t_per_pair = (size_t)H * XH * sizeof(float2);
+        int pb = (int)std::min<size_t>(workspace_bytes / t_per_pair, 32768);
+        pb = std::max(1, std::min(pb, n_pairs));
+        float2* T = static_cast<float2*>(d_workspace);
+        int ywin0 = (Y0 - Y / 2) % Y; if (ywin0 < 0) ywin0 += Y;
+        int xwin0 = (X0 - X / 2) % X; if (xwin0 < 0) xwin0 += X;
+        const double scale = 1.0 / ((double)Y * X) / sqrt((double)Y * X);
+        const int smem1 = 2 * kPR * kS1Cols * (int)sizeof(float2);    // 32 KB (>= twiddle chunk)
+        static_assert(kS1Groups * kKC * kPR <= 2 * kPR * kS1Cols, "scratch must hold the twiddles");
+        for (int p0 = 0; p0 < n_pairs; p0 += pb) {
+            const int nb = std::min(pb, n_pairs - p0);
+            for (int row0 = 0; row0 < H; row0 += kPR) {
+                const int nrows = std::min(kPR, H - row0);
+                dim3 g1((XH + kS1Cols - 1) / kS1Cols, nb);
+                rcc_pruned_rows_kernel<<<g1, kS1Cols * kS1Groups, smem1, s>>>(
+                    static_cast<const float2*>(d_spectra), spec, d_pair_i + p0, d_pair_j + p0, Y, XH,
+                    ywin0, row0, nrows, H, T);
+                g_pb_launches++;
+            }
+            dim3 g2(H, nb);
+            rcc_pruned_cols_kernel<<<g2, 256, 0, s>>>(T, H, W, XH, X, xwin0, scale,
+                                                      d_windows + (size_t)p0 * H * W);
+            g_pb_launches++;
+        }
+        PB_CUDA_CHECK(cudaGetLastError());
+        PB_CUDA_CHECK(cudaStreamSynchronize(s));
+        return PB_OK;
+    }
     float2* prod = static_cast<float2*>(d_workspace);
     float* corr = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + (size_t)batch * spec * 8);
     CufftPlan plan, tail;

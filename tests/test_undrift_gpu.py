@@ -128,3 +128,40 @@ def test_fused_undrift_equals_segment_plus_rcc(problem):
     postprocess.undrift(locs, info, 100, display=False, segmentation_callback=seg_cb.append,
                         rcc_callback=rcc_cb.append)
     assert seg_cb == list(range(9)) and rcc_cb == list(range(29))
+
+
+@pytest.mark.parametrize("shape,win", [((64, 64), (0, 0, 64, 64)), ((96, 80), (32, 24, 32, 32)),
+                                       ((128, 66), (40, 10, 37, 21)), ((50, 36), (9, 2, 32, 32)),
+                                       ((256, 256), (112, 112, 32, 32))])
+def test_pruned_inverse_equals_cufft_and_numpy(shape, win):
+    """The pruned inverse DFT of the window rows / columns (csrc/rcc.cu) and the cuFFT C2R + crop
+    path give the same correlation window as numpy's float64 xcorr (imageprocess.py:27-50)."""
+    import ctypes as C
+
+    from picasso_b200 import _lib
+    l = _lib.load()
+    l.pb_rcc_set_mode.argtypes = [C.c_int]
+    Y, X = shape
+    Y0, X0, H, W = win
+    rng = np.random.default_rng(5)
+    segs = rng.poisson(2.0, (3, Y, X)).astype(np.float32)
+    segs[1] = np.roll(segs[0], (2, -3), (0, 1)) + rng.poisson(0.3, (Y, X))
+    out = {}
+    try:
+        for mode in (0, 1):
+            assert l.pb_rcc_set_mode(mode) == 0
+            w = np.zeros((3, H, W), np.float32)
+            sums = np.zeros(3, np.float64)
+            _lib.check(l.pb_rcc_windows(3, Y, X, _lib.ptr(segs), Y0, X0, H, W, _lib.ptr(w), _lib.ptr(sums)))
+            out[mode] = w
+    finally:
+        l.pb_rcc_set_mode(-1)
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    for k, (i, j) in enumerate(pairs):
+        a, b = segs[i].astype(np.float64), segs[j].astype(np.float64)
+        ref = np.fft.fftshift(np.real(np.fft.ifft2(np.fft.fft2(a) * np.conj(np.fft.fft2(b))))) / np.sqrt(a.size)
+        ref = ref[Y0:Y0 + H, X0:X0 + W]
+        tol = 5e-6 * np.abs(ref).max()
+        np.testing.assert_allclose(out[0][k], ref, rtol=0, atol=tol)
+        np.testing.assert_allclose(out[1][k], ref, rtol=0, atol=tol)
+    assert l.pb_rcc_set_mode(7) != 0

@@ -243,30 +243,49 @@ def stage_rcc(torch, small):
     H = W = 32
     win = torch.empty((n_pairs, H, W), device="cuda")
     Y0, X0 = (Y - 32) // 2, (X - 32) // 2
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    rc = lib.pb_rcc_windows_dev(n_pairs, dpi.data_ptr(), dpj.data_ptr(), Y, X, spec.data_ptr(), Y0, X0, H, W,
-                                win.data_ptr(), batch, ws.data_ptr(), wsb, st)
-    torch.cuda.synchronize()
-    t_pairs = time.perf_counter() - t0
-    assert rc == 0
-    traffic = n_pairs * (3 * Y * (X // 2 + 1) * 8 + 2 * Y * X * 4)   # mul: 2 reads + 1 write; C2R: >= 1 read + 1 write
+    lib.pb_rcc_set_mode.argtypes = [C.c_int]
     # CPU: numpy xcorr for one pair (f64, pocketfft)
     a = seg[0].cpu().numpy().astype(np.float64); b = seg[1].cpu().numpy().astype(np.float64)
     t0 = time.perf_counter()
     xc = np.fft.fftshift(np.real(np.fft.ifft2(np.fft.fft2(a) * np.conj(np.fft.fft2(b))))) / np.sqrt(a.size)
     t_cpu = time.perf_counter() - t0
-    gwin = win[0].cpu().numpy()
     ref = xc[Y0:Y0 + 32, X0:X0 + 32]
+    spec_b = Y * (X // 2 + 1) * 8
+    res = {}
+    for mode, name in ((1, "pruned"), (0, "cufft")):
+        assert lib.pb_rcc_set_mode(mode) == 0
+        npr = n_pairs if (mode == 1 or small) else min(n_pairs, 4000)   # cuFFT path: timed sample
+        win.zero_()
+        lib.pb_rcc_windows_dev(min(npr, 64), dpi.data_ptr(), dpj.data_ptr(), Y, X, spec.data_ptr(), Y0, X0,
+                               H, W, win.data_ptr(), batch, ws.data_ptr(), wsb, st)      # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = lib.pb_rcc_windows_dev(npr, dpi.data_ptr(), dpj.data_ptr(), Y, X, spec.data_ptr(), Y0, X0, H, W,
+                                    win.data_ptr(), batch, ws.data_ptr(), wsb, st)
+        torch.cuda.synchronize()
+        t_pairs = time.perf_counter() - t0
+        assert rc == 0
+        if mode == 1:
+            # each pair reads both half-spectra once and writes H x (X/2+1) coefficients
+            traffic = npr * (2 * spec_b + 2 * H * (X // 2 + 1) * 8)
+            flops = npr * Y * (X // 2 + 1) * (8 * H + 6)
+            note = "algorithmic: both half-spectra read once per pair (the i-spectrum mostly from L2)"
+        else:
+            traffic = npr * (3 * spec_b + 2 * Y * X * 4)   # mul: 2 reads + 1 write; C2R: >= 1 read + 1 write
+            flops = None
+            note = "minimum traffic of multiply + C2R passes; cuFFT does more than one pass"
+        gwin = win[0].cpu().numpy()
+        res[name] = {"pairs_timed": int(npr), "seconds": t_pairs, "pairs_per_s": npr / t_pairs,
+                     "all_pairs_seconds": t_pairs * n_pairs / npr,
+                     "roofline": {"bound": "hbm", "achieved": traffic / t_pairs / 1e9, "peak": peaks(),
+                                  "unit": "GB/s", "frac": traffic / t_pairs / 1e9 / peaks(), "note": note},
+                     "fp32_tflops": None if flops is None else flops / t_pairs / 1e12,
+                     "window_max_abs_err_vs_numpy_f64": float(np.abs(gwin - ref).max())}
+    lib.pb_rcc_set_mode(-1)
     print(json.dumps({
-        "stage": "rcc (config 5)", "n_seg": n_seg, "image": [Y, X], "n_pairs": n_pairs,
-        "forward_r2c_all_segments_ms": t_spec, "all_pairs_seconds": t_pairs,
-        "pairs_per_s": n_pairs / t_pairs,
-        "roofline": {"bound": "hbm", "achieved": traffic / t_pairs / 1e9, "peak": peaks(), "unit": "GB/s",
-                     "frac": traffic / t_pairs / 1e9 / peaks(),
-                     "note": "minimum traffic of multiply + C2R passes; cuFFT does more than one pass"},
+        "stage": "rcc (config 5)", "n_seg": n_seg, "image": [Y, X], "n_pairs": n_pairs, "window": [H, W],
+        "forward_r2c_all_segments_ms": t_spec, **res,
         "cpu_numpy_xcorr_one_pair_s": t_cpu, "cpu_all_pairs_extrapolated_h": t_cpu * n_pairs / 3600,
-        "window_max_abs_err_vs_numpy_f64": float(np.abs(gwin - ref).max()),
         "window_peak": float(ref.max())}), flush=True)
 
 
