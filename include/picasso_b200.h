@@ -143,6 +143,43 @@ int pb_identify_get_spots(const void* movie, int dtype, size_t n_frames, int Y, 
                           long long* x, long long* y, float* ng, float* spots, size_t capacity,
                           size_t* n_found);
 
+/* ---- fused movie -> localisation table -----------------------------------------
+ * Replaces the body of localize.localize (picasso/localize.py:1682-1815): identify
+ * (:639-712) -> get_spots (:1115-1145) -> gaussmle.gaussmle (gaussmle.py:409-475) or
+ * gausslq.fit_spots (gausslq.py:247-289) -> locs_from_fits (gaussmle.py:957-1037,
+ * gausslq.py:404-544) in ONE pass over a host movie chunk: every frame crosses PCIe once,
+ * identifications / ROIs / theta / CRLB stay on the GPU, only the finished localisation
+ * columns come back.
+ *   fit      0 = MLE "sigma", 1 = MLE "sigmaxy", 2 = LQ, 3 = LQ in the Gpufit column layout
+ *            (fit_spots_gpufit + locs_from_fits_gpufit, gausslq.py:346-395, 487-544)
+ *   em       camera_info["Gain"] > 1 (doubles the LQ localisation variance, gausslq.py:547-589)
+ *   columns  (pb_locs_columns(fit), capacity) 4-byte elements, column-major:
+ *            MLE (17): frame u32, x, y, photons, sx, sy, bg, lpx, lpy, ellipticity, net_gradient,
+ *                      log_likelihood f32, iterations u32, photons_unc, bg_unc, sx_unc, sy_unc f32
+ *            LQ  (11): frame u32, x, y, photons, sx, sy, bg, lpx, lpy, ellipticity, net_gradient
+ *            rows ordered by (frame, y, x) of the identification -- the serial reference's order
+ *   n_found  number of localisations; above `capacity` the call returns PB_ERR_CAPACITY with
+ *            the required capacity in *n_found
+ * Pageable movies are staged through pinned buffers by PB_COPY_THREADS (default 8) host
+ * threads; pinned movies (pb_host_alloc) are copied directly. */
+int pb_locs_columns(int fit);
+int pb_localize(const void* movie, int dtype, size_t n_frames, int Y, int X, long long frame_offset,
+                int box, double min_ng, const int* roi, float baseline, float sensitivity,
+                float gain, int fit, double eps, int max_it, int em, void* columns,
+                size_t capacity, size_t* n_found);
+/* The column arithmetic alone (numpy's evaluation order and dtypes, float32 IEEE operations):
+ * identifications + fit results -> the columns above.  crlbs / logliks / iterations are read
+ * for fit 0/1 only; for fit 3 `thetas` is in the Gpufit layout [photons, x, y, sx, sy, bg].
+ * `ld` = elements between two columns of d_columns (>= n). */
+int pb_locs_from_fits(size_t n, int fit, int box, int em, const long long* frame,
+                      const long long* x, const long long* y, const float* ng, const float* thetas,
+                      const float* crlbs, const float* logliks, const int* iterations,
+                      void* columns);
+int pb_locs_from_fits_dev(size_t n, int fit, int box, int em, const long long* d_frame,
+                          const long long* d_x, const long long* d_y, const float* d_ng,
+                          const float* d_thetas, const float* d_crlbs, const float* d_logliks,
+                          const int* d_iterations, void* d_columns, size_t ld, void* stream);
+
 /* ---- least-squares Gaussian fit --------------------------------------------
  * Replaces picasso.gausslq.fit_spot / fit_spots / fit_spots_parallel
  * (picasso/gausslq.py:206-343: scipy.optimize.leastsq == MINPACK lmdif with

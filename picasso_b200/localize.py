@@ -38,6 +38,13 @@ def _declare(lib):
     lib.pb_identify_get_spots.argtypes = [vp, i32, sz, i32, i32, i64, i32, f64, vp, f32, f32, f32,
                                           vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
     lib.pb_identify_get_spots.restype = i32
+    lib.pb_locs_columns.argtypes = [i32]
+    lib.pb_locs_columns.restype = i32
+    lib.pb_localize.argtypes = [vp, i32, sz, i32, i32, i64, i32, f64, vp, f32, f32, f32, i32, f64, i32,
+                                i32, vp, sz, C.POINTER(sz)]
+    lib.pb_localize.restype = i32
+    lib.pb_locs_from_fits.argtypes = [sz, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.pb_locs_from_fits.restype = i32
     lib._localize_declared = True
 
 
@@ -376,6 +383,107 @@ def _identify_and_cut(movie, minimum_ng, box, camera_info, roi=None, frame_bound
     return ids, np.ascontiguousarray(cat[4])
 
 
+LOCS_COLUMNS_MLE = ("frame", "x", "y", "photons", "sx", "sy", "bg", "lpx", "lpy", "ellipticity",
+                    "net_gradient", "log_likelihood", "iterations", "photons_unc", "bg_unc",
+                    "sx_unc", "sy_unc")
+LOCS_COLUMNS_LQ = LOCS_COLUMNS_MLE[:11]
+_UINT_COLUMNS = ("frame", "iterations")
+_FIT_IDS = {("gaussmle", "sigma"): 0, ("gaussmle", "sigmaxy"): 1, ("gausslq", None): 2,
+            ("gausslq-gpu", None): 3}
+_FUSED_CALL_BYTES = 1 << 30
+
+
+def _columns_to_locs(cols, names):
+    """(ncols, n) 4-byte column block -> DataFrame with the reference's dtypes (zero-copy
+    views), then the reference's final ``sort_values(by="frame", kind="quicksort")``."""
+    data = {}
+    for k, name in enumerate(names):
+        data[name] = cols[k].view(np.uint32) if name in _UINT_COLUMNS else cols[k]
+    locs = pd.DataFrame(data, copy=False)
+    locs.sort_values(by="frame", kind="quicksort", inplace=True)
+    return locs
+
+
+def locs_columns_from_fits(identifications: pd.DataFrame, theta, box: int, fit: int, em: bool = False,
+                           CRLBs=None, log_likelihoods=None, iterations=None):
+    """The localization-table column arithmetic of ``gaussmle.locs_from_fits`` (fit 0/1),
+    ``gausslq.locs_from_fits`` (2) and ``locs_from_fits_gpufit`` (3) evaluated on the GPU
+    (csrc/localize.cu): returns ``{column: array}`` in identification order (unsorted)."""
+    lib = _lib_ready()
+    n = len(identifications)
+    names = LOCS_COLUMNS_MLE if fit <= 1 else LOCS_COLUMNS_LQ
+    cols = np.zeros((len(names), n), np.float32)
+    if n:
+        c64 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.int64)   # noqa: E731
+        c32 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.float32)   # noqa: E731
+        fr, xs, ys = (c64(identifications[k]) for k in ("frame", "x", "y"))
+        ng = c32(identifications["net_gradient"])
+        th = c32(theta)
+        cr = c32(CRLBs) if fit <= 1 else None
+        ll = c32(log_likelihoods) if fit <= 1 else None
+        it = np.ascontiguousarray(np.asarray(iterations), dtype=np.int32) if fit <= 1 else None
+        _lib.check(lib.pb_locs_from_fits(n, int(fit), int(box), int(bool(em)), _lib.ptr(fr), _lib.ptr(xs),
+                                         _lib.ptr(ys), _lib.ptr(ng), _lib.ptr(th),
+                                         _lib.ptr(cr) if cr is not None else None,
+                                         _lib.ptr(ll) if ll is not None else None,
+                                         _lib.ptr(it) if it is not None else None, _lib.ptr(cols)))
+    return {name: (cols[k].view(np.uint32) if name in _UINT_COLUMNS else cols[k])
+            for k, name in enumerate(names)}
+
+
+def _localize_fused(movie, minimum_ng, box, camera_info, fit, eps, max_it, roi=None,
+                    frame_bounds=None, progress_callback=None):
+    """movie -> localization table without leaving the GPU in between (``pb_localize``):
+    identify -> get_spots -> fit -> locs_from_fits per frame chunk; only the finished columns
+    come back.  Same result as ``identify`` + ``fit2D``."""
+    lib = _lib_ready()
+    N = len(movie)
+    lo, hi = _frame_range(N, frame_bounds)
+    roi_arr = _roi_array(roi)
+    baseline = float(camera_info["Baseline"])
+    sensitivity = float(camera_info["Sensitivity"])
+    gain = float(camera_info["Gain"])
+    em = int(camera_info["Gain"] > 1)
+    names = LOCS_COLUMNS_MLE if fit <= 1 else LOCS_COLUMNS_LQ
+    assert lib.pb_locs_columns(fit) == len(names)
+    parts = []
+    if N:
+        first = np.asarray(movie[0])
+        per_frame = max(1, first.size * (2 if first.dtype == np.uint16 else 4))
+        step = max(1, _FUSED_CALL_BYTES // per_frame)
+    f = 0
+    while f < N:
+        f1 = min(N, f + step)
+        a, b = max(f, lo), min(f1, hi + 1)
+        if a < b:
+            chunk, dtype = _as_device_movie(_movie_chunk(movie, a, b))
+            F, Y, X = chunk.shape
+            capacity = max(4096, 128 * F)
+            while True:
+                cols = np.empty((len(names), capacity), np.float32)
+                found = C.c_size_t(0)
+                rc = lib.pb_localize(_lib.ptr(chunk), dtype, F, Y, X, a, int(box), float(minimum_ng),
+                                     _lib.ptr(roi_arr) if roi_arr is not None else None, baseline,
+                                     sensitivity, gain, int(fit), float(eps), int(max_it), em,
+                                     _lib.ptr(cols), capacity, C.byref(found))
+                if rc == 4:
+                    capacity = int(found.value)
+                    continue
+                _lib.check(rc)
+                parts.append(cols[:, :int(found.value)])
+                break
+        if callable(progress_callback):
+            progress_callback(f1)
+        f = f1
+    if len(parts) == 1:
+        cols = parts[0]
+    elif parts:
+        cols = np.concatenate(parts, axis=1)
+    else:
+        cols = np.zeros((len(names), 0), np.float32)
+    return _columns_to_locs(cols, names)
+
+
 def _fit_spots(spots, identifications, box, camera_info, fitting_method, eps, max_it, mle_method,
                progress_callback):
     from . import gausslq, gaussmle
@@ -467,17 +575,29 @@ def localize(movie, camera_info: dict, parameters: dict, *, roi=None, frame_boun
         warnings.warn("Camera info in picasso.localize.fit2D does not contain 'Pixelsize', "
                       "i.e., effective camera pixel size in nm. Assuming 130.")
         camera_info["Pixelsize"] = 130
-    # identify + get_spots fused: each movie chunk crosses PCIe once
-    identifications, spots = _identify_and_cut(
-        movie, minimum_ng, box, camera_info, roi=roi, frame_bounds=frame_bounds,
-        progress_callback=identification_progress_callback
-        if callable(identification_progress_callback) else None)
+    id_cb = identification_progress_callback if callable(identification_progress_callback) else None
+    fit_id = _FIT_IDS.get((fitting_method, mle_method if fitting_method == "gaussmle" else None))
+    if fit_id is not None and isinstance(box, int) and 5 <= box <= 15 and box % 2 == 1:
+        # movie -> locs in one pass: each chunk crosses PCIe once, only the table comes back
+        locs = _localize_fused(movie, minimum_ng, box, camera_info, fit_id, eps, max_it, roi=roi,
+                               frame_bounds=frame_bounds, progress_callback=id_cb)
+        if callable(fit_progress_callback):
+            if fitting_method == "gausslq-gpu":
+                fit_progress_callback(1)
+            else:
+                for i in range(len(locs)):
+                    fit_progress_callback(i)
+    else:
+        # identify + get_spots fused (one upload), fit from host ROIs
+        identifications, spots = _identify_and_cut(
+            movie, minimum_ng, box, camera_info, roi=roi, frame_bounds=frame_bounds,
+            progress_callback=id_cb)
+        locs = _fit_spots(spots, identifications, box, camera_info, fitting_method, eps, max_it,
+                          mle_method, fit_progress_callback)
     identify_info = {
         "Generated by": f"Picasso: v{__version__} Identify (picasso_b200)",
         "Min. Net Gradient": minimum_ng, "Box Size": box, "ROI": roi, "Frame Bounds": frame_bounds,
     }
-    locs = _fit_spots(spots, identifications, box, camera_info, fitting_method, eps, max_it,
-                      mle_method, fit_progress_callback)
     fit_info = {"Generated by": f"Picasso: v{__version__} Fit 2D (picasso_b200)",
                 "Fit method": fitting_method}
     if fitting_method == "gaussmle":

@@ -146,6 +146,59 @@ def stage_identify(torch, small):
                       "fits_per_s": len(spots) / (ms_lq * 1e-3)}), flush=True)
 
 
+def stage_localize(torch, small):
+    """Config 3 end to end through the fused movie -> localization-table path (pb_localize and
+    localize.localize): host movie in (pageable / pinned), locs DataFrame out."""
+    from picasso_b200 import _lib, localize
+
+    lib = _lib.load()
+    localize._declare(lib)
+    F, Y, X = (200, 512, 512) if small else (2000, 512, 512)
+    movie = gen_movie_device(torch, F, Y, X)
+    hmovie = movie.cpu().numpy()
+    del movie
+    pin = _lib.PinnedArray(hmovie.shape, hmovie.dtype)
+    pin.array[...] = hmovie
+    cam = {"Baseline": 100, "Sensitivity": 1.0, "Gain": 1, "Pixelsize": 130}
+    par = {"Min. Net Gradient": 5000, "Box Size": 7}
+    out = {"stage": "localize fused (config 3)", "movie": [F, Y, X], "movie_bytes": int(hmovie.nbytes)}
+    for fm in ("gausslq", "gaussmle"):
+        localize.localize(hmovie[:8], dict(cam), par, return_info=False, fitting_method=fm)
+        for name, mv in (("pageable", hmovie), ("pinned", pin.array)):
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                locs = localize.localize(mv, dict(cam), par, return_info=False, fitting_method=fm)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            out[f"{fm}_{name}"] = {"seconds": best, "fps": F / best, "n_locs": len(locs),
+                                   "movie_GBs": hmovie.nbytes / best / 1e9}
+        # the C call alone (no pandas)
+        fit = 2 if fm == "gausslq" else 1
+        ncol = lib.pb_locs_columns(fit)
+        cap = 256 * F
+        cols = np.empty((ncol, cap), np.float32)
+        found = C.c_size_t(0)
+        for name, mv in (("pageable", hmovie), ("pinned", pin.array)):
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                rc = lib.pb_localize(_lib.ptr(mv), 0, F, Y, X, 0, 7, 5000.0, None, 100.0, 1.0, 1.0, fit, 1e-3,
+                                     100, 0, _lib.ptr(cols), cap, C.byref(found))
+                dt = time.perf_counter() - t0
+                assert rc == 0
+                best = dt if best is None else min(best, dt)
+            out[f"{fm}_{name}_c_call"] = {"seconds": best, "fps": F / best, "n_locs": int(found.value),
+                                          "movie_GBs": hmovie.nbytes / best / 1e9}
+    # two-call path for comparison (ROIs via host)
+    t0 = time.perf_counter()
+    ids = localize.identify(hmovie, 5000, 7, return_info=False)
+    locs2, _ = localize.fit2D(hmovie, [], dict(cam), ids, 7, fitting_method="gausslq")
+    out["two_call_identify_fit2D_gausslq_seconds"] = time.perf_counter() - t0
+    pin.free()
+    print(json.dumps(out), flush=True)
+
+
 def stage_render(torch, small):
     from picasso_b200 import _lib, render as pbrender
 
@@ -329,5 +382,5 @@ if __name__ == "__main__":
     small = "--small" in sys.argv
     which = args or ["identify", "render", "rcc"]
     for w in which:
-        {"identify": stage_identify, "render": stage_render, "rcc": stage_rcc,
+        {"identify": stage_identify, "localize": stage_localize, "render": stage_render, "rcc": stage_rcc,
          "undrift": stage_undrift}[w](torch, small)
