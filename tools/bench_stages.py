@@ -305,9 +305,11 @@ def stage_rcc(torch, small):
     ref = xc[Y0:Y0 + 32, X0:X0 + 32]
     spec_b = Y * (X // 2 + 1) * 8
     res = {}
-    for mode, name in ((1, "pruned"), (0, "cufft")):
+    ref_win = None
+    for mode, name, fft in ((1, "pruned_fft", "1"), (1, "pruned_direct", "0"), (0, "cufft", "1")):
+        os.environ["PB_RCC_FFT"] = fft
         assert lib.pb_rcc_set_mode(mode) == 0
-        npr = n_pairs if (mode == 1 or small) else min(n_pairs, 4000)   # cuFFT path: timed sample
+        npr = n_pairs if (name == "pruned_fft" or small) else min(n_pairs, 4000)   # slower paths: timed sample
         win.zero_()
         lib.pb_rcc_windows_dev(min(npr, 64), dpi.data_ptr(), dpj.data_ptr(), Y, X, spec.data_ptr(), Y0, X0,
                                H, W, win.data_ptr(), batch, ws.data_ptr(), wsb, st)      # warm-up
@@ -321,19 +323,28 @@ def stage_rcc(torch, small):
         if mode == 1:
             # each pair reads both half-spectra once and writes H x (X/2+1) coefficients
             traffic = npr * (2 * spec_b + 2 * H * (X // 2 + 1) * 8)
-            flops = npr * Y * (X // 2 + 1) * (8 * H + 6)
-            note = "algorithmic: both half-spectra read once per pair (the i-spectrum mostly from L2)"
+            flops = npr * Y * (X // 2 + 1) * (8 * H + 6) if fft == "0" else None
+            note = "algorithmic: both half-spectra read once per pair (mostly from L2 with pair tiling)"
         else:
             traffic = npr * (3 * spec_b + 2 * Y * X * 4)   # mul: 2 reads + 1 write; C2R: >= 1 read + 1 write
             flops = None
             note = "minimum traffic of multiply + C2R passes; cuFFT does more than one pass"
         gwin = win[0].cpu().numpy()
+        cur = win[:min(npr, 4000)].clone()
+        if ref_win is None:
+            ref_win = cur
+            dev_vs_first = 0.0
+        else:
+            m = min(len(cur), len(ref_win))
+            dev_vs_first = float((cur[:m] - ref_win[:m]).abs().max())
         res[name] = {"pairs_timed": int(npr), "seconds": t_pairs, "pairs_per_s": npr / t_pairs,
                      "all_pairs_seconds": t_pairs * n_pairs / npr,
                      "roofline": {"bound": "hbm", "achieved": traffic / t_pairs / 1e9, "peak": peaks(),
                                   "unit": "GB/s", "frac": traffic / t_pairs / 1e9 / peaks(), "note": note},
                      "fp32_tflops": None if flops is None else flops / t_pairs / 1e12,
-                     "window_max_abs_err_vs_numpy_f64": float(np.abs(gwin - ref).max())}
+                     "window_max_abs_err_vs_numpy_f64": float(np.abs(gwin - ref).max()),
+                     "max_abs_dev_vs_pruned_fft_windows": dev_vs_first}
+    os.environ.pop("PB_RCC_FFT", None)
     lib.pb_rcc_set_mode(-1)
     print(json.dumps({
         "stage": "rcc (config 5)", "n_seg": n_seg, "image": [Y, X], "n_pairs": n_pairs, "window": [H, W],
