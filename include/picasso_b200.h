@@ -194,6 +194,28 @@ int pb_lq_fit(size_t n, int box, const float* spots, float* thetas, int* infos, 
 int pb_lq_fit_dev(size_t n, int box, const float* d_spots, float* d_thetas, int* d_infos,
                   int* d_nfevs, void* stream);
 
+/* ---- astigmatic z fit ----------------------------------------------------------
+ * Replaces the per-localization loop and column arithmetic of picasso.zfit._fit_z
+ * (picasso/zfit.py:327-383, behind zfit.zfit :465-646 / localize.localize_3D
+ * localize.py:1818-2034): scipy.optimize.minimize_scalar(_fit_z_target, bounds=[-1000, 1000])
+ * = scipy's bounded Brent minimiser (xatol 1e-5, maxiter 500) on the target of zfit.py:255-291
+ * with the degree-6 calibration polynomials cx, cy (7 float64 each, z^6 .. z^0), then
+ *   z = float32(x_min) * magnification,  d_zcalib = sqrt(float32(f_min)),
+ *   lpz = _axial_localization_precision_astig (zfit.py:805-890), float32 like the reference's
+ *         pandas columns; sigma errors from gausslq.sigma_uncertainty (method 0),
+ *         gaussmle.sigma_uncertainty (1) or the sx_unc / sy_unc columns (2).
+ *   sx, sy, photons, bg, sx_unc, sy_unc  float32[n] (photons/bg only for lpz, *_unc only for
+ *   method 2);  z, d_zcalib, lpz float32[n] (lpz nullable);  nfev int32[n] nullable.
+ * ensure_sanity / filter_z_fits stay on the host (picasso_b200/zfit.py). */
+int pb_zfit(size_t n, const float* sx, const float* sy, const float* photons, const float* bg,
+            const float* sx_unc, const float* sy_unc, const double* cx, const double* cy,
+            double magnification, double pixelsize, int method, float* z, float* d_zcalib,
+            float* lpz, int* nfev);
+int pb_zfit_dev(size_t n, const float* d_sx, const float* d_sy, const float* d_photons,
+                const float* d_bg, const float* d_sx_unc, const float* d_sy_unc, const double* cx,
+                const double* cy, double magnification, double pixelsize, int method, float* d_z,
+                float* d_d_zcalib, float* d_lpz, int* d_nfev, void* stream);
+
 /* ---- rendering ----------------------------------------------------------------
  * Replaces the unrotated paths of picasso.render.render (picasso/render.py:37-174):
  * _render_hist (:798-853, mode 0), _render_gaussian (:1020-1112, mode 1) and

@@ -22,6 +22,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 LIBS = ["-lcufft"]
+# per-file flags: the z fit follows the reference's float64 trajectory without fused multiply-adds
+FILE_FLAGS = {"zfit.cu": ["-fmad=false"]}
 
 
 def _sources():
@@ -49,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
-        cmd = [NVCC, *ARCH, *CFLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *ARCH, *CFLAGS, *FILE_FLAGS.get(src, []), *extra, "-c", os.path.join(CSRC, src),
+               "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -1,5 +1,5 @@
 """The few ``picasso.lib`` helpers the hot path needs (reference picasso/lib.py):
-``get_from_metadata`` :878-920 and ``minimize_shifts`` :2034-2078.  Host-side numpy;
+``get_from_metadata`` :878-920, ``ensure_sanity`` :1786-1832 and ``minimize_shifts`` :2034-2078.  Host-side numpy;
 no GUI code."""
 from __future__ import annotations
 
@@ -42,3 +42,20 @@ def minimize_shifts(shifts_x, shifts_y, shifts_z=None):
     Dj = np.dot(np.linalg.pinv(A), rij)
     out = tuple(np.insert(np.cumsum(Dj[:, c]), 0, 0) for c in range(len(stacks)))
     return out
+
+
+def ensure_sanity(locs, info):
+    """Drop localizations with inf / NaN entries, outside the image or with negative
+    precisions / sizes (reference lib.py:1786-1832); ``info`` must hold Width, Height, Frames."""
+    locs = locs.copy()
+    locs.replace([np.inf, -np.inf], np.nan, inplace=True)
+    locs.dropna(axis=0, how="any", inplace=True)
+    for key in ["Width", "Height", "Frames"]:
+        if get_from_metadata(info, key) is None:
+            raise KeyError(f"Metadata is missing required key: '{key}'")
+    locs = locs[locs["x"] < get_from_metadata(info, "Width")]
+    locs = locs[locs["y"] < get_from_metadata(info, "Height")]
+    for attr in ["x", "y", "lpx", "lpy", "lpz", "photons", "ellipticity", "sx", "sy"]:
+        if attr in locs.columns:
+            locs = locs[locs[attr] >= 0]
+    return locs

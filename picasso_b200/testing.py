@@ -111,3 +111,38 @@ def synthetic_drift_locs(n_frames: int, Y: int, X: int, n_clusters: int = 40,
     drift = np.stack([amp_x * np.sin(2 * np.pi * np.arange(n_frames) / (n_frames / 2.0)),
                       amp_y * (np.arange(n_frames) / n_frames - 0.5)], 1)
     return locs, info, drift
+
+
+def synthetic_zfit_locs(n: int, seed: int = 11):
+    """2-D fitted localizations of an astigmatic 3-D acquisition with a degree-6 calibration
+    (coefficient order z^6 .. z^0 like picasso's calibration YAML): returns (locs, info,
+    calibration).  A few localizations have widths outside the calibrated range."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    cx = [1.0e-19, -2.0e-16, 1.0e-12, 2.0e-10, 1.5e-6, 1.2e-3, 1.30]
+    cy = [-1.5e-19, 1.0e-16, 1.2e-12, -2.5e-10, 1.4e-6, -1.1e-3, 1.32]
+    z = rng.uniform(-350, 350, n)
+    wx = np.polyval(cx, z)
+    wy = np.polyval(cy, z)
+    sx = (wx + rng.normal(0, 0.03, n)).astype(np.float32)
+    sy = (wy + rng.normal(0, 0.03, n)).astype(np.float32)
+    k = max(1, n // 100)
+    sx[:k] = rng.uniform(2.5, 3.5, k).astype(np.float32)        # outside the calibration
+    sy[k:2 * k] = rng.uniform(0.3, 0.6, k).astype(np.float32)
+    photons = rng.uniform(500, 5000, n).astype(np.float32)
+    bg = rng.uniform(5, 30, n).astype(np.float32)
+    locs = pd.DataFrame({
+        "frame": np.sort(rng.integers(0, 1000, n)).astype(np.uint32),
+        "x": rng.uniform(1, 63, n).astype(np.float32), "y": rng.uniform(1, 63, n).astype(np.float32),
+        "photons": photons, "sx": sx, "sy": sy, "bg": bg,
+        "lpx": rng.uniform(0.01, 0.05, n).astype(np.float32),
+        "lpy": rng.uniform(0.01, 0.05, n).astype(np.float32),
+        "ellipticity": (np.abs(sx - sy) / np.maximum(sx, sy)).astype(np.float32),
+        "net_gradient": rng.uniform(5000, 20000, n).astype(np.float32),
+        "sx_unc": (sx / np.sqrt(photons) * rng.uniform(0.9, 1.5, n)).astype(np.float32),
+        "sy_unc": (sy / np.sqrt(photons) * rng.uniform(0.9, 1.5, n)).astype(np.float32),
+    })
+    info = [{"Width": 64, "Height": 64, "Frames": 1000, "Pixelsize": 130}]
+    calib = {"X Coefficients": cx, "Y Coefficients": cy, "Magnification factor": 0.79}
+    return locs, info, calib

@@ -1,0 +1,79 @@
+"""GPU parity of the astigmatic z fit (csrc/zfit.cu through pb_zfit): the Brent trajectory is
+BIT-IDENTICAL to scipy's minimize_scalar on the real reference's target (z, residual and number
+of function evaluations, golden + oracle); lpz (float32 column arithmetic, the reference uses
+libm powf for z**k) within 2e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from picasso_b200 import testing, zfit
+
+pytestmark = pytest.mark.gpu
+
+CASES = (("lq_f0", "gausslq", True, 0), ("lq_f2", "gausslq", True, 2),
+         ("mle_f0", "gaussmle", True, 0), ("mleunc_f2", "gaussmle", False, 2))
+LPZ_RTOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "zfit.npz"))
+
+
+def test_minimiser_bit_identical_to_reference(g):
+    locs, info, calib = testing.synthetic_zfit_locs(3000, 11)
+    z, dz, lpz, nfev = zfit._run(locs, g["cx"], g["cy"], 1.0, 130, "gausslq", want_nfev=True)
+    assert z.tobytes() == g["raw_z"].astype(np.float32).tobytes()
+    assert dz.tobytes() == np.sqrt(g["raw_fun"].astype(np.float32)).tobytes()
+    np.testing.assert_array_equal(nfev, g["raw_nfev"])
+
+
+@pytest.mark.parametrize("tag,method,drop_unc,flt", CASES)
+def test_zfit_tables_match_reference(g, tag, method, drop_unc, flt):
+    locs, info, calib = testing.synthetic_zfit_locs(3000, 11)
+    if drop_unc:
+        locs = locs.drop(columns=["sx_unc", "sy_unc"])
+    n_info = len(info)
+    res, new_info = zfit.zfit(locs, info, calibration=dict(calib), fitting_method=method, filter=flt)
+    np.testing.assert_array_equal(res.index.to_numpy(), g[f"{tag}_index"])
+    assert list(res.columns[-3:]) == ["z", "d_zcalib", "lpz"]
+    for c in ("z", "d_zcalib", "lpz"):
+        assert res[c].dtype == np.float32
+    assert res["z"].to_numpy().tobytes() == g[f"{tag}_z"].tobytes()
+    assert res["d_zcalib"].to_numpy().tobytes() == g[f"{tag}_d_zcalib"].tobytes()
+    np.testing.assert_allclose(res["lpz"].to_numpy(), g[f"{tag}_lpz"], rtol=LPZ_RTOL)
+    assert len(new_info) == n_info + 1 and new_info[-1]["Filter range"] == flt
+    assert new_info[-1]["X Coefficients"] == calib["X Coefficients"]
+
+
+def test_large_batch_matches_oracle(oracle):
+    """200 k localizations: z, residual and nfev bit-identical to the C oracle; recovered z close
+    to the simulated one inside the calibrated range."""
+    locs, info, calib = testing.synthetic_zfit_locs(200_000, 5)
+    cx, cy = np.array(calib["X Coefficients"]), np.array(calib["Y Coefficients"])
+    z, dz, lpz, nfev = zfit._run(locs, cx, cy, 1.0, 130, "gaussmle", want_nfev=True)
+    oz, osq, _, _, onf = oracle.zfit_minimise(locs["sx"].to_numpy(), locs["sy"].to_numpy(), cx, cy)
+    assert z.tobytes() == oz.tobytes()
+    assert dz.tobytes() == np.sqrt(osq).tobytes()
+    np.testing.assert_array_equal(nfev, onf)
+    assert np.isfinite(lpz[2000:]).all() and (lpz[2000:] > 0).all()
+
+
+def test_api_contract(g):
+    locs, info, calib = testing.synthetic_zfit_locs(500, 3)
+    seen = []
+    res, inf2 = zfit.zfit(locs, [{"Width": 64, "Height": 64, "Frames": 1000}], calibration=dict(calib),
+                          pixelsize=100, magnification_factor=1.0, filter=0, progress_callback=seen.append)
+    assert seen == list(range(500))
+    assert inf2[-2] == {"Pixelsize": 100.0} and inf2[-1]["Magnification factor"] == 1.0
+    res2, _ = zfit.zfit(locs, info, calibration=dict(calib), filter=0)
+    # z scales with the magnification factor (reference test_zfit.py:222-234)
+    both = res.index.intersection(res2.index)
+    np.testing.assert_allclose(res2.loc[both, "z"], res.loc[both, "z"] * np.float32(0.79), rtol=1e-6)
+    par = zfit.fit_z_parallel(locs, info, calib, 0.79, 130, filter=0)
+    assert par["z"].to_numpy().tobytes() == res2["z"].to_numpy().tobytes()
+    fut = zfit.fit_z_parallel(locs, info, calib, 0.79, 130, asynch=True)
+    assert len(zfit.locs_from_futures(fut, filter=0)) == len(res2)
+    lp = zfit.axial_localization_precision(res2, info, calib, "gausslq")
+    np.testing.assert_allclose(lp.to_numpy(), res2["lpz"].to_numpy(), rtol=LPZ_RTOL)

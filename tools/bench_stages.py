@@ -199,6 +199,52 @@ def stage_localize(torch, small):
     print(json.dumps(out), flush=True)
 
 
+def stage_zfit(torch, small):
+    """Astigmatic z fit: pb_zfit_dev on device-resident columns, the Python
+    API end to end, and the CPU oracle (bit-identical to scipy's minimize_scalar loop)."""
+    from picasso_b200 import _lib, testing, zfit
+
+    lib = _lib.load()
+    zfit._declare(lib)
+    vp = C.c_void_p
+    lib.pb_zfit_dev.argtypes = [C.c_size_t, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int,
+                                vp, vp, vp, vp, vp]
+    lib.pb_zfit_dev.restype = C.c_int
+    n = 1_000_000 if small else 10_000_000
+    locs, info, calib = testing.synthetic_zfit_locs(n, 7)
+    cx = np.array(calib["X Coefficients"]); cy = np.array(calib["Y Coefficients"])
+    d = {k: torch.from_numpy(locs[k].to_numpy()).cuda() for k in ("sx", "sy", "photons", "bg")}
+    z = torch.empty(n, device="cuda"); dz = torch.empty(n, device="cuda"); lpz = torch.empty(n, device="cuda")
+    nf = torch.empty(n, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        rc = lib.pb_zfit_dev(n, d["sx"].data_ptr(), d["sy"].data_ptr(), d["photons"].data_ptr(),
+                             d["bg"].data_ptr(), None, None, cx.ctypes.data, cy.ctypes.data, 0.79, 130.0, 0,
+                             z.data_ptr(), dz.data_ptr(), lpz.data_ptr(), nf.data_ptr(), st)
+        assert rc == 0
+    ms = ev_time(torch, run)
+    alg = n * (16 + 16)          # 4 input + 4 output float32 columns
+    t0 = time.perf_counter()
+    res, _ = zfit.zfit(locs, info, calibration=dict(calib), fitting_method="gausslq", filter=2)
+    t_api = time.perf_counter() - t0
+    import oracle
+    oracle.build()
+    m = 200_000
+    t0 = time.perf_counter()
+    oz, osq, _, _, onf = oracle.zfit_minimise(locs["sx"].to_numpy()[:m], locs["sy"].to_numpy()[:m], cx, cy)
+    t_cpu = time.perf_counter() - t0
+    same = bool((z[:m].cpu().numpy() == oz * np.float32(0.79)).all())
+    print(json.dumps({"stage": "zfit (8f rank 3)", "n_locs": n, "kernel_ms": ms, "fits_per_s": n / (ms * 1e-3),
+                      "mean_nfev": float(nf.float().mean().item()),
+                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s",
+                                   "frac": alg / (ms * 1e-3) / 1e9 / peaks(),
+                                   "note": "32 B/localization; the fit is FP64-latency bound (a dependent chain of ~11 target evaluations)"},
+                      "python_api_seconds": t_api, "python_api_fits_per_s": n / t_api, "n_kept": len(res),
+                      "cpu_oracle": {"n": m, "fits_per_s_1thread": m / t_cpu},
+                      "z_bit_identical_to_oracle_sample": same}), flush=True)
+
+
 def stage_render(torch, small):
     from picasso_b200 import _lib, render as pbrender
 
@@ -393,5 +439,5 @@ if __name__ == "__main__":
     small = "--small" in sys.argv
     which = args or ["identify", "render", "rcc"]
     for w in which:
-        {"identify": stage_identify, "localize": stage_localize, "render": stage_render, "rcc": stage_rcc,
+        {"identify": stage_identify, "localize": stage_localize, "zfit": stage_zfit, "render": stage_render, "rcc": stage_rcc,
          "undrift": stage_undrift}[w](torch, small)

@@ -259,7 +259,42 @@ def gen_undrift(ref):
     save("undrift.npz", **out)
 
 
-GENERATORS = {"mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift}
+def zfit_problem(n=3000, seed=11):
+    """Synthetic astigmatism calibration + 2-D fitted localizations (shared with the tests)."""
+    from picasso_b200 import testing
+
+    return testing.synthetic_zfit_locs(n, seed)
+
+
+def gen_zfit(ref):
+    import pandas as pd
+
+    zf = ref["zfit"]
+    locs, info, calib = zfit_problem()
+    out = {k: locs[k].to_numpy() for k in locs.columns}
+    out["cx"] = np.array(calib["X Coefficients"]); out["cy"] = np.array(calib["Y Coefficients"])
+    out["magnification"] = np.float64(calib["Magnification factor"])
+    for tag, method, drop_unc, flt in (("lq_f0", "gausslq", True, 0), ("lq_f2", "gausslq", True, 2),
+                                       ("mle_f0", "gaussmle", True, 0), ("mleunc_f2", "gaussmle", False, 2)):
+        l = locs.drop(columns=["sx_unc", "sy_unc"]) if drop_unc else locs
+        res = zf._fit_z(l, info, calib, calib["Magnification factor"], 130, fitting_method=method, filter=flt)
+        out[f"{tag}_index"] = res.index.to_numpy()
+        for c in ("z", "d_zcalib", "lpz"):
+            out[f"{tag}_{c}"] = res[c].to_numpy()
+        print(tag, len(res), {c: res[c].dtype for c in ("z", "d_zcalib", "lpz")})
+    # raw minimiser outputs (before ensure_sanity / filter)
+    from scipy.optimize import minimize_scalar
+    sx = locs["sx"].to_numpy(); sy = locs["sy"].to_numpy()
+    cx, cy = out["cx"], out["cy"]
+    zr = np.zeros(len(locs)); fr = np.zeros(len(locs)); nf = np.zeros(len(locs), np.int32)
+    for i in range(len(locs)):
+        r = minimize_scalar(zf._fit_z_target, bounds=[-1000, 1000], args=(sx[i], sy[i], cx, cy))
+        zr[i], fr[i], nf[i] = r.x, r.fun, r.nfev
+    out["raw_z"] = zr; out["raw_fun"] = fr; out["raw_nfev"] = nf
+    save("zfit.npz", **out)
+
+
+GENERATORS = {"zfit": gen_zfit, "mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift}
 
 
 def main():
