@@ -608,3 +608,40 @@ def localize(movie, camera_info: dict, parameters: dict, *, roi=None, frame_boun
     if return_info:
         return locs, info
     return locs
+
+
+def localize_3D(movie, *, movie_info: list, camera_info: dict, box: int, minimum_ng: float,
+                calibration_3d: dict, roi=None, frame_bounds=None,
+                fitting_method: Literal["gausslq", "gausslq-gpu", "gaussmle"] = "gausslq",
+                eps: float = 0.001, max_it: int = 100,
+                mle_method: Literal["sigma", "sigmaxy"] = "sigmaxy", multiprocess: bool = True,
+                identification_progress_callback=None, fit_progress_callback=None,
+                fit_z_progress_callback=None):
+    """Identify, fit in 2-D and fit z from astigmatism (reference ``localize_3D``,
+    localize.py:1818-2034): the fused movie -> table pass followed by the z-fit kernel.
+    Returns ``(locs, info)`` with ``z``, ``d_zcalib``, ``lpz`` appended (no RMSD filter)."""
+    from . import zfit
+
+    assert hasattr(movie, "__getitem__") and hasattr(movie, "__len__"), \
+        "movie must be a numpy array or ND2Movie"
+    assert isinstance(movie_info, list), "movie_info must be a list"
+    assert isinstance(camera_info, dict), "camera_info must be a dict"
+    assert isinstance(box, int) and box > 0 and box % 2 == 1, "box must be a positive odd integer"
+    assert isinstance(minimum_ng, (int, float)), "minimum_ng must be a number"
+    assert isinstance(calibration_3d, (dict, str)), \
+        "calibration_3d must be a dict or a path to a YAML file"
+    assert fitting_method in ["gausslq", "gausslq-gpu", "gaussmle"], \
+        "fitting_method must be one of 'gausslq', 'gausslq-gpu', or 'gaussmle'"
+    assert isinstance(eps, (int, float)) and eps > 0, "eps must be a positive number"
+    assert isinstance(max_it, int) and max_it > 0, "max_it must be a positive integer"
+    assert mle_method in ["sigma", "sigmaxy"], "mle_method must be 'sigma' or 'sigmaxy'"
+    assert isinstance(multiprocess, bool), "multiprocess must be a boolean"
+    locs, info = localize(movie, camera_info, {"Min. Net Gradient": minimum_ng, "Box Size": box},
+                          roi=roi, frame_bounds=frame_bounds, movie_info=movie_info,
+                          fitting_method=fitting_method, eps=eps, max_it=max_it, mle_method=mle_method,
+                          threaded=multiprocess,
+                          identification_progress_callback=identification_progress_callback,
+                          fit_progress_callback=fit_progress_callback, return_info=True)
+    fitting_method_3d = "gausslq" if fitting_method in ["gausslq", "gausslq-gpu"] else "gaussmle"
+    return zfit.zfit(locs, info, calibration=calibration_3d, fitting_method=fitting_method_3d,
+                     filter=0, multiprocess=multiprocess, progress_callback=fit_z_progress_callback)

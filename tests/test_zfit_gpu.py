@@ -77,3 +77,27 @@ def test_api_contract(g):
     assert len(zfit.locs_from_futures(fut, filter=0)) == len(res2)
     lp = zfit.axial_localization_precision(res2, info, calib, "gausslq")
     np.testing.assert_allclose(lp.to_numpy(), res2["lpz"].to_numpy(), rtol=LPZ_RTOL)
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+@pytest.mark.parametrize("method", ["gausslq", "gaussmle"])
+def test_localize_3d_equals_localize_plus_zfit(method):
+    """Reference localize.py:1818-2034: localize_3D == localize(...) followed by zfit(filter=0)."""
+    from picasso_b200 import localize
+
+    movie = testing.synthetic_movie(8, 64, 64, emitters_per_frame=6, seed=13)
+    cam = {"Baseline": 100, "Sensitivity": 1.0, "Gain": 1, "Pixelsize": 130}
+    minfo = [{"Width": 64, "Height": 64, "Frames": 8}]
+    _, _, calib = testing.synthetic_zfit_locs(4, 1)
+    locs3, info3 = localize.localize_3D(movie, movie_info=list(minfo), camera_info=dict(cam), box=7,
+                                        minimum_ng=5000, calibration_3d=dict(calib), fitting_method=method)
+    locs2, info2 = localize.localize(movie, dict(cam), {"Min. Net Gradient": 5000, "Box Size": 7},
+                                     movie_info=list(minfo), fitting_method=method, return_info=True)
+    ref, _ = zfit.zfit(locs2, info2, calibration=dict(calib), fitting_method=method, filter=0)
+    assert len(locs3) == len(ref) > 20 and list(locs3.columns[-3:]) == ["z", "d_zcalib", "lpz"]
+    for c in ref.columns:
+        assert locs3[c].to_numpy().tobytes() == ref[c].to_numpy().tobytes(), c
+    assert info3[-1]["Filter range"] == 0 and info3[0] == minfo[0]
+    with pytest.raises(AssertionError):
+        localize.localize_3D(movie, movie_info=minfo, camera_info=cam, box=6, minimum_ng=5000,
+                             calibration_3d=calib)
