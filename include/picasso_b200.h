@@ -216,6 +216,33 @@ int pb_zfit_dev(size_t n, const float* d_sx, const float* d_sy, const float* d_p
                 const double* cy, double magnification, double pixelsize, int method, float* d_z,
                 float* d_d_zcalib, float* d_lpz, int* d_nfev, void* stream);
 
+/* ---- AIM drift correction: intersection counting ---------------------------------
+ * Replaces the counting core of picasso.aim (picasso/aim.py): _point_intersect_2d :297-344,
+ * _point_intersect_3d :377-431, _run_intersections(_multithread) :148-266 and
+ * _count_intersections :89-126 inside intersection_max :517-659 / intersection_max_z :662-773.
+ * A handle keeps the target coordinates, the reference hash table (1-D int32 index ->
+ * multiplicity) and scratch tables on the GPU for one round:
+ *   pb_aim_set_targets    localizations in frame order; each array float32 (flag 0) or float64
+ *                         (flag 1) -- the index arithmetic is done in the array's own dtype
+ *                         like the reference's pandas columns; z nullable (2-D)
+ *   pb_aim_set_reference  quantises the reference coordinates (index = round(x/d) +
+ *                         round(y/d)*width_units [+ round(z/d)*width_units*height_units],
+ *                         np.int32 truncation) and builds the table; rz == NULL selects 2-D
+ *   pb_aim_count          targets [first, first+count): adds rel_x/rel_y (2-D) or rel_z (3-D)
+ *                         before quantisation, then for each of the n_shifts shifts
+ *                         roi_cc[j] = sum_c min(ref[c + shift_j], target[c]).  2-D shifts are
+ *                         int32 values (int32 wrap-around sum), 3-D shifts float64.
+ * The sub-pixel peak, spline and subtraction stay on the host (picasso_b200/aim.py). */
+int pb_aim_create(void** handle);
+int pb_aim_destroy(void* handle);
+int pb_aim_set_targets(void* handle, size_t n, const void* x, int x_f64, const void* y, int y_f64,
+                       const void* z, int z_f64);
+int pb_aim_set_reference(void* handle, size_t n_ref, const void* rx, int rx_f64, const void* ry,
+                         int ry_f64, const void* rz, int rz_f64, double intersect_d,
+                         double width_units, double height_units);
+int pb_aim_count(void* handle, size_t first, size_t count, double rel_x, double rel_y, double rel_z,
+                 int n_shifts, const double* shifts, int* roi_cc);
+
 /* ---- rendering ----------------------------------------------------------------
  * Replaces the unrotated paths of picasso.render.render (picasso/render.py:37-174):
  * _render_hist (:798-853, mode 0), _render_gaussian (:1020-1112, mode 1) and

@@ -146,3 +146,21 @@ def synthetic_zfit_locs(n: int, seed: int = 11):
     info = [{"Width": 64, "Height": 64, "Frames": 1000, "Pixelsize": 130}]
     calib = {"X Coefficients": cx, "Y Coefficients": cy, "Magnification factor": 0.79}
     return locs, info, calib
+
+
+def synthetic_aim_locs(n_frames: int = 2000, Y: int = 64, X: int = 64, n_clusters: int = 60,
+                       locs_per_frame: float = 10.0, seed: int = 4, with_z: bool = False):
+    """Localizations for AIM undrifting: clusters with a slow analytic drift (well inside the
+    default 60 nm search radius per 100-frame segment), optional z column in nm."""
+    locs, info, drift = synthetic_drift_locs(n_frames, Y, X, n_clusters=n_clusters,
+                                             locs_per_frame=locs_per_frame, seed=seed, jitter=0.04,
+                                             amp_x=0.45, amp_y=0.6)
+    if with_z:
+        rng = np.random.default_rng(seed + 1000)
+        n = len(locs)
+        cz = rng.uniform(-300, 300, n_clusters)
+        which = rng.integers(0, n_clusters, n)
+        t = locs["frame"].to_numpy().astype(np.float64)
+        dz = 40.0 * np.sin(2 * np.pi * t / n_frames)
+        locs["z"] = (cz[which] + dz + rng.normal(0, 8.0, n)).astype(np.float32)
+    return locs, info, drift

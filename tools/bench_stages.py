@@ -245,6 +245,37 @@ def stage_zfit(torch, small):
                       "z_bit_identical_to_oracle_sample": same}), flush=True)
 
 
+def stage_aim(torch, small):
+    """AIM drift correction end to end through the Python API, with the CPU
+    oracle (same algorithm as the reference: one sort of the concatenated coordinates per shift and
+    segment) timed on a reduced instance."""
+    from picasso_b200 import aim, testing
+
+    n_frames, side, lpf = (4000, 256, 50.0) if small else (20000, 512, 250.0)
+    locs, info, truth = testing.synthetic_aim_locs(n_frames=n_frames, Y=side, X=side, n_clusters=4000,
+                                                   locs_per_frame=lpf, seed=12)
+    aim.aim(locs[locs["frame"] < 600], [{**info[0], "Frames": 600}], segmentation=100)      # warm-up
+    t0 = time.perf_counter()
+    und, _, drift = aim.aim(locs, info, segmentation=100)
+    t_gpu = time.perf_counter() - t0
+    d = drift["x"].to_numpy(); t = truth[:, 0]
+    err = float(np.abs((d - d.mean()) - (t - t.mean())).max())
+    from oracle import aim_oracle
+    nf_cpu = 1000
+    sub = locs[locs["frame"] < nf_cpu]
+    t0 = time.perf_counter()
+    ound, odrift = aim_oracle.aim(sub, [{**info[0], "Frames": nf_cpu}], 100)
+    t_cpu = time.perf_counter() - t0
+    gsub, _, gdrift = aim.aim(sub, [{**info[0], "Frames": nf_cpu}], segmentation=100)
+    same = gdrift["x"].to_numpy().tobytes() == odrift["x"].to_numpy().tobytes()
+    print(json.dumps({"stage": "aim (8f rank 4)", "n_locs": len(locs), "frames": n_frames, "image": [side, side],
+                      "n_segments": n_frames // 100, "seconds": t_gpu, "locs_per_s": len(locs) / t_gpu,
+                      "max_abs_drift_error_px_vs_injected": err,
+                      "cpu_oracle": {"n_locs": len(sub), "frames": nf_cpu, "seconds": t_cpu,
+                                     "locs_per_s_1thread": len(sub) / t_cpu},
+                      "drift_bit_identical_to_oracle_on_sample": bool(same)}), flush=True)
+
+
 def stage_render(torch, small):
     from picasso_b200 import _lib, render as pbrender
 
@@ -439,5 +470,5 @@ if __name__ == "__main__":
     small = "--small" in sys.argv
     which = args or ["identify", "render", "rcc"]
     for w in which:
-        {"identify": stage_identify, "localize": stage_localize, "zfit": stage_zfit, "render": stage_render, "rcc": stage_rcc,
+        {"identify": stage_identify, "localize": stage_localize, "zfit": stage_zfit, "aim": stage_aim, "render": stage_render, "rcc": stage_rcc,
          "undrift": stage_undrift}[w](torch, small)

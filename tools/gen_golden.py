@@ -294,7 +294,52 @@ def gen_zfit(ref):
     save("zfit.npz", **out)
 
 
-GENERATORS = {"zfit": gen_zfit, "mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift}
+def gen_aim(ref):
+    """aim.aim on 2-D and 3-D localizations, plus the per-segment intersection counts of every
+    round (recorded by wrapping the reference's _point_intersect_* helpers)."""
+    from picasso_b200 import testing
+
+    aim = ref["aim"]
+    out = {}
+    for tag, with_z in (("2d", False), ("3d", True)):
+        locs, info, _ = testing.synthetic_aim_locs(with_z=with_z)
+        rec2, rec3 = [], []
+        o2, o3 = aim._point_intersect_2d, aim._point_intersect_3d
+
+        def w2(*a, **k):
+            r = o2(*a, **k); rec2.append(np.array(r)); return r
+
+        def w3(*a, **k):
+            r = o3(*a, **k); rec3.append(np.array(r)); return r
+
+        aim._point_intersect_2d, aim._point_intersect_3d = w2, w3
+        try:
+            und, new_info, drift = aim.aim(locs, info, segmentation=100)
+        finally:
+            aim._point_intersect_2d, aim._point_intersect_3d = o2, o3
+        out[f"{tag}_roi_cc"] = np.stack(rec2)
+        if rec3:
+            out[f"{tag}_roi_cc_z"] = np.stack(rec3)
+        for c in drift.columns:
+            out[f"{tag}_drift_{c}"] = drift[c].to_numpy()
+        for c in ("x", "y") + (("z",) if with_z else ()):
+            out[f"{tag}_und_{c}"] = und[c].to_numpy()
+        print(tag, len(locs), out[f"{tag}_roi_cc"].shape, {c: und[c].dtype for c in und.columns},
+              drift.dtypes.to_dict(), new_info[-1])
+    # a second geometry: non-default intersect_d / roi_r, unsorted frames, frame offset
+    locs, info, _ = testing.synthetic_aim_locs(n_frames=900, Y=48, X=80, n_clusters=30, seed=9)
+    rng = np.random.default_rng(1)
+    locs = locs.iloc[rng.permutation(len(locs))].reset_index(drop=True)
+    locs["frame"] += 7
+    und, new_info, drift = aim.aim(locs, info, segmentation=150, intersect_d=0.2, roi_r=0.55)
+    out["alt_drift_x"] = drift["x"].to_numpy(); out["alt_drift_y"] = drift["y"].to_numpy()
+    out["alt_und_x"] = und["x"].to_numpy(); out["alt_und_y"] = und["y"].to_numpy()
+    out["alt_perm_frame"] = locs["frame"].to_numpy()
+    out["alt_perm_x"] = locs["x"].to_numpy(); out["alt_perm_y"] = locs["y"].to_numpy()
+    save("aim.npz", **out)
+
+
+GENERATORS = {"aim": gen_aim, "zfit": gen_zfit, "mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift}
 
 
 def main():

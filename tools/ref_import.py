@@ -67,7 +67,7 @@ def import_reference():
 
     mods = {}
     for m in ("lib", "io", "gaussmle", "gausslq", "localize", "render",
-              "imageprocess", "postprocess", "zfit"):
+              "imageprocess", "postprocess", "zfit", "aim"):
         mods[m] = importlib.import_module(f"picasso.{m}")
     return mods
 
