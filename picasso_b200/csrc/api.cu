@@ -60,12 +60,15 @@ extern "C" int pb_host_free(void* ptr) {
 }
 
 // ---- cached device workspaces (per device, per slot) ----------------------
-// The host-buffer entry points stream chunks through kSlots slots (own stream each);
-// the device buffers are kept between calls (cudaMalloc costs ~1 ms per 100 MB).
+// The host-buffer fit entry points stream chunks through kSlots slots (own stream each); the
+// device buffers and the pinned output staging are kept between calls (cudaMalloc costs ~1 ms
+// per 100 MB).
 namespace {
 struct Slot {
     void* buf = nullptr;
     size_t bytes = 0;
+    void* hout = nullptr;      // pinned staging for the outputs of one chunk (pageable callers)
+    size_t hbytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
 };
@@ -76,7 +79,7 @@ struct DevWs {
 std::mutex g_ws_mutex;
 std::vector<DevWs> g_ws;   // indexed by device
 
-int ws_get(int slot, size_t bytes, Slot** out) {
+int ws_get(int slot, size_t bytes, size_t host_bytes, Slot** out) {
     int dev = 0;
     PB_CUDA_CHECK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_ws_mutex);
@@ -93,10 +96,91 @@ int ws_get(int slot, size_t bytes, Slot** out) {
         PB_CUDA_CHECK(cudaMalloc(&s.buf, bytes));
         s.bytes = bytes;
     }
+    if (s.hbytes < host_bytes) {
+        if (s.hout) PB_CUDA_CHECK(cudaFreeHost(s.hout));
+        s.hout = nullptr;
+        s.hbytes = 0;
+        PB_CUDA_CHECK(cudaHostAlloc(&s.hout, host_bytes, cudaHostAllocDefault));
+        s.hbytes = host_bytes;
+    }
     *out = &s;
     return PB_OK;
 }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// One per-item output array of a fit: `host` (nullable) receives `stride` bytes per item.
+struct OutSpec {
+    void* host;
+    size_t stride;
+    bool device_only;      // allocated in the slot, never copied back (host == nullptr)
+    size_t off;            // byte offset inside the slot (filled in by the pipeline)
+};
+
+// Chunked H2D -> kernel -> D2H pipeline shared by pb_mle_fit and pb_lq_fit: kSlots chunks in
+// flight on separate streams, so the upload of chunk c+1/c+2 and the download of chunk c-1
+// overlap the kernel of chunk c.  Pageable inputs go through pb_h2d (threaded pinned staging);
+// pageable outputs come back with ONE DMA per chunk into the slot's pinned staging and are
+// copied out when the slot is recycled, so no call blocks on a pageable cudaMemcpy.
+template <class Launch>
+int fit_pipeline(size_t n, size_t in_stride, const void* in, OutSpec* outs, int n_outs, size_t chunk,
+                 Launch launch, volatile long long* progress) {
+    size_t off = align_up(chunk * in_stride, 256);
+    const size_t out0 = off;
+    for (int k = 0; k < n_outs; k++) { outs[k].off = off; off = align_up(off + chunk * outs[k].stride, 256); }
+    const size_t total = off;
+    bool staged = false;
+    for (int k = 0; k < n_outs; k++)
+        if (outs[k].host && !pb_host_is_pinned(outs[k].host)) staged = true;
+    Slot* sl[kSlots];
+    int rc;
+    for (int s = 0; s < kSlots; s++)
+        if ((rc = ws_get(s, total, staged ? total - out0 : 0, &sl[s])) != PB_OK) return rc;
+    size_t first_of[kSlots] = {0}, m_of[kSlots] = {0};
+    bool busy[kSlots] = {false};
+    auto retire = [&](int s) -> int {       // chunk in slot s finished: hand its outputs to the caller
+        PB_CUDA_CHECK(cudaEventSynchronize(sl[s]->done));
+        if (staged) {
+            const char* h = static_cast<const char*>(sl[s]->hout);
+            for (int k = 0; k < n_outs; k++)
+                if (outs[k].host)
+                    pb_parallel_memcpy(static_cast<char*>(outs[k].host) + first_of[s] * outs[k].stride,
+                                       h + (outs[k].off - out0), m_of[s] * outs[k].stride);
+        }
+        busy[s] = false;
+        if (progress) *progress = (long long)(first_of[s] + m_of[s]);
+        return PB_OK;
+    };
+    size_t c = 0;
+    for (size_t first = 0; first < n; first += chunk, c++) {
+        const int s = (int)(c % kSlots);
+        Slot* S = sl[s];
+        if (busy[s] && (rc = retire(s)) != PB_OK) return rc;
+        const size_t m = (n - first < chunk) ? n - first : chunk;
+        char* base = static_cast<char*>(S->buf);
+        if ((rc = pb_h2d(base, static_cast<const char*>(in) + first * in_stride, m * in_stride, S->stream)))
+            return rc;
+        if ((rc = launch(m, base, outs, S->stream)) != PB_OK) return rc;
+        if (staged) {
+            PB_CUDA_CHECK(cudaMemcpyAsync(S->hout, base + out0, total - out0, cudaMemcpyDeviceToHost, S->stream));
+        } else {
+            for (int k = 0; k < n_outs; k++)
+                if (outs[k].host)
+                    PB_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(outs[k].host) + first * outs[k].stride,
+                                                  base + outs[k].off, m * outs[k].stride,
+                                                  cudaMemcpyDeviceToHost, S->stream));
+        }
+        PB_CUDA_CHECK(cudaEventRecord(S->done, S->stream));
+        busy[s] = true;
+        first_of[s] = first;
+        m_of[s] = m;
+    }
+    for (size_t k = 0; k < (size_t)kSlots; k++) {      // remaining chunks, oldest first
+        const int s = (int)((c + k) % kSlots);
+        if (busy[s] && (rc = retire(s)) != PB_OK) return rc;
+    }
+    if (progress) *progress = (long long)n;
+    return PB_OK;
+}
 }  // namespace
 
 // Serialises host-buffer calls that share the cached workspaces.
@@ -131,59 +215,35 @@ extern "C" int pb_mle_fit(size_t n, int box, const float* spots, double eps, int
     chunk = chunk / 4096 * 4096;
     if (chunk < 4096) chunk = 4096;
     if (chunk > n) chunk = align_up(n, 4);
-    // slot layout: spots | thetas | crlbs | logliks | iterations | status
-    const size_t o_sp = 0;
-    const size_t o_th = align_up(o_sp + chunk * pix * 4, 256);
-    const size_t o_cr = align_up(o_th + chunk * 24, 256);
-    const size_t o_ll = align_up(o_cr + chunk * 24, 256);
-    const size_t o_it = align_up(o_ll + chunk * 4, 256);
-    const size_t o_st = align_up(o_it + chunk * 4, 256);
-    const size_t total = align_up(o_st + chunk * 4, 256);
-    Slot* sl[kSlots];
-    int rc;
-    for (int s = 0; s < kSlots; s++)
-        if ((rc = ws_get(s, total, &sl[s])) != PB_OK) return rc;
+    OutSpec outs[5] = {{thetas, 24, false, 0}, {crlbs, 24, false, 0}, {logliks, 4, false, 0},
+                       {iterations, 4, false, 0}, {status, 4, status == nullptr, 0}};
+    auto launch = [&](size_t m, char* base, const OutSpec* o, cudaStream_t st) {
+        return pb_mle_fit_dev(m, box, reinterpret_cast<float*>(base), eps, max_it, method,
+                              reinterpret_cast<float*>(base + o[0].off), reinterpret_cast<float*>(base + o[1].off),
+                              reinterpret_cast<float*>(base + o[2].off), reinterpret_cast<int*>(base + o[3].off),
+                              reinterpret_cast<int*>(base + o[4].off), st);
+    };
+    return fit_pipeline(n, pix * 4, spots, outs, 5, chunk, launch, progress);
+}
 
-    // kSlots chunks in flight: the H2D of chunk c+1/c+2 and the D2H of chunk c-1 overlap
-    // the kernel of chunk c (separate streams -> separate copy engines)
-    size_t done_spots[kSlots] = {0};
-    bool busy[kSlots] = {false};
-    size_t c = 0;
-    for (size_t first = 0; first < n; first += chunk, c++) {
-        const int s = (int)(c % kSlots);
-        Slot* S = sl[s];
-        if (busy[s]) {
-            PB_CUDA_CHECK(cudaEventSynchronize(S->done));
-            if (progress) *progress = (long long)done_spots[s];
-        }
-        const size_t m = (n - first < chunk) ? n - first : chunk;
-        char* base = static_cast<char*>(S->buf);
-        PB_CUDA_CHECK(cudaMemcpyAsync(base + o_sp, spots + first * pix, m * pix * 4,
-                                      cudaMemcpyHostToDevice, S->stream));
-        rc = pb_mle_fit_dev(m, box, reinterpret_cast<float*>(base + o_sp), eps, max_it, method,
-                            reinterpret_cast<float*>(base + o_th),
-                            reinterpret_cast<float*>(base + o_cr),
-                            reinterpret_cast<float*>(base + o_ll),
-                            reinterpret_cast<int*>(base + o_it),
-                            reinterpret_cast<int*>(base + o_st), S->stream);
-        if (rc != PB_OK) return rc;
-        PB_CUDA_CHECK(cudaMemcpyAsync(thetas + first * 6, base + o_th, m * 24,
-                                      cudaMemcpyDeviceToHost, S->stream));
-        PB_CUDA_CHECK(cudaMemcpyAsync(crlbs + first * 6, base + o_cr, m * 24,
-                                      cudaMemcpyDeviceToHost, S->stream));
-        PB_CUDA_CHECK(cudaMemcpyAsync(logliks + first, base + o_ll, m * 4, cudaMemcpyDeviceToHost,
-                                      S->stream));
-        PB_CUDA_CHECK(cudaMemcpyAsync(iterations + first, base + o_it, m * 4,
-                                      cudaMemcpyDeviceToHost, S->stream));
-        if (status)
-            PB_CUDA_CHECK(cudaMemcpyAsync(status + first, base + o_st, m * 4,
-                                          cudaMemcpyDeviceToHost, S->stream));
-        PB_CUDA_CHECK(cudaEventRecord(S->done, S->stream));
-        busy[s] = true;
-        done_spots[s] = first + m;
+// Host-buffer LQ fit through the same pipeline (declared in include/picasso_b200.h).
+extern "C" int pb_lq_fit(size_t n, int box, const float* spots, float* thetas, int* infos, int* nfevs) {
+    if (n == 0) return PB_OK;
+    if (!spots || !thetas) { pb_set_error("pb_lq_fit: null pointer"); return PB_ERR_INVALID; }
+    if (box < 5 || box > 15 || !(box & 1)) {
+        pb_set_error("unsupported box size %d for LQ fit (odd 5..15)", box);
+        return PB_ERR_INVALID;
     }
-    for (int s = 0; s < kSlots; s++)
-        if (busy[s]) PB_CUDA_CHECK(cudaEventSynchronize(sl[s]->done));
-    if (progress) *progress = (long long)n;
-    return PB_OK;
+    std::lock_guard<std::mutex> call_lk(g_host_call_mutex);
+    const size_t pix = (size_t)box * box;
+    size_t chunk = ((size_t)64 << 20) / (pix * 4);
+    chunk = chunk / 4096 * 4096;
+    if (chunk < 4096) chunk = 4096;
+    if (chunk > n) chunk = align_up(n, 4);
+    OutSpec outs[3] = {{thetas, 24, false, 0}, {infos, 4, infos == nullptr, 0}, {nfevs, 4, nfevs == nullptr, 0}};
+    auto launch = [&](size_t m, char* base, const OutSpec* o, cudaStream_t st) {
+        return pb_lq_fit_dev(m, box, reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + o[0].off),
+                             reinterpret_cast<int*>(base + o[1].off), reinterpret_cast<int*>(base + o[2].off), st);
+    };
+    return fit_pipeline(n, pix * 4, spots, outs, 3, chunk, launch, nullptr);
 }

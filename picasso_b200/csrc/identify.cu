@@ -542,8 +542,7 @@ extern "C" int pb_identify(const void* movie, int dtype, size_t n_frames, int Y,
         const int s = (int)(c & 1);
         const size_t nf = std::min(chunk, n_frames - f0);
         if (c >= 2) cudaEventSynchronize(ev[s]);
-        cudaMemcpyAsync(mv[s].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz,
-                        cudaMemcpyHostToDevice, st[s]);
+        if ((rc = pb_h2d(mv[s].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz, st[s])) != PB_OK) break;
         rc = pb_identify_dev(mv[s].p, dtype, nf, Y, X, frame_offset + (long long)f0, box, min_ng,
                              roi, static_cast<long long*>(dfr.p), static_cast<long long*>(dx.p),
                              static_cast<long long*>(dy.p), static_cast<float*>(dng.p), capacity,
@@ -609,8 +608,9 @@ extern "C" int pb_get_spots(const void* movie, int dtype, size_t n_frames, int Y
     if ((rc = mv.alloc(nf * fsz)) || (rc = dfr.alloc(m * 8)) || (rc = dx.alloc(m * 8)) ||
         (rc = dy.alloc(m * 8)) || (rc = dsp.alloc(m * pix * 4)))
         return rc;
-    PB_CUDA_CHECK(cudaMemcpy(mv.p, static_cast<const char*>(movie) + (size_t)(fmin - frame_offset) * fsz,
-                             nf * fsz, cudaMemcpyHostToDevice));
+    if ((rc = pb_h2d(mv.p, static_cast<const char*>(movie) + (size_t)(fmin - frame_offset) * fsz, nf * fsz,
+                     nullptr)) != PB_OK)
+        return rc;
     PB_CUDA_CHECK(cudaMemcpy(dfr.p, hf.data(), m * 8, cudaMemcpyHostToDevice));
     PB_CUDA_CHECK(cudaMemcpy(dx.p, hx.data(), m * 8, cudaMemcpyHostToDevice));
     PB_CUDA_CHECK(cudaMemcpy(dy.p, hy.data(), m * 8, cudaMemcpyHostToDevice));
@@ -619,7 +619,7 @@ extern "C" int pb_get_spots(const void* movie, int dtype, size_t n_frames, int Y
                           baseline, sensitivity, gain, static_cast<float*>(dsp.p), nullptr);
     if (rc != PB_OK) return rc;
     std::vector<float> hs(m * pix);
-    PB_CUDA_CHECK(cudaMemcpy(hs.data(), dsp.p, m * pix * 4, cudaMemcpyDeviceToHost));
+    if ((rc = pb_d2h(hs.data(), dsp.p, m * pix * 4, nullptr)) != PB_OK) return rc;
     for (size_t k = 0; k < m; k++)
         memcpy(spots + sel[k] * pix, hs.data() + k * pix, pix * 4);
     return PB_OK;
@@ -664,8 +664,7 @@ extern "C" int pb_identify_get_spots(const void* movie, int dtype, size_t n_fram
         const size_t f0 = c * chunk;
         if (f0 >= n_frames) return;
         const size_t nf = std::min(chunk, n_frames - f0);
-        cudaMemcpyAsync(mv[c & 1].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz,
-                        cudaMemcpyHostToDevice, st[c & 1]);
+        pb_h2d(mv[c & 1].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz, st[c & 1]);
     };
     upload(0);
     size_t total = 0;

@@ -197,29 +197,6 @@ int get_pipeline(Pipeline** out) {
 
 inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
-// multi-threaded host copy (pageable -> pinned staging)
-void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    unsigned nt = std::min(8u, hw);
-    if (const char* e = getenv("PB_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-    if (bytes < ((size_t)4 << 20) || nt == 1) { memcpy(dst, src, bytes); return; }
-    const size_t per = up256((bytes + nt - 1) / nt);
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; t++) {
-        const size_t o = t * per;
-        if (o >= bytes) break;
-        th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, std::min(per, bytes - o)); });
-    }
-    memcpy(dst, src, std::min(per, bytes));
-    for (auto& t : th) t.join();
-}
-
-bool host_pointer_is_pinned(const void* p) {
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-}
-
 int fit_columns(int fit) { return fit <= 1 ? kColsMle : kColsLq; }
 
 }  // namespace
@@ -313,7 +290,7 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
         if (v >= 1) chunk = (size_t)v;
     }
     chunk = std::min(chunk, std::min<size_t>(n_frames, (size_t)1 << 22));
-    const bool pinned_src = host_pointer_is_pinned(movie);
+    const bool pinned_src = pb_host_is_pinned(movie);
     for (int s = 0; s < 2; s++) {
         if ((rc = P->mv[s].grow(chunk * fsz))) return rc;
         if (!pinned_src && (rc = P->stage[s].grow(chunk * fsz))) return rc;
@@ -362,7 +339,7 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
         const char* src = static_cast<const char*>(movie) + f0 * fsz;
         if (!pinned_src) {
             if (c >= 2) PB_CUDA_CHECK(cudaEventSynchronize(P->staged[s]));   // staging buffer drained
-            parallel_memcpy(P->stage[s].p, src, nf * fsz);
+            pb_parallel_memcpy(P->stage[s].p, src, nf * fsz);
             src = static_cast<const char*>(P->stage[s].p);
         }
         if (c >= 2) PB_CUDA_CHECK(cudaStreamWaitEvent(P->copy, P->cut[s], 0));   // chunk c-2 no longer read

@@ -748,35 +748,4 @@ extern "C" int pb_lq_fit_dev(size_t n, int box, const float* d_spots, float* d_t
     }
 }
 
-// host-buffer variant: H2D, fit, D2H (chunked)
-extern "C" int pb_lq_fit(size_t n, int box, const float* spots, float* thetas, int* infos,
-                         int* nfevs) {
-    if (n == 0) return PB_OK;
-    if (!spots || !thetas) { pb_set_error("pb_lq_fit: null pointer"); return PB_ERR_INVALID; }
-    if (box < 5 || box > 15 || !(box & 1)) {
-        pb_set_error("unsupported box size %d for LQ fit (odd 5..15)", box);
-        return PB_ERR_INVALID;
-    }
-    const size_t pix = (size_t)box * box;
-    const size_t chunk = std::min<size_t>(n, (size_t)1 << 20);
-    float *dsp = nullptr, *dth = nullptr;
-    int *din = nullptr, *dnf = nullptr;
-    PB_CUDA_CHECK(cudaMalloc(&dsp, chunk * pix * 4));
-    PB_CUDA_CHECK(cudaMalloc(&dth, chunk * 24));
-    PB_CUDA_CHECK(cudaMalloc(&din, chunk * 4));
-    PB_CUDA_CHECK(cudaMalloc(&dnf, chunk * 4));
-    int rc = PB_OK;
-    for (size_t f = 0; f < n && rc == PB_OK; f += chunk) {
-        const size_t m = std::min(chunk, n - f);
-        cudaMemcpy(dsp, spots + f * pix, m * pix * 4, cudaMemcpyHostToDevice);
-        rc = pb_lq_fit_dev(m, box, dsp, dth, din, dnf, nullptr);
-        if (rc != PB_OK) break;
-        cudaMemcpy(thetas + f * 6, dth, m * 24, cudaMemcpyDeviceToHost);
-        if (infos) cudaMemcpy(infos + f, din, m * 4, cudaMemcpyDeviceToHost);
-        if (nfevs) cudaMemcpy(nfevs + f, dnf, m * 4, cudaMemcpyDeviceToHost);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { pb_set_error("pb_lq_fit: %s", cudaGetErrorString(e)); rc = PB_ERR_CUDA; }
-    }
-    cudaFree(dsp); cudaFree(dth); cudaFree(din); cudaFree(dnf);
-    return rc;
-}
+// The host-buffer variant pb_lq_fit lives in api.cu (shared chunked H2D -> kernel -> D2H pipeline).

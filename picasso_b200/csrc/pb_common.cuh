@@ -25,6 +25,19 @@ void pb_set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
+// ---- host <-> device transfers for pageable memory (csrc/transfer.cu) ---------------------
+// numpy arrays are pageable: cudaMemcpy then runs at 5-10 GB/s through the driver's staging
+// copy.  These helpers stage through pinned double buffers filled / drained by several host
+// threads (PB_COPY_THREADS, default min(12, cores)) so that the DMA of one chunk overlaps the host copy of
+// the next; pinned memory (pb_host_alloc) is copied directly.
+bool pb_host_is_pinned(const void* p);
+void pb_parallel_memcpy(void* dst, const void* src, size_t bytes);
+// Enqueue host -> device on `s`.  On return `h_src` is no longer referenced when it is pageable;
+// pinned sources follow cudaMemcpyAsync semantics (valid until the stream reaches the copy).
+int pb_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t s);
+// Device -> host after everything enqueued on `s` so far; blocking, `h_dst` is complete on return.
+int pb_d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t s);
+
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint32_t pb_smem_u32(const void* p) {

@@ -697,7 +697,7 @@ extern "C" int pb_rcc_windows(int n_seg, int Y, int X, const float* segments, in
         std::vector<int> pi, pj;
         for (int i = 0; i < n_seg - 1; i++)
             for (int j = i + 1; j < n_seg; j++) { pi.push_back(i); pj.push_back(j); }
-        ok(cudaMemcpy(dseg, segments, n_seg * img * 4, cudaMemcpyHostToDevice));
+        if (pb_h2d(dseg, segments, n_seg * img * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);   // threaded pinned staging
         if (n_pairs) {
             ok(cudaMemcpy(dpi, pi.data(), n_pairs * 4, cudaMemcpyHostToDevice));
             ok(cudaMemcpy(dpj, pj.data(), n_pairs * 4, cudaMemcpyHostToDevice));
@@ -708,7 +708,7 @@ extern "C" int pb_rcc_windows(int n_seg, int Y, int X, const float* segments, in
                                     wsb, nullptr);
         if (e == cudaSuccess && rc == PB_OK) {
             ok(cudaMemcpy(sums, dsum, n_seg * 8, cudaMemcpyDeviceToHost));
-            if (n_pairs) ok(cudaMemcpy(windows, dwin, (size_t)n_pairs * H * W * 4, cudaMemcpyDeviceToHost));
+            if (n_pairs && pb_d2h(windows, dwin, (size_t)n_pairs * H * W * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
         }
     }
     cudaFree(dseg); cudaFree(dspec); cudaFree(dsum); cudaFree(dws); cudaFree(dwin); cudaFree(dpi); cudaFree(dpj);
@@ -761,10 +761,10 @@ extern "C" int pb_undrift_windows(int n_seg, const long long* seg_start, const f
     int rc = PB_OK;
     if (e == cudaSuccess) {
         if (n_locs) {
-            ok(cudaMemcpy(dx, x, n_locs * 4, cudaMemcpyHostToDevice));
-            ok(cudaMemcpy(dy, y, n_locs * 4, cudaMemcpyHostToDevice));
-            ok(cudaMemcpy(dlx, lpx, n_locs * 4, cudaMemcpyHostToDevice));
-            ok(cudaMemcpy(dly, lpy, n_locs * 4, cudaMemcpyHostToDevice));
+            if (pb_h2d(dx, x, n_locs * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
+            if (pb_h2d(dy, y, n_locs * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
+            if (pb_h2d(dlx, lpx, n_locs * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
+            if (pb_h2d(dly, lpy, n_locs * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
         }
         for (int i = 0; i < n_seg && rc == PB_OK && e == cudaSuccess; i++) {
             const size_t a0 = (size_t)seg_start[i], m = (size_t)(seg_start[i + 1] - seg_start[i]);
@@ -784,8 +784,8 @@ extern "C" int pb_undrift_windows(int n_seg, const long long* seg_start, const f
             rc = pb_rcc_windows_dev(n_pairs, dpi, dpj, Y, X, dspec, Y0, X0, H, W, dwin, batch, dws, wsb, nullptr);
         if (e == cudaSuccess && rc == PB_OK) {
             ok(cudaMemcpy(sums, dsum, n_seg * 8, cudaMemcpyDeviceToHost));
-            if (n_pairs) ok(cudaMemcpy(windows, dwin, (size_t)n_pairs * H * W * 4, cudaMemcpyDeviceToHost));
-            if (segments_out) ok(cudaMemcpy(segments_out, dseg, n_seg * img * 4, cudaMemcpyDeviceToHost));
+            if (n_pairs && pb_d2h(windows, dwin, (size_t)n_pairs * H * W * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
+            if (segments_out && pb_d2h(segments_out, dseg, n_seg * img * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
         }
     }
     cudaFree(dseg); cudaFree(dspec); cudaFree(dsum); cudaFree(dcnt); cudaFree(dws); cudaFree(dwin);

@@ -412,19 +412,20 @@ extern "C" int pb_render(size_t n, const float* x, const float* y, const float* 
     if (mode) { ok(cudaMalloc(&dlx, nb)); ok(cudaMalloc(&dly, nb)); ok(cudaMalloc(&dws, wsb)); }
     ok(cudaMalloc(&dimg, npix * 4)); ok(cudaMalloc(&dcnt, 8));
     if (e == cudaSuccess && n) {
-        ok(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
-        ok(cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice));
+        // pageable numpy columns: threaded pinned staging (csrc/transfer.cu)
+        if (rc == PB_OK) rc = pb_h2d(dx, x, n * 4, nullptr);
+        if (rc == PB_OK) rc = pb_h2d(dy, y, n * 4, nullptr);
         if (mode) {
-            ok(cudaMemcpy(dlx, lpx, n * 4, cudaMemcpyHostToDevice));
-            ok(cudaMemcpy(dly, lpy, n * 4, cudaMemcpyHostToDevice));
+            if (rc == PB_OK) rc = pb_h2d(dlx, lpx, n * 4, nullptr);
+            if (rc == PB_OK) rc = pb_h2d(dly, lpy, n * 4, nullptr);
         }
     }
-    if (e == cudaSuccess)
+    if (e == cudaSuccess && rc == PB_OK)
         rc = pb_render_dev(n, dx, dy, dlx, dly, oversampling, y_min, x_min, y_max, x_max,
                            min_blur_width, mode, dimg, n_pixel_y, n_pixel_x, dcnt, dws, wsb, nullptr);
     unsigned long long cnt = 0;
     if (e == cudaSuccess && rc == PB_OK) {
-        ok(cudaMemcpy(image, dimg, npix * 4, cudaMemcpyDeviceToHost));
+        rc = pb_d2h(image, dimg, npix * 4, nullptr);
         ok(cudaMemcpy(&cnt, dcnt, 8, cudaMemcpyDeviceToHost));
     }
     cudaFree(dx); cudaFree(dy); cudaFree(dlx); cudaFree(dly); cudaFree(dimg); cudaFree(dcnt); cudaFree(dws);

@@ -64,10 +64,11 @@ def gaussmle(
     method_id = _method_id(method)
     spots = _as_spots(spots)
     N = len(spots)
-    thetas = np.zeros((N, 6), dtype=np.float32)
-    CRLBs = np.inf * np.ones((N, 6), dtype=np.float32)
-    likelihoods = np.zeros(N, dtype=np.float32)
-    iterations = np.zeros(N, dtype=np.int32)
+    # every entry is written by the kernel (the reference pre-fills CRLBs with inf, :457)
+    thetas = np.empty((N, 6), dtype=np.float32)
+    CRLBs = np.empty((N, 6), dtype=np.float32)
+    likelihoods = np.empty(N, dtype=np.float32)
+    iterations = np.empty(N, dtype=np.int32)
     if N:
         _fit_into(spots, eps, max_it, method_id, thetas, CRLBs, likelihoods, iterations)
     if progress_callback == "console":
