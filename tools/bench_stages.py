@@ -102,13 +102,18 @@ def stage_identify(torch, small):
     # warm-up (CUDA context, local-memory pool for the LQ kernel, pandas)
     localize.localize(hmovie[:8], dict(cam), {"Min. Net Gradient": 5000, "Box Size": 7},
                       return_info=False, fitting_method="gausslq")
-    t0 = time.perf_counter()
-    ids = localize.identify(hmovie, 5000, 7, return_info=False)
-    t1 = time.perf_counter()
-    spots = localize.get_spots(hmovie, ids, 7, cam)
-    t2 = time.perf_counter()
-    theta = gausslq.fit_spots(spots)
-    t3 = time.perf_counter()
+    # first calls pay lazy module loading and the cached pinned / device buffers: time the second
+    first = {}
+    for rep in range(2):
+        t0 = time.perf_counter()
+        ids = localize.identify(hmovie, 5000, 7, return_info=False)
+        t1 = time.perf_counter()
+        spots = localize.get_spots(hmovie, ids, 7, cam)
+        t2 = time.perf_counter()
+        theta = gausslq.fit_spots(spots)
+        t3 = time.perf_counter()
+        if rep == 0:
+            first = {"identify_host_movie": t1 - t0, "get_spots": t2 - t1, "gausslq": t3 - t2}
     locs = localize.localize(hmovie, dict(cam), {"Min. Net Gradient": 5000, "Box Size": 7},
                              return_info=False, fitting_method="gausslq")
     t3b = time.perf_counter()
@@ -131,7 +136,7 @@ def stage_identify(torch, small):
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks(), "unit": "GB/s",
                      "frac": ach / peaks(), "algorithmic_bytes": bytes_alg},
         "e2e_seconds": {"identify_host_movie": t1 - t0, "get_spots": t2 - t1, "gausslq": t3 - t2,
-                        "total": t3 - t0, "localize_fused": t3b - t3},
+                        "total": t3 - t0, "localize_fused": t3b - t3, "first_call": first},
         "e2e_fps": F / (t3 - t0), "e2e_fps_fused_localize": F / (t3b - t3), "lq_fits_per_s_e2e": len(spots) / (t3 - t2),
         "cpu_oracle": {"identify_fps_1thread": nf_cpu / (t5 - t4),
                        "lq_fits_per_s_allcores": ns / (t6 - t5), "cores": os.cpu_count()},
