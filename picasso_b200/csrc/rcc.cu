@@ -380,6 +380,90 @@ rcc_pruned_cols_kernel(const float2* __restrict__ T, int H, int W, int XH, int X
 }
 
 
+
+// Variant with asynchronous staging (LDGSTS): the 64 spectrum rows of the NEXT q stream into
+// the warp's 16 KB shared-memory stage with 8-byte cp.async copies (half-spectrum rows are only
+// 8-byte aligned: X/2+1 is odd) while the warp runs the FFT of the current q out of registers.
+// No raw-load registers (128 in the register variant) -> 168 registers, 12 warps per SM, and
+// the load latency is hidden behind ~800 instructions of arithmetic per warp.  Twiddles come
+// through L1 (warp-uniform 16-byte loads).
+__device__ __forceinline__ void rcc_cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pb_smem_u32(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void rcc_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(32 * kFW, 3)
+rcc_fft_rows_async_kernel(const float2* __restrict__ spectra, size_t spec_elems, const int* __restrict__ pi,
+                          const int* __restrict__ pj, int XH, int M, const float2* __restrict__ tw_g,
+                          int c0, int row0, int nrows, int H, float2* __restrict__ T) {
+    extern __shared__ __align__(16) unsigned char rcc_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float2* stage = reinterpret_cast<float2*>(rcc_smem) + (size_t)w * 64 * 32;   // [64 rows][32 lanes]
+    float2* red = reinterpret_cast<float2*>(rcc_smem);                            // [kFW][32][32] after the loop
+    const int pair = blockIdx.x;
+    const int kx_raw = blockIdx.y * 32 + lane;
+    const int kx = kx_raw < XH ? kx_raw : XH - 1;
+    const float2* A = spectra + (size_t)pi[pair] * spec_elems + kx;
+    const float2* B = spectra + (size_t)pj[pair] * spec_elems + kx;
+    const size_t pstride = (size_t)M * XH;
+    auto prefetch = [&](int q) {
+        const float2* a = A + (size_t)q * XH;
+        const float2* b = B + (size_t)q * XH;
+#pragma unroll
+        for (int p = 0; p < 32; p++) {
+            rcc_cp_async8(stage + p * 32 + lane, a + p * pstride);
+            rcc_cp_async8(stage + (32 + p) * 32 + lane, b + p * pstride);
+        }
+    };
+    float accr[32], acci[32];
+#pragma unroll
+    for (int n = 0; n < 32; n++) { accr[n] = 0.f; acci[n] = 0.f; }
+    if (w < M) prefetch(w);
+    for (int q = w; q < M; q += kFW) {
+        float xr[32], xi[32];
+        rcc_cp_async_wait_all();
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 32; p++) {
+            const float2 u = stage[p * 32 + lane];
+            const float2 v = stage[(32 + p) * 32 + lane];
+            xr[p] = fmaf(u.x, v.x, u.y * v.y);       // u * conj(v)
+            xi[p] = fmaf(u.y, v.x, -u.x * v.y);
+        }
+        __syncwarp();
+        if (q + kFW < M) prefetch(q + kFW);
+        rcc_fft32_inv(xr, xi);
+        const float4* t4 = reinterpret_cast<const float4*>(tw_g + q * 32);
+#pragma unroll
+        for (int n = 0; n < 32; n += 2) {
+            const float4 t = __ldg(t4 + (n >> 1));
+            accr[n] = fmaf(xr[n], t.x, fmaf(-xi[n], t.y, accr[n]));
+            acci[n] = fmaf(xr[n], t.y, fmaf(xi[n], t.x, acci[n]));
+            accr[n + 1] = fmaf(xr[n + 1], t.z, fmaf(-xi[n + 1], t.w, accr[n + 1]));
+            acci[n + 1] = fmaf(xr[n + 1], t.w, fmaf(xi[n + 1], t.z, acci[n + 1]));
+        }
+    }
+    __syncthreads();     // every warp is done with its stage: reuse the buffer for the reduction
+#pragma unroll
+    for (int n = 0; n < 32; n++) red[(w * 32 + n) * 32 + lane] = make_float2(accr[n], acci[n]);
+    __syncthreads();
+    if (kx_raw < XH) {
+#pragma unroll
+        for (int k = 0; k < 32 / kFW; k++) {
+            const int pos = w * (32 / kFW) + k;
+            float sr = 0.f, si = 0.f;
+#pragma unroll
+            for (int u = 0; u < kFW; u++) {
+                const float2 v = red[(u * 32 + pos) * 32 + lane];
+                sr += v.x; si += v.y;
+            }
+            const int r = (rcc_bitrev5(pos) - c0) & 31;
+            if (r < nrows) T[((size_t)pair * H + row0 + r) * XH + kx] = make_float2(sr, si);
+        }
+    }
+}
+
 // Stage 2, table driven: out[pair][r][c] = scale * sum_kx Re(T[pair][r][kx] * E[kx][c]) with
 // E[kx][c] = w_kx e^{2 pi i kx x_c / X} tabulated once per call (float64 sincospi, stored as
 // (w cos, -w sin) so that the real part is two FMAs).  One CTA = 32 window rows x 32 window
@@ -568,7 +652,14 @@ extern "C" int pb_rcc_windows_dev(int n_pairs, const int* d_pair_i, const int* d
             if (const char* e = getenv("PB_RCC_OCC")) occ = atoi(e) == 3 ? 3 : 2;
             auto rows_kernel = occ == 2 ? rcc_fft_rows_kernel<2> : rcc_fft_rows_kernel<3>;
             cudaFuncSetAttribute(rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(tw_bytes, 32768));
-            const int smem_fft = (int)std::max<size_t>(tw_bytes, (size_t)kFW * 32 * 32 * sizeof(float2));
+            int smem_fft = (int)std::max<size_t>(tw_bytes, (size_t)kFW * 32 * 32 * sizeof(float2));
+            // PB_RCC_ROWS=regs selects the register-staged variant (A/B measurement); default: async staging
+            bool use_async = true;
+            if (const char* e = getenv("PB_RCC_ROWS")) use_async = strcmp(e, "regs") != 0;
+            if (use_async) {
+                smem_fft = kFW * 64 * 32 * (int)sizeof(float2);      // 64 KB: one 16 KB stage per warp
+                cudaFuncSetAttribute(rcc_fft_rows_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fft);
+            }
             const int nkb = (XH + 31) / 32;
             for (int p0 = 0; p0 < n_pairs;) {
                 // batch = as many pairs as T fits into the workspace, cut at a tile boundary
@@ -589,9 +680,14 @@ extern "C" int pb_rcc_windows_dev(int n_pairs, const int* d_pair_i, const int* d
                         const long long kk = key(order[t0]);
                         while (t1 < p1 && key(order[t1]) == kk) t1++;
                         dim3 g1(t1 - t0, nkb);
-                        rows_kernel<<<g1, 32 * kFW, smem_fft, s>>>(
-                            static_cast<const float2*>(d_spectra), spec, d_perm + t0, d_perm + n_pairs + t0,
-                            XH, M, d_tw, y_first & 31, row0, nrows, H, T + (size_t)(t0 - p0) * H * XH);
+                        if (use_async)
+                            rcc_fft_rows_async_kernel<<<g1, 32 * kFW, smem_fft, s>>>(
+                                static_cast<const float2*>(d_spectra), spec, d_perm + t0, d_perm + n_pairs + t0,
+                                XH, M, d_tw, y_first & 31, row0, nrows, H, T + (size_t)(t0 - p0) * H * XH);
+                        else
+                            rows_kernel<<<g1, 32 * kFW, smem_fft, s>>>(
+                                static_cast<const float2*>(d_spectra), spec, d_perm + t0, d_perm + n_pairs + t0,
+                                XH, M, d_tw, y_first & 31, row0, nrows, H, T + (size_t)(t0 - p0) * H * XH);
                         g_pb_launches++;
                         t0 = t1;
                     }
