@@ -304,6 +304,13 @@ int pb_undrift_windows(int n_seg, const long long* seg_start, const float* x, co
                        const float* lpx, const float* lpy, int Y, int X, double min_blur_width,
                        int Y0, int X0, int H, int W, float* windows, double* sums,
                        float* segments_out);
+/* Same for a subset of the pairs (pair_i[k], pair_j[k]), k < n_pairs; windows (n_pairs, H, W).
+ * Multi-GPU undrift: every rank renders and transforms all segments (cheap) and correlates
+ * only its share of the pairs -- no exchange of spectra.  n_pairs < 0 selects all i < j pairs. */
+int pb_undrift_windows_pairs(int n_seg, const long long* seg_start, const float* x, const float* y,
+                             const float* lpx, const float* lpy, int Y, int X, double min_blur_width,
+                             int Y0, int X0, int H, int W, int n_pairs, const int* pair_i,
+                             const int* pair_j, float* windows, double* sums, float* segments_out);
 
 #ifdef __cplusplus
 }

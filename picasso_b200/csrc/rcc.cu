@@ -822,15 +822,28 @@ extern "C" int pb_undrift_windows(int n_seg, const long long* seg_start, const f
                                   const float* y, const float* lpx, const float* lpy, int Y, int X,
                                   double min_blur_width, int Y0, int X0, int H, int W,
                                   float* windows, double* sums, float* segments_out /*nullable*/) {
+    return pb_undrift_windows_pairs(n_seg, seg_start, x, y, lpx, lpy, Y, X, min_blur_width, Y0, X0, H, W,
+                                    -1, nullptr, nullptr, windows, sums, segments_out);
+}
+
+// Same for a SUBSET of the pairs (multi-GPU: every rank renders all segments and transforms them
+// -- 33 ms for 200 x 4096^2 -- and correlates only its share of the pairs; no spectra exchange).
+// n_pairs < 0: all i < j pairs in the reference's order.
+extern "C" int pb_undrift_windows_pairs(int n_seg, const long long* seg_start, const float* x,
+                                        const float* y, const float* lpx, const float* lpy, int Y, int X,
+                                        double min_blur_width, int Y0, int X0, int H, int W,
+                                        int n_pairs_in, const int* pair_i, const int* pair_j,
+                                        float* windows, double* sums, float* segments_out /*nullable*/) {
     if (n_seg < 1) return PB_OK;
-    if (!seg_start || !sums || (n_seg > 1 && !windows)) { pb_set_error("pb_undrift_windows: null pointer"); return PB_ERR_INVALID; }
+    if (n_pairs_in > 0 && (!pair_i || !pair_j)) { pb_set_error("pb_undrift_windows_pairs: null pair list"); return PB_ERR_INVALID; }
+    if (!seg_start || !sums || (n_seg > 1 && n_pairs_in != 0 && !windows)) { pb_set_error("pb_undrift_windows: null pointer"); return PB_ERR_INVALID; }
     if (Y < 1 || X < 1 || H < 1 || W < 1 || Y0 < 0 || X0 < 0 || Y0 + H > Y || X0 + W > X) {
         pb_set_error("pb_undrift_windows: bad window");
         return PB_ERR_INVALID;
     }
     const size_t n_locs = (size_t)seg_start[n_seg];
     const size_t img = (size_t)Y * X, spec = (size_t)Y * (X / 2 + 1);
-    const int n_pairs = n_seg * (n_seg - 1) / 2;
+    const int n_pairs = n_pairs_in >= 0 ? n_pairs_in : n_seg * (n_seg - 1) / 2;
     int batch = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)1 << 30) / (spec * 8 + img * 4)));
     batch = std::max(1, std::min(batch, std::max(n_pairs, 1)));
     size_t max_seg = 0;
@@ -869,8 +882,18 @@ extern "C" int pb_undrift_windows(int n_seg, const long long* seg_start, const f
                                wsb, nullptr);
         }
         std::vector<int> pi, pj;
-        for (int i = 0; i < n_seg - 1; i++)
-            for (int j = i + 1; j < n_seg; j++) { pi.push_back(i); pj.push_back(j); }
+        if (n_pairs_in >= 0) {
+            pi.assign(pair_i, pair_i + n_pairs);
+            pj.assign(pair_j, pair_j + n_pairs);
+            for (int k = 0; k < n_pairs; k++)
+                if (pi[k] < 0 || pj[k] < 0 || pi[k] >= n_seg || pj[k] >= n_seg) {
+                    pb_set_error("pb_undrift_windows_pairs: pair index out of range");
+                    rc = PB_ERR_INVALID;
+                }
+        } else {
+            for (int i = 0; i < n_seg - 1; i++)
+                for (int j = i + 1; j < n_seg; j++) { pi.push_back(i); pj.push_back(j); }
+        }
         if (n_pairs) {
             ok(cudaMemcpy(dpi, pi.data(), n_pairs * 4, cudaMemcpyHostToDevice));
             ok(cudaMemcpy(dpj, pj.data(), n_pairs * 4, cudaMemcpyHostToDevice));

@@ -21,6 +21,9 @@ def _declare(l):
     vp, i32 = C.c_void_p, C.c_int
     l.pb_rcc_windows.argtypes = [i32, i32, i32, vp, i32, i32, i32, i32, vp, vp]
     l.pb_rcc_windows.restype = i32
+    l.pb_undrift_windows_pairs.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, C.c_double, i32, i32, i32, i32,
+                                           i32, vp, vp, vp, vp, vp]
+    l.pb_undrift_windows_pairs.restype = i32
     l.pb_undrift_windows.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, C.c_double, i32, i32, i32,
                                      i32, vp, vp, vp]
     l.pb_undrift_windows.restype = i32
@@ -273,10 +276,11 @@ def rcc(segments, max_shift: float | None = None, callback: Callable[[int], None
     return _rcc_from_windows(win, sums, Y, X, Y_, X_, callback)
 
 
-def _rcc_of_locs(locs, info, bounds, min_blur_width, max_shift, callback):
+def _windows_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=None):
     """Fused device path used by postprocess.undrift: render the segment images on the GPU
     and cross-correlate them there (same kernels as segment() + rcc(), no host round trip
-    of the (n_seg, Y, X) image stack)."""
+    of the (n_seg, Y, X) image stack).  ``pairs`` = (pair_i, pair_j) restricts the work to a
+    subset of the pairs (multi-GPU sharding); returns ``(windows, sums, (Y, X, Y_, X_))``."""
     l = _lib.load()
     _declare(l)
     _lib.require_gpu()
@@ -293,10 +297,24 @@ def _rcc_of_locs(locs, info, bounds, min_blur_width, max_shift, callback):
     take = lambda c: np.ascontiguousarray(locs[c].to_numpy()[idx], dtype=np.float32)
     x, y, lpx, lpy = take("x"), take("y"), take("lpx"), take("lpy")
     Y_, X_, H, W = _crop_geometry(Y, X, max_shift)
-    n_pairs = n_seg * (n_seg - 1) // 2
-    win = np.zeros((n_pairs, H, W), dtype=np.float32)
     sums = np.zeros(n_seg, dtype=np.float64)
-    _lib.check(l.pb_undrift_windows(n_seg, _lib.ptr(seg_start), _lib.ptr(x), _lib.ptr(y),
-                                    _lib.ptr(lpx), _lib.ptr(lpy), Y, X, float(min_blur_width),
-                                    Y_, X_, H, W, _lib.ptr(win), _lib.ptr(sums), None))
+    if pairs is None:
+        n_pairs = n_seg * (n_seg - 1) // 2
+        win = np.zeros((n_pairs, H, W), dtype=np.float32)
+        _lib.check(l.pb_undrift_windows(n_seg, _lib.ptr(seg_start), _lib.ptr(x), _lib.ptr(y),
+                                        _lib.ptr(lpx), _lib.ptr(lpy), Y, X, float(min_blur_width),
+                                        Y_, X_, H, W, _lib.ptr(win), _lib.ptr(sums), None))
+    else:
+        pi = np.ascontiguousarray(pairs[0], dtype=np.int32)
+        pj = np.ascontiguousarray(pairs[1], dtype=np.int32)
+        win = np.zeros((len(pi), H, W), dtype=np.float32)
+        _lib.check(l.pb_undrift_windows_pairs(n_seg, _lib.ptr(seg_start), _lib.ptr(x), _lib.ptr(y),
+                                              _lib.ptr(lpx), _lib.ptr(lpy), Y, X, float(min_blur_width),
+                                              Y_, X_, H, W, len(pi), _lib.ptr(pi), _lib.ptr(pj),
+                                              _lib.ptr(win), _lib.ptr(sums), None))
+    return win, sums, (Y, X, Y_, X_)
+
+
+def _rcc_of_locs(locs, info, bounds, min_blur_width, max_shift, callback):
+    win, sums, (Y, X, Y_, X_) = _windows_of_locs(locs, info, bounds, min_blur_width, max_shift)
     return _rcc_from_windows(win, sums, Y, X, Y_, X_, callback)

@@ -436,6 +436,15 @@ def _localize_fused(movie, minimum_ng, box, camera_info, fit, eps, max_it, roi=N
     """movie -> localization table without leaving the GPU in between (``pb_localize``):
     identify -> get_spots -> fit -> locs_from_fits per frame chunk; only the finished columns
     come back.  Same result as ``identify`` + ``fit2D``."""
+    names = LOCS_COLUMNS_MLE if fit <= 1 else LOCS_COLUMNS_LQ
+    cols = _localize_fused_columns(movie, minimum_ng, box, camera_info, fit, eps, max_it, roi=roi,
+                                   frame_bounds=frame_bounds, progress_callback=progress_callback)
+    return _columns_to_locs(cols, names)
+
+
+def _localize_fused_columns(movie, minimum_ng, box, camera_info, fit, eps, max_it, roi=None,
+                            frame_bounds=None, progress_callback=None):
+    """The (ncols, n) float32 column block of ``_localize_fused`` in (frame, y, x) order."""
     lib = _lib_ready()
     N = len(movie)
     lo, hi = _frame_range(N, frame_bounds)
@@ -481,7 +490,7 @@ def _localize_fused(movie, minimum_ng, box, camera_info, fit, eps, max_it, roi=N
         cols = np.concatenate(parts, axis=1)
     else:
         cols = np.zeros((len(names), 0), np.float32)
-    return _columns_to_locs(cols, names)
+    return cols
 
 
 def _fit_spots(spots, identifications, box, camera_info, fitting_method, eps, max_it, mle_method,

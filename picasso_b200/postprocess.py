@@ -84,7 +84,7 @@ def apply_drift(locs: pd.DataFrame, info, *, drift):
 
 def undrift(locs: pd.DataFrame, info, segmentation: int, display: bool = True,
             segmentation_callback: Callable[[int], None] | None = None,
-            rcc_callback: Callable[[int], None] | None = None):
+            rcc_callback: Callable[[int], None] | None = None, _shifts_fn=None):
     """Undrift by RCC (reference postprocess.py:2903-2961): render segments
     (gaussian blur, min_blur_width=1, oversampling 1), cross-correlate all pairs
     (max_shift 32), spline the segment shifts over all frames and subtract.  Returns
@@ -103,7 +103,9 @@ def undrift(locs: pd.DataFrame, info, segmentation: int, display: bool = True,
             segmentation_callback(i)
     if rcc_callback is None:
         rcc_callback = lambda _i: None
-    shift_y, shift_x = imageprocess._rcc_of_locs(locs, info, bounds, 1, 32, rcc_callback)
+    # _shifts_fn: multi-GPU callers (picasso_b200.distributed.undrift_sharded) shard the pairs
+    rcc_of_locs = _shifts_fn if _shifts_fn is not None else imageprocess._rcc_of_locs
+    shift_y, shift_x = rcc_of_locs(locs, info, bounds, 1, 32, rcc_callback)
     t = (bounds[1:] + bounds[:-1]) / 2
     drift_x_pol = interpolate.InterpolatedUnivariateSpline(t, shift_x, k=3)
     drift_y_pol = interpolate.InterpolatedUnivariateSpline(t, shift_y, k=3)

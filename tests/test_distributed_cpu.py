@@ -52,8 +52,18 @@ def _worker(rank, world, port, q):
         part = {k: v[lo:hi] for k, v in locs.items()}
         n_part, img = oracle.render(part, info, oversampling=4, blur_method="gaussian")
         img = pbd.all_reduce_image(dist, torch, img)
+        # column blocks of the fused localize path (uint32 bit patterns in a float32 block)
+        n_r = 5 + 3 * rank
+        blk = np.arange(3 * n_r, dtype=np.float32).reshape(3, n_r) + 100 * rank
+        blk[0] = (np.arange(n_r, dtype=np.uint32) + 0x7FC00000 + rank).view(np.float32)   # NaN payloads
+        cols = pbd.gather_column_blocks(dist, torch, blk)
+        # pair windows sharded round-robin (undrift)
+        n_seg = 7
+        pi, pj = pbd.my_pairs(n_seg, rank, world)
+        win = np.stack([np.full((4, 4), 100 * i + j, np.float32) for i, j in zip(pi, pj)])
+        full = pbd.gather_pair_windows(dist, torch, win, n_seg)
         if rank == 0:
-            q.put((th, cr, ll, it, g, img))
+            q.put((th, cr, ll, it, g, img, cols, full))
     finally:
         dist.destroy_process_group()
 
@@ -69,7 +79,7 @@ def test_two_rank_gloo_plumbing(oracle):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    th, cr, ll, it, g, img = q.get(timeout=180)
+    th, cr, ll, it, g, img, cols, full = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -91,6 +101,15 @@ def test_two_rank_gloo_plumbing(oracle):
     n_all, ref = oracle.render(locs, [{"Height": 16, "Width": 16, "Pixelsize": 100}],
                                oversampling=4, blur_method="gaussian")
     np.testing.assert_allclose(img, ref, rtol=1e-5, atol=1e-7)
+    # gathered column blocks: rank order, payload bits preserved
+    assert cols.shape == (3, 5 + 8)
+    np.testing.assert_array_equal(cols[0].view(np.uint32)[:5], np.arange(5, dtype=np.uint32) + 0x7FC00000)
+    np.testing.assert_array_equal(cols[0].view(np.uint32)[5:], np.arange(8, dtype=np.uint32) + 0x7FC00001)
+    np.testing.assert_array_equal(cols[1][5:], np.arange(8, 16, dtype=np.float32) + 100)
+    # gathered pair windows: the reference's pair order (i outer, j inner)
+    pairs = [(i, j) for i in range(6) for j in range(i + 1, 7)]
+    assert full.shape == (21, 4, 4)
+    np.testing.assert_array_equal(full[:, 0, 0], [100 * i + j for i, j in pairs])
 
 
 def test_shard_bounds():
