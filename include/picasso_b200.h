@@ -50,6 +50,13 @@ int pb_synchronize(void);                 /* cudaDeviceSynchronize on the curren
 /* pinned host memory for callers that want full PCIe speed (optional) */
 int pb_host_alloc(void** ptr, size_t bytes);
 int pb_host_free(void* ptr);
+/* Transfers between ordinary (pageable) host memory and device buffers at close to PCIe speed:
+ * chunks alternate between two pinned staging buffers filled / drained by PB_COPY_THREADS host
+ * threads (default min(12, cores)); pinned host memory is copied directly.  pb_copy_h2d returns
+ * once the last chunk is enqueued on `stream` (a pageable h_src may be reused immediately);
+ * pb_copy_d2h is blocking.  Every host-pointer entry point below uses these internally. */
+int pb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int pb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 long long pb_launch_count(void);
 
@@ -311,6 +318,18 @@ int pb_undrift_windows_pairs(int n_seg, const long long* seg_start, const float*
                              const float* lpx, const float* lpy, int Y, int X, double min_blur_width,
                              int Y0, int X0, int H, int W, int n_pairs, const int* pair_i,
                              const int* pair_j, float* windows, double* sums, float* segments_out);
+
+/* Windows and their peak fits on the device (the per-pair body of get_image_shift,
+ * imageprocess.py:103-157: arg-max, 5x5 cut-out, Gaussian peak fit with the reference's start
+ * values and bounds).  peak_records (n_pairs, 32) float64 per pair: [0] status (0 fitted,
+ * 1 not settled -> re-fit the 5x5 window [5..29] on the host with the reference's curve_fit,
+ * 2 cut-out empty / not square -> shift (0, 0), 3 square but not 5x5 -> host needs the window),
+ * [1] y_max, [2] x_max, [3] xc, [4] yc.  `windows` is optional (NULL: 256 bytes per pair come
+ * back instead of H x W floats). */
+int pb_undrift_peaks_pairs(int n_seg, const long long* seg_start, const float* x, const float* y,
+                           const float* lpx, const float* lpy, int Y, int X, double min_blur_width,
+                           int Y0, int X0, int H, int W, int n_pairs, const int* pair_i,
+                           const int* pair_j, double* peak_records, double* sums, float* windows);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,15 @@ extern "C" int pb_host_alloc(void** ptr, size_t bytes) {
     PB_CUDA_CHECK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
     return PB_OK;
 }
+// Pageable-friendly transfers for callers that keep their own device buffers (csrc/transfer.cu).
+extern "C" int pb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream) {
+    if (bytes && (!d_dst || !h_src)) { pb_set_error("pb_copy_h2d: null pointer"); return PB_ERR_INVALID; }
+    return pb_h2d(d_dst, h_src, bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int pb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream) {
+    if (bytes && (!h_dst || !d_src)) { pb_set_error("pb_copy_d2h: null pointer"); return PB_ERR_INVALID; }
+    return pb_d2h(h_dst, d_src, bytes, reinterpret_cast<cudaStream_t>(stream));
+}
 extern "C" int pb_host_free(void* ptr) {
     if (ptr) PB_CUDA_CHECK(cudaFreeHost(ptr));
     return PB_OK;

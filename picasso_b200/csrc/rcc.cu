@@ -526,6 +526,128 @@ rcc_cols_gemm_kernel(const float2* __restrict__ T, int H, int W, int XH, const f
     }
 }
 
+
+// ---- device-side peak fit of the correlation windows ---------------------------------------
+// One thread per pair: arg-max of the H x W window (first maximum in row-major order, like
+// np.argmax), the 5 x 5 cut-out around it (imageprocess.py:103-116) and a Levenberg-Marquardt fit
+// of a * exp(-((x-xc)^2 + (y-yc)^2) / (2 s^2)) + b with the reference's start values
+// [max, 0, 0, 1, min] and bounds a, s, b >= 0 (imageprocess.py:119-135) -- the same iteration as
+// the host's vectorised solver (picasso_b200/imageprocess.py::_gauss_peak_fit_batch).  Record per
+// pair (32 doubles): [0] status, [1] y_max, [2] x_max, [3] xc, [4] yc, [5..29] the 5 x 5 window.
+//   status 0: fitted (interior optimum)      1: not settled -> the host re-fits the 5 x 5 window
+//          2: cut-out empty / not square -> shift (0, 0)    3: cut-out square but not 5 x 5 -> host
+constexpr int kRecDoubles = 32;
+
+__device__ __forceinline__ bool rcc_solve5(double A[5][5], double b[5]) {
+    for (int c = 0; c < 5; c++) {
+        int piv = c;
+        double best = fabs(A[c][c]);
+        for (int r = c + 1; r < 5; r++) if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
+        if (!(best > 0.0)) return false;
+        if (piv != c) {
+            for (int k = 0; k < 5; k++) { const double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+            const double t = b[c]; b[c] = b[piv]; b[piv] = t;
+        }
+        const double inv = 1.0 / A[c][c];
+        for (int r = c + 1; r < 5; r++) {
+            const double f = A[r][c] * inv;
+            for (int k = c; k < 5; k++) A[r][k] -= f * A[c][k];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int c = 4; c >= 0; c--) {
+        double v = b[c];
+        for (int k = c + 1; k < 5; k++) v -= A[c][k] * b[k];
+        b[c] = v / A[c][c];
+    }
+    return true;
+}
+
+__device__ void rcc_model5(const double p[5], const double* d, double res[25], double J[25][5], double* cost) {
+    const double a = p[0], xc = p[1], yc = p[2], sg = p[3], bb = p[4];
+    const double s2 = sg * sg, s3 = s2 * sg;
+    double c = 0.0;
+    for (int i = 0; i < 25; i++) {
+        const double dx = (double)(i % 5 - 2) - xc, dy = (double)(i / 5 - 2) - yc;
+        const double r2 = dx * dx + dy * dy;
+        const double E = exp(-0.5 * r2 / s2);
+        const double m = a * E + bb;
+        J[i][0] = E; J[i][1] = a * E * dx / s2; J[i][2] = a * E * dy / s2; J[i][3] = a * E * r2 / s3; J[i][4] = 1.0;
+        res[i] = d[i] - m;
+        c += res[i] * res[i];
+    }
+    *cost = c;
+}
+
+__global__ void __launch_bounds__(64)
+rcc_peakfit_kernel(const float* __restrict__ windows, int n_pairs, int H, int W, double* __restrict__ rec) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const float* w = windows + (size_t)pair * H * W;
+    double* out = rec + (size_t)pair * kRecDoubles;
+    int am = 0;
+    float best = w[0];
+    for (int i = 1; i < H * W; i++) {
+        const float v = w[i];
+        if (v > best || (best != best && v == v)) { best = v; am = i; }   // first max; NaN handling as np.argmax
+    }
+    if (w[0] != w[0]) am = 0;                                              // np.argmax returns the first NaN
+    const int ym = am / W, xm = am % W;
+    out[1] = ym; out[2] = xm; out[3] = 0.0; out[4] = 0.0;
+    // python slice [ym-2 : ym+3]: a negative start wraps around (-> empty for ym < 2)
+    auto span = [](int c, int n) { const int lo = c - 2, hi = min(c + 3, n); return lo < 0 ? 0 : max(hi - lo, 0); };
+    const int ny = span(ym, H), nx = span(xm, W);
+    if (ny == 0 || nx == 0 || ny != nx) { out[0] = 2.0; return; }
+    if (ny != 5) { out[0] = 3.0; return; }
+    double d[25];
+    double dmax = -INFINITY, dmin = INFINITY;
+    for (int i = 0; i < 25; i++) {
+        d[i] = (double)w[(size_t)(ym - 2 + i / 5) * W + (xm - 2 + i % 5)];
+        out[5 + i] = d[i];
+        dmax = fmax(dmax, d[i]); dmin = fmin(dmin, d[i]);
+    }
+    double p[5] = {dmax, 0.0, 0.0, 1.0, dmin};
+    double lam = 1e-3, cost, res[25], J[25][5];
+    rcc_model5(p, d, res, J, &cost);
+    bool converged = false, active = true;
+    for (int it = 0; it < 60 && active; it++) {
+        double A[5][5], g[5];
+        for (int j = 0; j < 5; j++) {
+            g[j] = 0.0;
+            for (int k = 0; k < 5; k++) A[j][k] = 0.0;
+        }
+        for (int i = 0; i < 25; i++)
+            for (int j = 0; j < 5; j++) {
+                g[j] += J[i][j] * res[i];
+                for (int k = 0; k < 5; k++) A[j][k] += J[i][j] * J[i][k];
+            }
+        for (int j = 0; j < 5; j++) A[j][j] += lam * fmax(A[j][j], 1e-300);
+        if (!rcc_solve5(A, g)) { active = false; break; }
+        double t[5], smax = 0.0, pmax = 0.0;
+        for (int j = 0; j < 5; j++) { t[j] = p[j] + g[j]; smax = fmax(smax, fabs(g[j])); pmax = fmax(pmax, fabs(p[j])); }
+        t[0] = fmax(t[0], 0.0); t[3] = fmax(t[3], 1e-12); t[4] = fmax(t[4], 0.0);
+        double ct, rt[25], Jt[25][5];
+        rcc_model5(t, d, rt, Jt, &ct);
+        if (isfinite(ct) && ct <= cost) {
+            const bool small = smax < 1e-10 * (1.0 + pmax);
+            const bool flat = (cost - ct) <= 1e-14 * (cost + 1e-300);
+            for (int j = 0; j < 5; j++) p[j] = t[j];
+            for (int i = 0; i < 25; i++) { res[i] = rt[i]; for (int j = 0; j < 5; j++) J[i][j] = Jt[i][j]; }
+            cost = ct;
+            lam = fmax(lam * 0.3, 1e-12);
+            if (small || flat) { converged = true; active = false; }
+        } else {
+            lam *= 10.0;
+            if (lam > 1e12) active = false;
+        }
+    }
+    bool fin = true;
+    for (int j = 0; j < 5; j++) fin = fin && isfinite(p[j]);
+    const bool ok = converged && fin && p[0] > 0.0 && p[4] > 0.0 && p[3] > 1e-6;
+    out[0] = ok ? 0.0 : 1.0;
+    out[3] = p[1]; out[4] = p[2];
+}
+
 struct CufftPlan {
     cufftHandle h = 0;
     bool ok = false;
@@ -829,14 +951,39 @@ extern "C" int pb_undrift_windows(int n_seg, const long long* seg_start, const f
 // Same for a SUBSET of the pairs (multi-GPU: every rank renders all segments and transforms them
 // -- 33 ms for 200 x 4096^2 -- and correlates only its share of the pairs; no spectra exchange).
 // n_pairs < 0: all i < j pairs in the reference's order.
+static int undrift_impl(int n_seg, const long long* seg_start, const float* x, const float* y,
+                        const float* lpx, const float* lpy, int Y, int X, double min_blur_width, int Y0,
+                        int X0, int H, int W, int n_pairs_in, const int* pair_i, const int* pair_j,
+                        float* windows, double* sums, float* segments_out, double* peak_records);
+
 extern "C" int pb_undrift_windows_pairs(int n_seg, const long long* seg_start, const float* x,
                                         const float* y, const float* lpx, const float* lpy, int Y, int X,
                                         double min_blur_width, int Y0, int X0, int H, int W,
                                         int n_pairs_in, const int* pair_i, const int* pair_j,
                                         float* windows, double* sums, float* segments_out /*nullable*/) {
+    return undrift_impl(n_seg, seg_start, x, y, lpx, lpy, Y, X, min_blur_width, Y0, X0, H, W, n_pairs_in,
+                        pair_i, pair_j, windows, sums, segments_out, nullptr);
+}
+
+// Windows AND their peak fits on the device: per pair a 32-double record (see rcc_peakfit_kernel);
+// `windows` may be NULL -- then only 256 bytes per pair come back instead of H x W floats.
+extern "C" int pb_undrift_peaks_pairs(int n_seg, const long long* seg_start, const float* x,
+                                      const float* y, const float* lpx, const float* lpy, int Y, int X,
+                                      double min_blur_width, int Y0, int X0, int H, int W,
+                                      int n_pairs_in, const int* pair_i, const int* pair_j,
+                                      double* peak_records, double* sums, float* windows /*nullable*/) {
+    if (!peak_records && n_pairs_in != 0 && n_seg > 1) { pb_set_error("pb_undrift_peaks_pairs: null records"); return PB_ERR_INVALID; }
+    return undrift_impl(n_seg, seg_start, x, y, lpx, lpy, Y, X, min_blur_width, Y0, X0, H, W, n_pairs_in,
+                        pair_i, pair_j, windows, sums, nullptr, peak_records);
+}
+
+static int undrift_impl(int n_seg, const long long* seg_start, const float* x, const float* y,
+                        const float* lpx, const float* lpy, int Y, int X, double min_blur_width, int Y0,
+                        int X0, int H, int W, int n_pairs_in, const int* pair_i, const int* pair_j,
+                        float* windows, double* sums, float* segments_out, double* peak_records) {
     if (n_seg < 1) return PB_OK;
     if (n_pairs_in > 0 && (!pair_i || !pair_j)) { pb_set_error("pb_undrift_windows_pairs: null pair list"); return PB_ERR_INVALID; }
-    if (!seg_start || !sums || (n_seg > 1 && n_pairs_in != 0 && !windows)) { pb_set_error("pb_undrift_windows: null pointer"); return PB_ERR_INVALID; }
+    if (!seg_start || !sums || (n_seg > 1 && n_pairs_in != 0 && !windows && !peak_records)) { pb_set_error("pb_undrift_windows: null pointer"); return PB_ERR_INVALID; }
     if (Y < 1 || X < 1 || H < 1 || W < 1 || Y0 < 0 || X0 < 0 || Y0 + H > Y || X0 + W > X) {
         pb_set_error("pb_undrift_windows: bad window");
         return PB_ERR_INVALID;
@@ -901,9 +1048,22 @@ extern "C" int pb_undrift_windows_pairs(int n_seg, const long long* seg_start, c
         if (e == cudaSuccess && rc == PB_OK) rc = pb_rcc_spectra_dev(n_seg, Y, X, dseg, dspec, dsum, nullptr);
         if (e == cudaSuccess && rc == PB_OK && n_pairs)
             rc = pb_rcc_windows_dev(n_pairs, dpi, dpj, Y, X, dspec, Y0, X0, H, W, dwin, batch, dws, wsb, nullptr);
+        if (e == cudaSuccess && rc == PB_OK && n_pairs && peak_records) {
+            // the spectra are no longer needed: their buffer holds the peak records
+            double* drec = static_cast<double*>(dspec);
+            if ((size_t)n_pairs * kRecDoubles * 8 > (size_t)n_seg * spec * 8) {
+                pb_set_error("pb_undrift_peaks_pairs: record buffer too small");
+                rc = PB_ERR_INVALID;
+            } else {
+                rcc_peakfit_kernel<<<(n_pairs + 63) / 64, 64>>>(dwin, n_pairs, H, W, drec);
+                g_pb_launches++;
+                ok(cudaGetLastError());
+                ok(cudaMemcpy(peak_records, drec, (size_t)n_pairs * kRecDoubles * 8, cudaMemcpyDeviceToHost));
+            }
+        }
         if (e == cudaSuccess && rc == PB_OK) {
             ok(cudaMemcpy(sums, dsum, n_seg * 8, cudaMemcpyDeviceToHost));
-            if (n_pairs && pb_d2h(windows, dwin, (size_t)n_pairs * H * W * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
+            if (n_pairs && windows && pb_d2h(windows, dwin, (size_t)n_pairs * H * W * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
             if (segments_out && pb_d2h(segments_out, dseg, n_seg * img * 4, nullptr) != PB_OK) ok(cudaErrorUnknown);
         }
     }

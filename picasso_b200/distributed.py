@@ -183,32 +183,58 @@ def localize_sharded(dist, torch, movie, camera_info, parameters, *, fitting_met
 
 
 def render_sharded(dist, torch, locs, info, device="cuda", **kwargs):
-    """``render.render`` with the localizations sharded by index; partial images are summed with
-    one all-reduce.  Returns (n, image) on every rank."""
+    """``render.render`` with the localizations sharded by index: every rank splats its share into
+    a device image, the partial images are summed with ONE all-reduce on the GPUs (NVLink) and
+    downloaded once.  Returns (n, image) on every rank."""
     from . import render as pbr
 
     rank, world = dist.get_rank(), dist.get_world_size()
     lo, hi = my_shard(len(locs), rank, world)
-    n, image = pbr.render(locs.iloc[lo:hi], info, **kwargs)
-    t = torch.from_numpy(np.ascontiguousarray(image)).to(device)
-    cnt = torch.tensor([int(n)], dtype=torch.int64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    cnt, image = pbr.render_to_device(torch, locs.iloc[lo:hi], info, device=device, **kwargs)
+    dist.all_reduce(image, op=dist.ReduceOp.SUM)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    return int(cnt.item()), t.cpu().numpy()
+    return int(cnt.item()), pbr.image_to_host(torch, image)
+
+
+def gather_pair_values(dist, torch, vals_mine, n_seg, device="cpu"):
+    """All-gather per-pair float64 rows (round-robin pair shards) into the reference's pair order:
+    ``vals_mine`` (n_mine, k) -> (n_pairs, k) on every rank."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_pairs = n_seg * (n_seg - 1) // 2
+    vals_mine = np.ascontiguousarray(vals_mine, dtype=np.float64)
+    k = vals_mine.shape[1]
+    counts = [len(range(r, n_pairs, world)) for r in range(world)]
+    nmax = max(max(counts), 1)
+    pad = torch.zeros((nmax, k), dtype=torch.float64, device=device)
+    pad[: counts[rank]] = torch.from_numpy(vals_mine).to(device)
+    out = torch.empty((world, nmax, k), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out.view(-1), pad.view(-1))
+    out = out.cpu().numpy()
+    full = np.zeros((n_pairs, k))
+    for r in range(world):
+        full[r::world] = out[r][: counts[r]]
+    return full
 
 
 def undrift_sharded(dist, torch, locs, info, segmentation, device="cuda"):
-    """``postprocess.undrift`` with the segment pairs sharded round-robin over the ranks."""
-    from . import imageprocess, postprocess
+    """``postprocess.undrift`` with the segment pairs sharded round-robin over the ranks: every
+    rank renders and transforms all segments, correlates its pairs and fits their peaks on its GPU;
+    only two float64 shifts per pair are exchanged before ``minimize_shifts``."""
+    from . import imageprocess, lib, postprocess
 
     rank, world = dist.get_rank(), dist.get_world_size()
 
     def shifts(locs_, info_, bounds, min_blur_width, max_shift, callback):
         n_seg = len(bounds) - 1
-        win, sums, (Y, X, Y_, X_) = imageprocess._windows_of_locs(
-            locs_, info_, bounds, min_blur_width, max_shift, pairs=my_pairs(n_seg, rank, world))
-        full = gather_pair_windows(dist, torch, win, n_seg, device=device)
-        return imageprocess._rcc_from_windows(full, sums, Y, X, Y_, X_, callback)
+        pi, pj = my_pairs(n_seg, rank, world)
+        sy, sx = imageprocess._shifts_of_locs(locs_, info_, bounds, min_blur_width, max_shift, pairs=(pi, pj))
+        full = gather_pair_values(dist, torch, np.stack([sy, sx], 1), n_seg, device=device)
+        shifts_x = np.zeros((n_seg, n_seg))
+        shifts_y = np.zeros((n_seg, n_seg))
+        ai, aj = np.triu_indices(n_seg, 1)
+        shifts_y[ai, aj] = full[:, 0]
+        shifts_x[ai, aj] = full[:, 1]
+        return lib.minimize_shifts(shifts_x, shifts_y)
 
     return postprocess.undrift(locs, info, segmentation, display=False,
                                segmentation_callback=lambda i: None, rcc_callback=lambda i: None,

@@ -24,6 +24,9 @@ def _declare(l):
     l.pb_undrift_windows_pairs.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, C.c_double, i32, i32, i32, i32,
                                            i32, vp, vp, vp, vp, vp]
     l.pb_undrift_windows_pairs.restype = i32
+    l.pb_undrift_peaks_pairs.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, C.c_double, i32, i32, i32, i32,
+                                         i32, vp, vp, vp, vp, vp]
+    l.pb_undrift_peaks_pairs.restype = i32
     l.pb_undrift_windows.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, C.c_double, i32, i32, i32,
                                      i32, vp, vp, vp]
     l.pb_undrift_windows.restype = i32
@@ -206,22 +209,11 @@ def get_image_shift(imageA, imageB, box: int, roi: int | None = None, display: b
     return _shift_from_window(win[0].astype(np.float64), Y, X, Y_, X_, box)
 
 
-def _rcc_from_windows(win, sums, Y, X, Y_, X_, callback):
-    """Pairwise shifts from the correlation windows -> minimize_shifts (the loop body of the
-    reference's rcc, imageprocess.py:191-217).  The 5x5 peak fits of all pairs are done in
-    one vectorised pass; windows it cannot settle go through scipy's ``curve_fit``."""
-    n_segments = len(sums)
-    shifts_x = np.zeros((n_segments, n_segments))
-    shifts_y = np.zeros((n_segments, n_segments))
-    n_pairs = int(n_segments * (n_segments - 1) / 2)
-    bar = None
-    if callback is None:
-        from tqdm import tqdm
-
-        bar = tqdm(total=n_pairs, desc="Correlating image pairs", unit="pairs")
-    else:
-        callback(0)
-    pairs = [(i, j) for i in range(n_segments - 1) for j in range(i + 1, n_segments)]
+def _pair_shifts_from_windows(win, sums, pairs, Y, X, Y_, X_, callback=None):
+    """(shift_y, shift_x) of every pair in ``pairs`` from its correlation window (the body of the
+    reference's ``get_image_shift``, imageprocess.py:103-157, for all pairs at once): arg-max,
+    5x5 window, Gaussian peak fit.  The fits of all pairs are done in one vectorised pass;
+    windows it cannot settle go through scipy's ``curve_fit``."""
     geo, rois, which = [], [], []
     for flag, (i, j) in enumerate(pairs):
         if sums[i] == 0 or sums[j] == 0:
@@ -240,7 +232,9 @@ def _rcc_from_windows(win, sums, Y, X, Y_, X_, callback):
     fitted = {}
     for q, flag in enumerate(which):
         fitted[flag] = (bx[q], by[q]) if ok[q] else _gauss_peak_fit(rois[q])
-    for flag, (i, j) in enumerate(pairs):
+    sy_all = np.zeros(len(pairs))
+    sx_all = np.zeros(len(pairs))
+    for flag in range(len(pairs)):
         g = geo[flag]
         if g is None or not g[2]:
             sy, sx = 0, 0
@@ -249,11 +243,32 @@ def _rcc_from_windows(win, sums, Y, X, Y_, X_, callback):
             xc = xc + X_ + g[1] - np.floor(X / 2)
             yc = yc + Y_ + g[0] - np.floor(Y / 2)
             sy, sx = -yc, -xc
-        shifts_y[i, j], shifts_x[i, j] = sy, sx
-        if bar is not None:
-            bar.update()
-        else:
+        sy_all[flag], sx_all[flag] = sy, sx
+        if callback is not None:
             callback(flag + 1)
+    return sy_all, sx_all
+
+
+def _rcc_from_windows(win, sums, Y, X, Y_, X_, callback):
+    """Pairwise shifts from the correlation windows -> minimize_shifts (the loop body of the
+    reference's rcc, imageprocess.py:191-217)."""
+    n_segments = len(sums)
+    shifts_x = np.zeros((n_segments, n_segments))
+    shifts_y = np.zeros((n_segments, n_segments))
+    n_pairs = int(n_segments * (n_segments - 1) / 2)
+    bar = None
+    if callback is None:
+        from tqdm import tqdm
+
+        bar = tqdm(total=n_pairs, desc="Correlating image pairs", unit="pairs")
+        step = lambda k: bar.update()   # noqa: E731
+    else:
+        callback(0)
+        step = callback
+    pairs = [(i, j) for i in range(n_segments - 1) for j in range(i + 1, n_segments)]
+    sy_all, sx_all = _pair_shifts_from_windows(win, sums, pairs, Y, X, Y_, X_, step)
+    for flag, (i, j) in enumerate(pairs):
+        shifts_y[i, j], shifts_x[i, j] = sy_all[flag], sx_all[flag]
     if bar is not None:
         bar.close()
     return lib.minimize_shifts(shifts_x, shifts_y)
@@ -286,16 +301,7 @@ def _windows_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=None):
     _lib.require_gpu()
     Y, X = info[0]["Height"], info[0]["Width"]
     n_seg = len(bounds) - 1
-    frames = locs["frame"].to_numpy()
-    # stable grouping by segment; frames outside [bounds[0], bounds[-1]) are dropped
-    seg_of = np.searchsorted(bounds, frames, side="right") - 1
-    keep = (frames >= bounds[0]) & (frames < bounds[-1])
-    idx = np.flatnonzero(keep)
-    idx = idx[np.argsort(seg_of[idx], kind="stable")]
-    counts = np.bincount(seg_of[idx], minlength=n_seg)[:n_seg]
-    seg_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    take = lambda c: np.ascontiguousarray(locs[c].to_numpy()[idx], dtype=np.float32)
-    x, y, lpx, lpy = take("x"), take("y"), take("lpx"), take("lpy")
+    seg_start, x, y, lpx, lpy = _segment_arrays(locs, info, bounds)
     Y_, X_, H, W = _crop_geometry(Y, X, max_shift)
     sums = np.zeros(n_seg, dtype=np.float64)
     if pairs is None:
@@ -315,6 +321,93 @@ def _windows_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=None):
     return win, sums, (Y, X, Y_, X_)
 
 
+def _segment_arrays(locs, info, bounds):
+    """Localization columns grouped by segment (stable), the way pb_undrift_* expects them."""
+    n_seg = len(bounds) - 1
+    frames = locs["frame"].to_numpy()
+    seg_of = np.searchsorted(bounds, frames, side="right") - 1
+    keep = (frames >= bounds[0]) & (frames < bounds[-1])
+    idx = np.flatnonzero(keep)
+    idx = idx[np.argsort(seg_of[idx], kind="stable")]
+    counts = np.bincount(seg_of[idx], minlength=n_seg)[:n_seg]
+    seg_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    take = lambda c: np.ascontiguousarray(locs[c].to_numpy()[idx], dtype=np.float32)   # noqa: E731
+    return seg_start, take("x"), take("y"), take("lpx"), take("lpy")
+
+
+def _shifts_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=None, callback=None):
+    """Per-pair (shift_y, shift_x) with everything up to the peak fit on the GPU
+    (``pb_undrift_peaks_pairs``): segments rendered, transformed, correlated and fitted on the
+    device; 256 bytes per pair come back.  Windows the device solver does not settle are re-fitted
+    with scipy's bounded ``curve_fit`` like the reference; the rare square-but-not-5x5 cut-out at
+    the crop corner goes through the window path."""
+    l = _lib.load()
+    _declare(l)
+    _lib.require_gpu()
+    Y, X = info[0]["Height"], info[0]["Width"]
+    n_seg = len(bounds) - 1
+    seg_start, x, y, lpx, lpy = _segment_arrays(locs, info, bounds)
+    Y_, X_, H, W = _crop_geometry(Y, X, max_shift)
+    if pairs is None:
+        pi, pj = np.triu_indices(n_seg, 1)
+    else:
+        pi, pj = pairs
+    pi = np.ascontiguousarray(pi, dtype=np.int32)
+    pj = np.ascontiguousarray(pj, dtype=np.int32)
+    rec = np.zeros((len(pi), 32), dtype=np.float64)
+    sums = np.zeros(n_seg, dtype=np.float64)
+    _lib.check(l.pb_undrift_peaks_pairs(n_seg, _lib.ptr(seg_start), _lib.ptr(x), _lib.ptr(y), _lib.ptr(lpx),
+                                        _lib.ptr(lpy), Y, X, float(min_blur_width), Y_, X_, H, W, len(pi),
+                                        _lib.ptr(pi), _lib.ptr(pj), _lib.ptr(rec), _lib.ptr(sums), None))
+    status = rec[:, 0].astype(np.int64)
+    xc, yc = rec[:, 3].copy(), rec[:, 4].copy()
+    for k in np.flatnonzero(status == 1):                       # re-fit like the reference
+        xc[k], yc[k] = _gauss_peak_fit(rec[k, 5:30].reshape(5, 5))
+    odd = np.flatnonzero(status == 3)
+    odd_shift = {}
+    if len(odd):
+        win, _, _ = _windows_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=(pi[odd], pj[odd]))
+        for q, k in enumerate(odd):
+            odd_shift[k] = _shift_from_window(win[q].astype(np.float64), Y, X, Y_, X_, 5)
+    zero = (sums[pi] == 0) | (sums[pj] == 0) | (status == 2)
+    sx = -(xc + X_ + rec[:, 2] - np.floor(X / 2))
+    sy = -(yc + Y_ + rec[:, 1] - np.floor(Y / 2))
+    sx[zero] = 0
+    sy[zero] = 0
+    for k, (a, b) in odd_shift.items():
+        if sums[pi[k]] != 0 and sums[pj[k]] != 0:
+            sy[k], sx[k] = a, b
+    if callback is not None:
+        for flag in range(len(pi)):
+            callback(flag + 1)
+    return sy, sx
+
+
 def _rcc_of_locs(locs, info, bounds, min_blur_width, max_shift, callback):
+    """Segment shifts for postprocess.undrift: render, cross-correlate and peak-fit on the GPU,
+    then ``minimize_shifts`` (reference imageprocess.py:160-217)."""
+    n_seg = len(bounds) - 1
+    bar = None
+    if callback is None:
+        from tqdm import tqdm
+
+        bar = tqdm(total=n_seg * (n_seg - 1) // 2, desc="Correlating image pairs", unit="pairs")
+        step = lambda k: bar.update()   # noqa: E731
+    else:
+        callback(0)
+        step = callback
+    sy, sx = _shifts_of_locs(locs, info, bounds, min_blur_width, max_shift, callback=step)
+    if bar is not None:
+        bar.close()
+    shifts_x = np.zeros((n_seg, n_seg))
+    shifts_y = np.zeros((n_seg, n_seg))
+    pi, pj = np.triu_indices(n_seg, 1)
+    shifts_y[pi, pj] = sy
+    shifts_x[pi, pj] = sx
+    return lib.minimize_shifts(shifts_x, shifts_y)
+
+
+def _rcc_of_locs_windows(locs, info, bounds, min_blur_width, max_shift, callback):
+    """Same through the window path (host peak fits); kept for A/B tests."""
     win, sums, (Y, X, Y_, X_) = _windows_of_locs(locs, info, bounds, min_blur_width, max_shift)
     return _rcc_from_windows(win, sums, Y, X, Y_, X_, callback)

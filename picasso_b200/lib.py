@@ -27,9 +27,35 @@ def get_from_metadata(info, key: Any, default=None, *, raise_error: bool = False
 
 
 def minimize_shifts(shifts_x, shifts_y, shifts_z=None):
-    """Least-squares chain of pairwise shifts (RCC; reference lib.py:2034-2078):
-    solve ``A d = r`` with ``A[pair(i, j), i:j] = 1`` by pseudo-inverse and return the
-    cumulative shifts (leading 0) as ``(shift_y, shift_x[, shift_z])``."""
+    """Least-squares chain of pairwise shifts (RCC; reference lib.py:2034-2078): the reference
+    solves ``A d = r`` with ``A[pair(i, j), i:j] = 1`` by ``pinv`` of the (n(n-1)/2, n-1) matrix and
+    returns the cumulative shifts (leading 0) as ``(shift_y, shift_x[, shift_z])``.
+
+    ``A`` has full column rank, so ``pinv(A) r`` is the solution of the normal equations, and both
+    sides have closed forms: ``(A^T A)[k, l] = (min(k, l) + 1) (n - 1 - max(k, l))`` (pairs with
+    i <= min, j > max) and ``(A^T r)[k] = sum_{i <= k < j} r_ij`` (two prefix sums of the shift
+    matrix).  O(n^2) instead of the SVD of a 19 900 x 199 matrix at 200 segments (0.2-1 s);
+    agrees with the pinv formulation to 2e-14 (tests pin it to the reference at 1e-9)."""
+    n = shifts_x.shape[0]
+    stacks = [shifts_y, shifts_x] + ([shifts_z] if shifts_z is not None else [])
+    m = n - 1
+    if m < 1:
+        return tuple(np.zeros(max(n, 1))[:n] for _ in stacks)
+    k = np.arange(m)
+    gram = (np.minimum.outer(k, k) + 1.0) * (n - 1 - np.maximum.outer(k, k))
+    out = []
+    for sh in stacks:
+        upper = np.triu(np.asarray(sh, dtype=np.float64), 1)
+        below = np.cumsum(upper, axis=0)                          # sum over i <= k
+        right = np.cumsum(below[:, ::-1], axis=1)[:, ::-1]        # ... and over j' >= j
+        rhs = right[k, k + 1]
+        d = np.linalg.solve(gram, rhs)
+        out.append(np.insert(np.cumsum(d), 0, 0))
+    return tuple(out)
+
+
+def _minimize_shifts_pinv(shifts_x, shifts_y, shifts_z=None):
+    """The reference's literal formulation (lib.py:2034-2078), kept for the equivalence test."""
     n = shifts_x.shape[0]
     pairs = [(i, j) for i in range(n - 1) for j in range(i + 1, n)]
     stacks = [shifts_y, shifts_x] + ([shifts_z] if shifts_z is not None else [])
@@ -40,8 +66,7 @@ def minimize_shifts(shifts_x, shifts_y, shifts_z=None):
             rij[row, col] = sh[i, j]
         A[row, i:j] = 1
     Dj = np.dot(np.linalg.pinv(A), rij)
-    out = tuple(np.insert(np.cumsum(Dj[:, c]), 0, 0) for c in range(len(stacks)))
-    return out
+    return tuple(np.insert(np.cumsum(Dj[:, c]), 0, 0) for c in range(len(stacks)))
 
 
 def ensure_sanity(locs, info):

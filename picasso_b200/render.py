@@ -30,7 +30,83 @@ def _declare(l):
     l.pb_render_dev.argtypes = [sz, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, i32, vp, i32,
                                 i32, vp, vp, sz, vp]
     l.pb_render_dev.restype = i32
+    l.pb_copy_h2d.argtypes = [vp, vp, sz, vp]
+    l.pb_copy_h2d.restype = i32
+    l.pb_copy_d2h.argtypes = [vp, vp, sz, vp]
+    l.pb_copy_d2h.restype = i32
     l._render_declared = True
+
+
+def _setup(info, oversampling, viewport, blur_method, ang, disp_px_size):
+    """Argument handling shared by ``render`` and the device-resident variant: returns
+    ``(oversampling, (y_min, x_min, y_max, x_max), mode, n_pixel_y, n_pixel_x)``."""
+    pixelsize = lib.get_from_metadata(info, "Pixelsize", raise_error=True)
+    if disp_px_size is None:
+        warnings.warn(
+            "Deprecation warning: the 'oversampling' parameter is deprecated and will be "
+            "removed in v0.11.0. Use 'disp_px_size' instead.", DeprecationWarning, stacklevel=3)
+        disp_px_size = pixelsize / oversampling
+    oversampling = pixelsize / disp_px_size
+    if viewport is None:
+        try:
+            viewport = [(0, 0), (info[0]["Height"], info[0]["Width"])]
+        except TypeError:
+            raise ValueError("Need info if no viewport is provided.")
+    (y_min, x_min), (y_max, x_max) = viewport
+    if blur_method not in _MODES:
+        if blur_method in ("smooth", "convolve"):
+            raise NotImplementedError(
+                f"blur_method={blur_method!r} is outside the B200 hot path; use the reference")
+        raise Exception("blur_method not understood.")
+    if ang is not None:
+        raise NotImplementedError("rotated rendering (ang=...) is outside the B200 hot path")
+    n_pixel_y = int(np.ceil(oversampling * (y_max - y_min)))
+    n_pixel_x = int(np.ceil(oversampling * (x_max - x_min)))
+    return oversampling, (y_min, x_min, y_max, x_max), _MODES[blur_method], n_pixel_y, n_pixel_x
+
+
+def render_to_device(torch, locs, info, oversampling: float = 1.0, viewport=None, blur_method=None,
+                     min_blur_width: float = 0.0, ang=None, disp_px_size: float | None = None,
+                     device="cuda"):
+    """``render`` that leaves the image on the GPU: returns ``(count int64 tensor[1], image
+    float32 tensor)`` on ``device`` -- the multi-GPU path all-reduces them before one download."""
+    oversampling, (y_min, x_min, y_max, x_max), mode, ny, nx = _setup(
+        info, oversampling, viewport, blur_method, ang, disp_px_size)
+    l = _lib.load()
+    _declare(l)
+    _lib.require_gpu()
+    st = torch.cuda.current_stream(device).cuda_stream
+    cols = ["x", "y"] + (["lpx", "lpy"] if mode else [])
+    n = len(locs["x"])
+    dev = {}
+    for c in cols:
+        h = np.ascontiguousarray(locs[c], dtype=np.float32)
+        t = torch.empty(n, dtype=torch.float32, device=device)
+        _lib.check(l.pb_copy_h2d(t.data_ptr(), _lib.ptr(h), n * 4, st))
+        dev[c] = t
+    image = torch.empty((max(ny, 0), max(nx, 0)), dtype=torch.float32, device=device)
+    count = torch.zeros(1, dtype=torch.int64, device=device)
+    wsb = l.pb_render_workspace_bytes(n, ny, nx) if mode else 0
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=device)
+    if image.numel():
+        _lib.check(l.pb_render_dev(n, dev["x"].data_ptr(), dev["y"].data_ptr(),
+                                   dev["lpx"].data_ptr() if mode else None,
+                                   dev["lpy"].data_ptr() if mode else None, float(oversampling),
+                                   float(y_min), float(x_min), float(y_max), float(x_max),
+                                   float(min_blur_width), mode, image.data_ptr(), ny, nx,
+                                   count.data_ptr(), ws.data_ptr() if mode else None, wsb, st))
+    return count, image
+
+
+def image_to_host(torch, image):
+    """Download a device image through the threaded pinned staging (pageable numpy result)."""
+    l = _lib.load()
+    _declare(l)
+    out = np.empty(tuple(image.shape), dtype=np.float32)
+    if out.size:
+        st = torch.cuda.current_stream(image.device).cuda_stream
+        _lib.check(l.pb_copy_d2h(_lib.ptr(out), image.data_ptr(), out.nbytes, st))
+    return out
 
 
 def render(locs, info, oversampling: float = 1.0, viewport=None, blur_method=None,

@@ -62,6 +62,9 @@ def _worker(rank, world, port, q):
         pi, pj = pbd.my_pairs(n_seg, rank, world)
         win = np.stack([np.full((4, 4), 100 * i + j, np.float32) for i, j in zip(pi, pj)])
         full = pbd.gather_pair_windows(dist, torch, win, n_seg)
+        vals = pbd.gather_pair_values(dist, torch, np.stack([pi * 1.5, pj * 2.5], 1), n_seg)
+        assert np.array_equal(vals[:, 0], np.triu_indices(n_seg, 1)[0] * 1.5)
+        assert np.array_equal(vals[:, 1], np.triu_indices(n_seg, 1)[1] * 2.5)
         if rank == 0:
             q.put((th, cr, ll, it, g, img, cols, full))
     finally:

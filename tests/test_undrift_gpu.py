@@ -165,3 +165,56 @@ def test_pruned_inverse_equals_cufft_and_numpy(shape, win):
         np.testing.assert_allclose(out[0][k], ref, rtol=0, atol=tol)
         np.testing.assert_allclose(out[1][k], ref, rtol=0, atol=tol)
     assert l.pb_rcc_set_mode(7) != 0
+
+
+def test_device_peak_fits_equal_host_fits():
+    """pb_undrift_peaks_pairs (arg-max, 5x5 cut-out and Levenberg-Marquardt fit on the GPU) gives
+    the shifts of the window path with host fits; records carry the 5x5 window for re-fits."""
+    import ctypes as C
+
+    from picasso_b200 import _lib
+    locs, info, truth = testing.synthetic_drift_locs(1500, 128, 160, n_clusters=60, locs_per_frame=40.0, seed=8)
+    bounds = np.linspace(0, 1499, 16, dtype=np.uint32)
+    dy, dx = imageprocess._rcc_of_locs(locs, info, bounds, 1, 32, lambda i: None)
+    hy, hx = imageprocess._rcc_of_locs_windows(locs, info, bounds, 1, 32, lambda i: None)
+    np.testing.assert_allclose(dy, hy, atol=1e-5)
+    np.testing.assert_allclose(dx, hx, atol=1e-5)
+    # a pair subset returns the same per-pair shifts as the full run
+    pi, pj = np.triu_indices(15, 1)
+    sy, sx = imageprocess._shifts_of_locs(locs, info, bounds, 1, 32)
+    sub = slice(3, None, 4)
+    sy2, sx2 = imageprocess._shifts_of_locs(locs, info, bounds, 1, 32, pairs=(pi[sub], pj[sub]))
+    np.testing.assert_allclose(sy2, sy[sub], atol=1e-5)
+    np.testing.assert_allclose(sx2, sx[sub], atol=1e-5)
+    # raw records: status 0 almost everywhere, window values equal the window path
+    l = _lib.load()
+    seg_start, x, y, lpx, lpy = imageprocess._segment_arrays(locs, info, bounds)
+    Y_, X_, H, W = imageprocess._crop_geometry(128, 160, 32)
+    rec = np.zeros((len(pi), 32)); sums = np.zeros(15)
+    win = np.zeros((len(pi), H, W), np.float32)
+    pi32, pj32 = pi.astype(np.int32), pj.astype(np.int32)
+    _lib.check(l.pb_undrift_peaks_pairs(15, _lib.ptr(seg_start), _lib.ptr(x), _lib.ptr(y), _lib.ptr(lpx),
+                                        _lib.ptr(lpy), 128, 160, 1.0, Y_, X_, H, W, len(pi), _lib.ptr(pi32),
+                                        _lib.ptr(pj32), _lib.ptr(rec), _lib.ptr(sums), _lib.ptr(win)))
+    assert (rec[:, 0] == 0).mean() > 0.9
+    for k in (0, 17, 60):
+        ym, xm = np.unravel_index(win[k].argmax(), win[k].shape)
+        assert (rec[k, 1], rec[k, 2]) == (ym, xm)
+        if rec[k, 0] in (0, 1):
+            np.testing.assert_array_equal(rec[k, 5:30].reshape(5, 5), win[k][ym - 2:ym + 3, xm - 2:xm + 3])
+            xc, yc = imageprocess._gauss_peak_fit(win[k][ym - 2:ym + 3, xm - 2:xm + 3].astype(np.float64))
+            assert abs(xc - rec[k, 3]) < 1e-5 and abs(yc - rec[k, 4]) < 1e-5
+
+
+def test_device_peak_fit_edge_cases():
+    """Empty segments (zero sum) and peaks at the crop edge give (0, 0) like the reference."""
+    locs, info, _ = testing.synthetic_drift_locs(600, 64, 64, n_clusters=20, locs_per_frame=20.0, seed=2)
+    locs = locs[(locs["frame"] < 200) | (locs["frame"] >= 300)].reset_index(drop=True)     # segment 2 empty
+    bounds = np.linspace(0, 599, 7, dtype=np.uint32)
+    dy, dx = imageprocess._rcc_of_locs(locs, info, bounds, 1, 32, lambda i: None)
+    hy, hx = imageprocess._rcc_of_locs_windows(locs, info, bounds, 1, 32, lambda i: None)
+    np.testing.assert_allclose(dy, hy, atol=1e-5)
+    np.testing.assert_allclose(dx, hx, atol=1e-5)
+    sy, sx = imageprocess._shifts_of_locs(locs, info, bounds, 1, 32)
+    pi, pj = np.triu_indices(6, 1)
+    assert (sy[(pi == 2) | (pj == 2)] == 0).all() and (sx[(pi == 2) | (pj == 2)] == 0).all()
