@@ -209,8 +209,8 @@ def test_device_peak_fits_equal_host_fits():
 def test_device_peak_fit_edge_cases():
     """Empty segments (zero sum) and peaks at the crop edge give (0, 0) like the reference."""
     locs, info, _ = testing.synthetic_drift_locs(600, 64, 64, n_clusters=20, locs_per_frame=20.0, seed=2)
-    locs = locs[(locs["frame"] < 200) | (locs["frame"] >= 300)].reset_index(drop=True)     # segment 2 empty
-    bounds = np.linspace(0, 599, 7, dtype=np.uint32)
+    bounds = np.linspace(0, 599, 7, dtype=np.uint32)                      # [0, 99, 199, 299, ...]
+    locs = locs[(locs["frame"] < 199) | (locs["frame"] >= 299)].reset_index(drop=True)     # segment 2 empty
     dy, dx = imageprocess._rcc_of_locs(locs, info, bounds, 1, 32, lambda i: None)
     hy, hx = imageprocess._rcc_of_locs_windows(locs, info, bounds, 1, 32, lambda i: None)
     np.testing.assert_allclose(dy, hy, atol=1e-5)
