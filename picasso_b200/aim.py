@@ -119,8 +119,11 @@ def _segments_in_frame_order(frame, seg_bounds):
     """Stable frame order and, per segment s, the range of sorted positions with
     seg_bounds[s] < frame <= seg_bounds[s + 1] (the reference's boolean masks)."""
     f = np.asarray(frame)
-    order = np.argsort(f, kind="stable")
-    fs = f[order]
+    if len(f) < 2 or bool(np.all(f[1:] >= f[:-1])):
+        order, fs = slice(None), f            # already in frame order (the normal case): no gather
+    else:
+        order = np.argsort(f, kind="stable")
+        fs = f[order]
     start = np.searchsorted(fs, seg_bounds[:-1], side="right")
     end = np.searchsorted(fs, seg_bounds[1:], side="right")
     return order, start, end

@@ -325,14 +325,20 @@ def _segment_arrays(locs, info, bounds):
     """Localization columns grouped by segment (stable), the way pb_undrift_* expects them."""
     n_seg = len(bounds) - 1
     frames = locs["frame"].to_numpy()
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)   # noqa: E731
+    if len(frames) < 2 or bool(np.all(frames[1:] >= frames[:-1])):
+        # frames already in order (the normal case): segments are contiguous slices
+        cut = np.searchsorted(frames, np.asarray(bounds), side="left")
+        a, b = int(cut[0]), int(cut[-1])
+        seg_start = (cut - cut[0]).astype(np.int64)
+        return (seg_start,) + tuple(f32(locs[c].to_numpy()[a:b]) for c in ("x", "y", "lpx", "lpy"))
     seg_of = np.searchsorted(bounds, frames, side="right") - 1
     keep = (frames >= bounds[0]) & (frames < bounds[-1])
     idx = np.flatnonzero(keep)
     idx = idx[np.argsort(seg_of[idx], kind="stable")]
     counts = np.bincount(seg_of[idx], minlength=n_seg)[:n_seg]
     seg_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    take = lambda c: np.ascontiguousarray(locs[c].to_numpy()[idx], dtype=np.float32)   # noqa: E731
-    return seg_start, take("x"), take("y"), take("lpx"), take("lpy")
+    return (seg_start,) + tuple(f32(locs[c].to_numpy()[idx]) for c in ("x", "y", "lpx", "lpy"))
 
 
 def _shifts_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=None, callback=None):

@@ -49,10 +49,12 @@ def test_segment_ranges_equal_reference_masks():
     rng = np.random.default_rng(0)
     frame = rng.integers(1, 501, 3000)
     bounds = np.concatenate((np.arange(0, 500, 70), [500]))
-    order, start, end = aim._segments_in_frame_order(frame, bounds)
-    for s in range(len(bounds) - 1):
-        mask = (frame > bounds[s]) & (frame <= bounds[s + 1])
-        assert sorted(order[start[s]:end[s]]) == list(np.flatnonzero(mask))
+    for fr in (frame, np.sort(frame)):                      # unsorted: argsort path; sorted: slice path
+        order, start, end = aim._segments_in_frame_order(fr, bounds)
+        idx = np.arange(len(fr))[order]
+        for s in range(len(bounds) - 1):
+            mask = (fr > bounds[s]) & (fr <= bounds[s + 1])
+            assert sorted(idx[start[s]:end[s]]) == list(np.flatnonzero(mask))
 
 
 def test_fft_peaks():

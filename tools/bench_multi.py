@@ -36,14 +36,28 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    def timed(fn):
-        dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        r = fn()
-        torch.cuda.synchronize(); dist.barrier()
-        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return r, float(t.item())
+    def timed(fn, reps=3):
+        """Best of `reps` (the first full-size call grows the cached pinned / device buffers and
+        sets up NCCL channels for the message size); max over ranks of each repeat."""
+        best = None
+        for _ in range(reps):
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize(); dist.barrier()
+            t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item()) if best is None else min(best, float(t.item()))
+        return r, best
+
+    def timed_one(fn, reps=3):
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return r, best
 
     out = {"world": world}
     cam = {"Baseline": 100, "Sensitivity": 1.0, "Gain": 1, "Pixelsize": 130}
@@ -56,9 +70,8 @@ def main():
                                                     fitting_method="gaussmle", device=dev))
     res = {"frames": F, "sharded_seconds": t_sh, "n_locs": len(locs)}
     if rank == 0:
-        t0 = time.perf_counter()
-        one = localize.localize(movie, dict(cam), par, fitting_method="gaussmle", return_info=False)
-        res["one_gpu_seconds"] = time.perf_counter() - t0
+        one, res["one_gpu_seconds"] = timed_one(lambda: localize.localize(
+            movie, dict(cam), par, fitting_method="gaussmle", return_info=False))
         res["tables_bit_identical"] = all(locs[c].to_numpy().tobytes() == one[c].to_numpy().tobytes()
                                           for c in one.columns) and len(one) == len(locs)
     out["localize"] = res
@@ -75,9 +88,7 @@ def main():
     (k, img), t_sh = timed(lambda: pbd.render_sharded(dist, torch, rl, info, device=dev, **kw))
     res = {"n_locs": n, "sharded_seconds": t_sh, "n_in_view": k}
     if rank == 0:
-        t0 = time.perf_counter()
-        k1, img1 = render.render(rl, info, **kw)
-        res["one_gpu_seconds"] = time.perf_counter() - t0
+        (k1, img1), res["one_gpu_seconds"] = timed_one(lambda: render.render(rl, info, **kw))
         big = img1 > 1e-3 * img1.max()
         res["n_equal"] = bool(k1 == k)
         res["max_rel_dev_bright_pixels"] = float(np.max(np.abs(img[big] - img1[big]) / img1[big]))
@@ -90,10 +101,8 @@ def main():
     (drift, und), t_sh = timed(lambda: pbd.undrift_sharded(dist, torch, dl, dinfo, 100, device=dev))
     res = {"n_locs": len(dl), "segments": nf // 100, "image": [side, side], "sharded_seconds": t_sh}
     if rank == 0:
-        t0 = time.perf_counter()
-        d1, u1 = postprocess.undrift(dl, dinfo, 100, display=False, segmentation_callback=lambda i: None,
-                                     rcc_callback=lambda i: None)
-        res["one_gpu_seconds"] = time.perf_counter() - t0
+        (d1, u1), res["one_gpu_seconds"] = timed_one(lambda: postprocess.undrift(
+            dl, dinfo, 100, display=False, segmentation_callback=lambda i: None, rcc_callback=lambda i: None))
         res["drift_bit_identical"] = bool(d1["x"].to_numpy().tobytes() == drift["x"].to_numpy().tobytes()
                                           and d1["y"].to_numpy().tobytes() == drift["y"].to_numpy().tobytes())
         res["max_abs_drift_dev"] = float(max(np.abs(d1["x"] - drift["x"]).max(), np.abs(d1["y"] - drift["y"]).max()))
