@@ -250,6 +250,22 @@ int pb_aim_set_reference(void* handle, size_t n_ref, const void* rx, int rx_f64,
 int pb_aim_count(void* handle, size_t first, size_t count, double rel_x, double rel_y, double rel_z,
                  int n_shifts, const double* shifts, int* roi_cc);
 
+/* ---- linking localizations into binding events -------------------------------------
+ * Replaces the numba loops behind picasso.postprocess.link (picasso/postprocess.py:2007-2072):
+ * pb_link_groups = _get_link_groups :2440-2507 (+ _get_next_loc_index_in_link_group :2510-2552):
+ *   frame (sorted ascending, int64), x / y (float32, or float64 when xy_f64), group int32,
+ *   d_max, max_dark_time -> link_group int32[n] (0 .. n_groups-1 in the reference's order of
+ *   chain starts) and *n_groups.  Bit-exact with the sequential reference.
+ * pb_link_reduce = _link_group_sum / _link_group_min_max / _link_group_last :2567-2661 for
+ *   several columns at once: per group, in localization order, in the column's dtype
+ *   (dtype 0 f32, 1 f64, 2 u32, 3 i32; op 0 sum, 1 min, 2 max, 3 last); outs[k] has n_groups
+ *   elements of the column's dtype.  link_group must use every value 0 .. n_groups-1. */
+int pb_link_groups(size_t n, const long long* frame, const void* x, const void* y, int xy_f64,
+                   const int* group, double d_max, long long max_dark_time, int* link_group,
+                   int* n_groups);
+int pb_link_reduce(size_t n, const int* link_group, int n_groups, int n_cols,
+                   const void* const* cols, const int* dtypes, const int* ops, void* const* outs);
+
 /* ---- rendering ----------------------------------------------------------------
  * Replaces the unrotated paths of picasso.render.render (picasso/render.py:37-174):
  * _render_hist (:798-853, mode 0), _render_gaussian (:1020-1112, mode 1) and

@@ -118,3 +118,186 @@ def undrift(locs: pd.DataFrame, info, segmentation: int, display: bool = True,
     drift = pd.DataFrame({"x": drift_x_pol(t_inter), "y": drift_y_pol(t_inter)})
     locs = apply_drift(locs, info, drift=drift)
     return drift, locs
+
+
+# ---- linking (reference postprocess.py:2007-2821) ------------------------------------------
+_LINK_DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.uint32): 2,
+                np.dtype(np.int32): 3}
+
+
+def _declare_link(l):
+    if getattr(l, "_link_declared", False):
+        return
+    import ctypes as C
+
+    vp, i32 = C.c_void_p, C.c_int
+    l.pb_link_groups.argtypes = [C.c_size_t, vp, vp, vp, i32, vp, C.c_double, C.c_longlong, vp, C.POINTER(i32)]
+    l.pb_link_groups.restype = i32
+    l.pb_link_reduce.argtypes = [C.c_size_t, vp, i32, i32, vp, vp, vp, vp]
+    l.pb_link_reduce.restype = i32
+    l._link_declared = True
+
+
+def _get_link_groups(frame, x, y, d_max: float, max_dark_time: int, group):
+    """Link group of every localization (reference ``_get_link_groups``, postprocess.py:2440-2507);
+    ``frame`` must be sorted ascending.  Runs on the GPU (csrc/link.cu), bit-exact."""
+    import ctypes as C
+
+    from . import _lib
+
+    l = _lib.load()
+    _declare_link(l)
+    _lib.require_gpu()
+    frame = np.ascontiguousarray(frame, dtype=np.int64)
+    x = np.asarray(x)
+    f64 = int(x.dtype == np.float64 or np.asarray(y).dtype == np.float64)
+    dt = np.float64 if f64 else np.float32
+    x = np.ascontiguousarray(x, dtype=dt)
+    y = np.ascontiguousarray(y, dtype=dt)
+    group = np.ascontiguousarray(group, dtype=np.int32)
+    link_group = np.empty(len(frame), np.int32)
+    n_groups = C.c_int(0)
+    _lib.check(l.pb_link_groups(len(frame), _lib.ptr(frame), _lib.ptr(x), _lib.ptr(y), f64, _lib.ptr(group),
+                                float(d_max), int(max_dark_time), _lib.ptr(link_group), C.byref(n_groups)))
+    return link_group
+
+
+get_link_groups = _get_link_groups
+
+
+def _group_reduce(link_group, n_groups, columns, ops):
+    """Per-group reductions of several columns in one GPU pass (``pb_link_reduce``)."""
+    import ctypes as C
+
+    from . import _lib
+
+    l = _lib.load()
+    _declare_link(l)
+    cols, orig = [], []
+    for c in columns:
+        c = np.ascontiguousarray(c)
+        orig.append(c.dtype)
+        if c.dtype not in _LINK_DTYPES:       # e.g. int64 frames / groups: values fit 32 bits
+            c = c.astype(np.float64 if c.dtype.kind == "f" else (np.uint32 if c.dtype.kind == "u" else np.int32))
+        cols.append(c)
+    outs = [np.zeros(n_groups, dtype=c.dtype) for c in cols]
+    k = len(cols)
+    if k and n_groups:
+        VP = C.c_void_p * k
+        I = C.c_int * k
+        _lib.check(l.pb_link_reduce(len(link_group), _lib.ptr(link_group), int(n_groups), k,
+                                    VP(*[c.ctypes.data for c in cols]), I(*[_LINK_DTYPES[c.dtype] for c in cols]),
+                                    I(*ops), VP(*[o.ctypes.data for o in outs])))
+    return [o if o.dtype == d else o.astype(d) for o, d in zip(outs, orig)]
+
+
+def _link_loc_groups(locs: pd.DataFrame, info, link_group, remove_ambiguous_lengths: bool = True):
+    """Combine linked localizations into binding events (reference ``_link_loc_groups``,
+    postprocess.py:2680-2821): weighted mean position, summed photons / bg, mean widths, ``len``,
+    ``n``, ``photon_rate``.  The per-group accumulations run on the GPU in the reference's order
+    and dtypes; the elementwise steps are the reference's numpy expressions."""
+    from collections import OrderedDict
+
+    link_group = np.ascontiguousarray(link_group, dtype=np.int32)
+    n_groups = int(link_group.max()) + 1
+    SUM, MIN, MAX, LAST = 0, 1, 2, 3
+    jobs = OrderedDict()          # name -> (column, op)
+    jobs["n"] = (np.ones(len(link_group), np.uint32), SUM)
+    has = lambda c: c in locs.columns   # noqa: E731
+    col = lambda c: locs[c].to_numpy()  # noqa: E731
+    if has("frame"):
+        jobs["first"] = (col("frame"), MIN)
+        jobs["last"] = (col("frame"), MAX)
+    weights = {}
+    for c, lp in (("x", "lpx"), ("y", "lpy")):
+        if has(c):
+            weights[c] = 1 / col(lp) ** 2
+            jobs["w_" + c] = (weights[c], SUM)
+            jobs["wsum_" + c] = (col(c) * weights[c], SUM)
+    if has("z") and has("lpz"):
+        weights["z"] = 1 / col("lpz") ** 2
+        jobs["w_z"] = (weights["z"], SUM)
+        jobs["wsum_z"] = (col("z") * weights["z"], SUM)
+    plain_sum = [c for c in ("photons", "bg") if has(c)]
+    plain_mean = [c for c in ("sx", "sy", "ellipticity", "net_gradient", "likelihood", "iterations", "d_zcalib")
+                  if has(c)]
+    if has("z") and not has("lpz"):
+        plain_mean.append("z")
+    for c in plain_sum + plain_mean:
+        jobs["sum_" + c] = (col(c), SUM)
+    if has("group"):
+        jobs["group"] = (col("group"), LAST)
+    res = dict(zip(jobs, _group_reduce(link_group, n_groups, [v[0] for v in jobs.values()],
+                                       [v[1] for v in jobs.values()])))
+    n_ = res["n"]
+
+    def f32_div(a, b):
+        out = np.empty(n_groups, dtype=np.float32)      # "this ensures float32 after the division"
+        out[:] = a / b
+        return out
+
+    columns = OrderedDict()
+    if has("frame"):
+        columns["frame"] = res["first"]
+    for c in ("x", "y"):
+        if has(c):
+            columns[c] = f32_div(res["wsum_" + c], res["w_" + c])
+    if has("photons"):
+        columns["photons"] = res["sum_photons"]
+    for c in ("sx", "sy"):
+        if has(c):
+            columns[c] = f32_div(res["sum_" + c], n_)
+    if has("bg"):
+        columns["bg"] = res["sum_bg"]
+    if has("x"):
+        columns["lpx"] = np.sqrt(1 / res["w_x"])
+    if has("y"):
+        columns["lpy"] = np.sqrt(1 / res["w_y"])
+    for c in ("ellipticity", "net_gradient", "likelihood", "iterations"):
+        if has(c):
+            columns[c] = f32_div(res["sum_" + c], n_)
+    if has("z"):
+        if has("lpz"):
+            columns["z"] = f32_div(res["wsum_z"], res["w_z"])
+            columns["lpz"] = np.sqrt(1 / res["w_z"])
+        else:
+            columns["z"] = f32_div(res["sum_z"], n_)
+    if has("d_zcalib"):
+        columns["d_zcalib"] = f32_div(res["sum_d_zcalib"], n_)
+    if has("group"):
+        columns["group"] = res["group"]
+    if has("frame"):
+        columns["len"] = res["last"] - res["first"] + 1
+    columns["n"] = n_
+    if has("photons"):
+        columns["photon_rate"] = np.float32(columns["photons"] / n_)
+    linked_locs = pd.DataFrame(columns)
+    if remove_ambiguous_lengths:
+        valid = np.logical_and(res["first"] > 0, res["last"] < info[0]["Frames"])
+        linked_locs = linked_locs[valid]
+    return linked_locs
+
+
+link_loc_groups = _link_loc_groups
+
+
+def link(locs: pd.DataFrame, info, r_max: float = 0.05, max_dark_time: int = 3,
+         combine_mode: str = "average", remove_ambiguous_lengths: bool = True) -> pd.DataFrame:
+    """Link localizations into binding events (reference ``link``, postprocess.py:2007-2072)."""
+    if len(locs) == 0:
+        linked_locs = locs.copy()
+        if "frame" in locs.columns:
+            linked_locs["len"] = np.array([], dtype=np.int32)
+            linked_locs["n"] = np.array([], dtype=np.int32)
+        if "photons" in locs.columns:
+            linked_locs["photon_rate"] = np.array([], dtype=np.float32)
+        return linked_locs
+    locs = locs.sort_values(kind="quicksort", by="frame")
+    group = locs["group"].to_numpy() if "group" in locs.columns else np.zeros(len(locs), dtype=np.int32)
+    link_group = _get_link_groups(locs["frame"].to_numpy(), locs["x"].to_numpy(), locs["y"].to_numpy(),
+                                  r_max, max_dark_time, group)
+    if combine_mode == "average":
+        return _link_loc_groups(locs, info, link_group, remove_ambiguous_lengths=remove_ambiguous_lengths)
+    if combine_mode == "refit":
+        raise NotImplementedError("Refit mode is not implemented yet. Please use 'average' mode.")
+    return None

@@ -164,3 +164,81 @@ def synthetic_aim_locs(n_frames: int = 2000, Y: int = 64, X: int = 64, n_cluster
         dz = 40.0 * np.sin(2 * np.pi * t / n_frames)
         locs["z"] = (cz[which] + dz + rng.normal(0, 8.0, n)).astype(np.float32)
     return locs, info, drift
+
+
+def synthetic_link_locs(n_frames: int = 600, n_sites: int = 150, side: int = 64, seed: int = 5,
+                        with_group: bool = False, f64_xy: bool = False):
+    """Blinking binding sites (on-times ~6 frames, dark gaps inside an event up to 2 frames, sites
+    >= 0.5 px apart) for postprocess.link: frame-sorted DataFrame + info."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    sites = []
+    while len(sites) < n_sites:
+        p = rng.uniform(3, side - 3, 2)
+        if all((p[0] - q[0]) ** 2 + (p[1] - q[1]) ** 2 > 0.25 for q in sites):
+            sites.append(p)
+    rows = []
+    for k, (sx_, sy_) in enumerate(sites):
+        t = int(rng.integers(0, 40))
+        while t < n_frames:
+            length = 1 + int(rng.geometric(1 / 6.0))
+            for f in range(t, min(t + length, n_frames)):
+                if rng.random() < 0.85:                                # missed frames inside an event
+                    rows.append((f, sx_ + rng.normal(0, 0.012), sy_ + rng.normal(0, 0.012), k))
+            t += length + int(rng.integers(8, 120))
+    rows.sort(key=lambda r: r[0])
+    a = np.array(rows)
+    n = len(a)
+    xy = np.float64 if f64_xy else np.float32
+    locs = pd.DataFrame({
+        "frame": a[:, 0].astype(np.uint32), "x": a[:, 1].astype(xy), "y": a[:, 2].astype(xy),
+        "photons": rng.uniform(500, 5000, n).astype(np.float32), "sx": rng.uniform(0.9, 1.3, n).astype(np.float32),
+        "sy": rng.uniform(0.9, 1.3, n).astype(np.float32), "bg": rng.uniform(5, 30, n).astype(np.float32),
+        "lpx": rng.uniform(0.008, 0.02, n).astype(np.float32), "lpy": rng.uniform(0.008, 0.02, n).astype(np.float32),
+        "ellipticity": rng.uniform(0, 0.2, n).astype(np.float32),
+        "net_gradient": rng.uniform(5000, 20000, n).astype(np.float32),
+    })
+    if with_group:
+        locs["group"] = (a[:, 3].astype(np.int32) % 7)
+    info = [{"Height": side, "Width": side, "Frames": n_frames, "Pixelsize": 130}]
+    return locs, info
+
+
+def synthetic_link_locs_fast(n_frames: int, n_sites: int, side: float, seed: int = 3):
+    """Vectorised variant of ``synthetic_link_locs`` for large benchmarks: sites on a jittered grid
+    (>= 0.5 px apart), geometric on-times (mean 6 frames), 15 % missed frames."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    k = int(np.ceil(np.sqrt(n_sites)))
+    pitch = side / k
+    assert pitch >= 0.7, "sites would be closer than 0.5 px"
+    gy, gx = np.divmod(np.arange(n_sites), k)
+    sx = (gx + 0.5) * pitch + rng.uniform(-0.1, 0.1, n_sites)
+    sy = (gy + 0.5) * pitch + rng.uniform(-0.1, 0.1, n_sites)
+    n_ev = max(1, n_frames // 50)
+    on = rng.geometric(1 / 6.0, (n_sites, n_ev))
+    off = rng.integers(8, 90, (n_sites, n_ev))
+    start = np.cumsum(on + off, axis=1) - on - rng.integers(0, 8, (n_sites, 1))
+    site = np.repeat(np.arange(n_sites), n_ev)
+    start, on = start.ravel(), on.ravel()
+    reps = np.repeat(np.arange(len(on)), on)
+    within = np.arange(on.sum()) - np.repeat(np.cumsum(on) - on, on)
+    frame = start[reps] + within
+    s = site[reps]
+    keep = (frame >= 0) & (frame < n_frames) & (rng.random(len(frame)) < 0.85)
+    frame, s = frame[keep], s[keep]
+    order = np.argsort(frame, kind="stable")
+    frame, s = frame[order], s[order]
+    n = len(frame)
+    f32 = np.float32
+    locs = pd.DataFrame({
+        "frame": frame.astype(np.uint32), "x": (sx[s] + rng.normal(0, 0.012, n)).astype(f32),
+        "y": (sy[s] + rng.normal(0, 0.012, n)).astype(f32), "photons": rng.uniform(500, 5000, n).astype(f32),
+        "sx": rng.uniform(0.9, 1.3, n).astype(f32), "sy": rng.uniform(0.9, 1.3, n).astype(f32),
+        "bg": rng.uniform(5, 30, n).astype(f32), "lpx": rng.uniform(0.008, 0.02, n).astype(f32),
+        "lpy": rng.uniform(0.008, 0.02, n).astype(f32), "ellipticity": rng.uniform(0, 0.2, n).astype(f32),
+        "net_gradient": rng.uniform(5000, 20000, n).astype(f32),
+    })
+    return locs, [{"Height": int(side), "Width": int(side), "Frames": n_frames, "Pixelsize": 130}]

@@ -281,6 +281,34 @@ def stage_aim(torch, small):
                       "drift_bit_identical_to_oracle_on_sample": bool(same)}), flush=True)
 
 
+def stage_link(torch, small):
+    """postprocess.link: blinking binding sites, GPU link groups + combined
+    table through the Python API; the C oracle (the reference's sequential greedy) beside it."""
+    from picasso_b200 import postprocess, testing
+
+    nf, sites, side = (2000, 2000, 256) if small else (10000, 5000, 512)
+    locs, info = testing.synthetic_link_locs_fast(nf, sites, side, seed=3)
+    postprocess.link(locs.iloc[:20000], info)
+    t0 = time.perf_counter()
+    linked = postprocess.link(locs, info)
+    t_gpu = time.perf_counter() - t0
+    sl = locs.sort_values(kind="quicksort", by="frame")
+    fr, x, y = sl["frame"].to_numpy(), sl["x"].to_numpy(), sl["y"].to_numpy()
+    grp = np.zeros(len(sl), np.int32)
+    t0 = time.perf_counter()
+    lg = postprocess.get_link_groups(fr, x, y, 0.05, 3, grp)
+    t_lg = time.perf_counter() - t0
+    import oracle
+    oracle.build()
+    t0 = time.perf_counter()
+    olg = oracle.get_link_groups(fr, x, y, 0.05, 3, grp)
+    t_cpu = time.perf_counter() - t0
+    print(json.dumps({"stage": "link (8f rank 4)", "n_locs": len(locs), "frames": nf, "locs_per_frame": len(locs) / nf,
+                      "n_events": len(linked), "link_seconds_python_api": t_gpu, "locs_per_s": len(locs) / t_gpu,
+                      "get_link_groups_seconds": t_lg, "cpu_oracle_get_link_groups_seconds_1thread": t_cpu,
+                      "link_groups_bit_identical_to_oracle": bool(np.array_equal(lg, olg))}), flush=True)
+
+
 def stage_render(torch, small):
     from picasso_b200 import _lib, render as pbrender
 
@@ -478,5 +506,5 @@ if __name__ == "__main__":
     small = "--small" in sys.argv
     which = args or ["identify", "render", "rcc"]
     for w in which:
-        {"identify": stage_identify, "localize": stage_localize, "zfit": stage_zfit, "aim": stage_aim, "render": stage_render, "rcc": stage_rcc,
+        {"identify": stage_identify, "localize": stage_localize, "zfit": stage_zfit, "aim": stage_aim, "link": stage_link, "render": stage_render, "rcc": stage_rcc,
          "undrift": stage_undrift}[w](torch, small)

@@ -339,7 +339,29 @@ def gen_aim(ref):
     save("aim.npz", **out)
 
 
-GENERATORS = {"aim": gen_aim, "zfit": gen_zfit, "mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift}
+def gen_link(ref):
+    """postprocess.link (average mode) and the raw link groups on blinking-site data."""
+    from picasso_b200 import testing
+
+    post = ref["postprocess"]
+    out = {}
+    for tag, kw in (("plain", {}), ("group", {"with_group": True}), ("f64", {"f64_xy": True, "seed": 8})):
+        locs, info = testing.synthetic_link_locs(**kw)
+        sl = locs.sort_values(kind="quicksort", by="frame")
+        group = sl["group"].to_numpy() if "group" in sl.columns else np.zeros(len(sl), dtype=np.int32)
+        for dark in (3, 1):
+            lg = post._get_link_groups(sl["frame"].to_numpy(), sl["x"].to_numpy(), sl["y"].to_numpy(), 0.05, dark, group)
+            out[f"{tag}_lg_dark{dark}"] = lg
+        out[f"{tag}_sorted_index"] = sl.index.to_numpy()
+        linked = post.link(locs, info, r_max=0.05, max_dark_time=3)
+        out[f"{tag}_linked_index"] = linked.index.to_numpy()
+        for c in linked.columns:
+            out[f"{tag}_linked_{c}"] = linked[c].to_numpy()
+        print(tag, len(locs), "->", len(linked), {c: str(linked[c].dtype) for c in linked.columns})
+    save("link.npz", **out)
+
+
+GENERATORS = {"link": gen_link, "aim": gen_aim, "zfit": gen_zfit, "mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift}
 
 
 def main():
