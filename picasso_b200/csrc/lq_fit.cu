@@ -42,7 +42,7 @@ constexpr double kDwarf = 2.2250738585072014e-308;
 __device__ __forceinline__ double sq(double v) { return v * v; }
 
 // MINPACK enorm (three accumulators guard against under/overflow)
-__device__ double lq_enorm(int n, const double* x) {
+__device__ __noinline__ double lq_enorm(int n, const double* x) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
     const double agiant = rgiant / (double)n;
@@ -142,17 +142,22 @@ __device__ void lq_qrfac(double* a /*M x 6 col-major*/, int* ipvt, double* rdiag
 
 __device__ void lq_qrsolv(double* r, int ldr, const int* ipvt, const double* diag,
                           const double* qtb, double* x, double* sdiag, double* wa) {
+#pragma unroll 1
     for (int j = 0; j < kN; j++) {
+#pragma unroll 1
         for (int i = j; i < kN; i++) r[i + ldr * j] = r[j + ldr * i];
         x[j] = r[j + ldr * j];
         wa[j] = qtb[j];
     }
+#pragma unroll 1
     for (int j = 0; j < kN; j++) {
         const int l = ipvt[j];
         if (diag[l] != 0.0) {
+#pragma unroll 1
             for (int k = j; k < kN; k++) sdiag[k] = 0.0;
             sdiag[j] = diag[l];
             double qtbpj = 0.0;
+#pragma unroll 1
             for (int k = j; k < kN; k++) {
                 if (sdiag[k] == 0.0) continue;
                 double cs, sn;
@@ -169,6 +174,7 @@ __device__ void lq_qrsolv(double* r, int ldr, const int* ipvt, const double* dia
                 double temp = cs * wa[k] + sn * qtbpj;
                 qtbpj = -sn * wa[k] + cs * qtbpj;
                 wa[k] = temp;
+#pragma unroll 1
                 for (int i = k + 1; i < kN; i++) {
                     temp = cs * r[i + ldr * k] + sn * sdiag[i];
                     sdiag[i] = -sn * r[i + ldr * k] + cs * sdiag[i];
@@ -180,15 +186,19 @@ __device__ void lq_qrsolv(double* r, int ldr, const int* ipvt, const double* dia
         r[j + ldr * j] = x[j];
     }
     int nsing = kN;
+#pragma unroll 1
     for (int j = 0; j < kN; j++) {
         if (sdiag[j] == 0.0 && nsing == kN) nsing = j;
         if (nsing < kN) wa[j] = 0.0;
     }
+#pragma unroll 1
     for (int j = nsing - 1; j >= 0; j--) {
         double sum = 0.0;
+#pragma unroll 1
         for (int i = j + 1; i < nsing; i++) sum += r[i + ldr * j] * wa[i];
         wa[j] = (wa[j] - sum) / sdiag[j];
     }
+#pragma unroll 1
     for (int j = 0; j < kN; j++) x[ipvt[j]] = wa[j];
 }
 
@@ -196,35 +206,45 @@ __device__ void lq_lmpar(double* r, int ldr, const int* ipvt, const double* diag
                          const double* qtb, double delta, double& par, double* x, double* sdiag,
                          double* wa1, double* wa2) {
     int nsing = kN;
+#pragma unroll 1
     for (int j = 0; j < kN; j++) {
         wa1[j] = qtb[j];
         if (r[j + ldr * j] == 0.0 && nsing == kN) nsing = j;
         if (nsing < kN) wa1[j] = 0.0;
     }
+#pragma unroll 1
     for (int j = nsing - 1; j >= 0; j--) {
         wa1[j] /= r[j + ldr * j];
         const double temp = wa1[j];
+#pragma unroll 1
         for (int i = 0; i < j; i++) wa1[i] -= r[i + ldr * j] * temp;
     }
+#pragma unroll 1
     for (int j = 0; j < kN; j++) x[ipvt[j]] = wa1[j];
     int iter = 0;
+#pragma unroll 1
     for (int j = 0; j < kN; j++) wa2[j] = diag[j] * x[j];
     double dxnorm = lq_enorm(kN, wa2);
     double fp = dxnorm - delta;
     if (fp <= 0.1 * delta) { par = 0.0; return; }
     double parl = 0.0;
     if (nsing >= kN) {
+#pragma unroll 1
         for (int j = 0; j < kN; j++) { const int l = ipvt[j]; wa1[j] = diag[l] * (wa2[l] / dxnorm); }
+#pragma unroll 1
         for (int j = 0; j < kN; j++) {
             double sum = 0.0;
+#pragma unroll 1
             for (int i = 0; i < j; i++) sum += r[i + ldr * j] * wa1[i];
             wa1[j] = (wa1[j] - sum) / r[j + ldr * j];
         }
         const double temp = lq_enorm(kN, wa1);
         parl = ((fp / delta) / temp) / temp;
     }
+#pragma unroll 1
     for (int j = 0; j < kN; j++) {
         double sum = 0.0;
+#pragma unroll 1
         for (int i = 0; i <= j; i++) sum += r[i + ldr * j] * qtb[i];
         wa1[j] = sum / diag[ipvt[j]];
     }
@@ -233,21 +253,27 @@ __device__ void lq_lmpar(double* r, int ldr, const int* ipvt, const double* diag
     if (paru == 0.0) paru = kDwarf / fmin(delta, 0.1);
     par = fmin(fmax(par, parl), paru);
     if (par == 0.0) par = gnorm / dxnorm;
+#pragma unroll 1
     for (;;) {
         iter++;
         if (par == 0.0) par = fmax(kDwarf, 0.001 * paru);
         double temp = sqrt(par);
+#pragma unroll 1
         for (int j = 0; j < kN; j++) wa1[j] = temp * diag[j];
         lq_qrsolv(r, ldr, ipvt, wa1, qtb, x, sdiag, wa2);
+#pragma unroll 1
         for (int j = 0; j < kN; j++) wa2[j] = diag[j] * x[j];
         dxnorm = lq_enorm(kN, wa2);
         temp = fp;
         fp = dxnorm - delta;
         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+#pragma unroll 1
         for (int j = 0; j < kN; j++) { const int l = ipvt[j]; wa1[j] = diag[l] * (wa2[l] / dxnorm); }
+#pragma unroll 1
         for (int j = 0; j < kN; j++) {
             wa1[j] /= sdiag[j];
             const double t = wa1[j];
+#pragma unroll 1
             for (int i = j + 1; i < kN; i++) wa1[i] -= r[i + ldr * j] * t;
         }
         temp = lq_enorm(kN, wa1);
@@ -441,8 +467,13 @@ __global__ void __launch_bounds__(kThreads) lq_fit_kernel(const float* __restric
 // acceptance, convergence tests) is the MINPACK logic unchanged.
 
 // float32 point-sampled normalised Gaussian vector (gausslq.py:33-39)
+// lq_enorm, lq_gauss_vec and lq_resnorm are kept out of line and the small linear-algebra loops
+// rolled: inlined and unrolled at every call site (10 Gaussian vectors x 7 float64 divisions +
+// exponentials, 8 enorm copies with three division branches x 6, 21-fold unrolled Givens /
+// back-substitution steps) the kernel was 330 KB of SASS and stalled on instruction fetch
+// (ncu: no_instruction 4.0 stall cycles per issued instruction, issue slots 21 % busy).
 template <int BOX>
-__device__ __forceinline__ void lq_gauss_vec(double mu, double sigma, float* out) {
+__device__ __noinline__ void lq_gauss_vec(double mu, double sigma, float* out) {
     constexpr int H = BOX / 2;
     const double nrm = 0.3989422804014327 / sigma;
 #pragma unroll
@@ -454,7 +485,7 @@ __device__ __forceinline__ void lq_gauss_vec(double mu, double sigma, float* out
 
 // ||spot - f32(model)|| with MINPACK's enorm summation (mid-range branch) in pixel order
 template <int BOX>
-__device__ double lq_resnorm(const float* spot, const double* x) {
+__device__ __noinline__ double lq_resnorm(const float* spot, const double* x) {
     float mx[BOX], my[BOX];
     lq_gauss_vec<BOX>(x[0], x[4], mx);
     lq_gauss_vec<BOX>(x[1], x[5], my);
@@ -597,15 +628,19 @@ __global__ void __launch_bounds__(kThreads) lq_fit_ne_kernel(const float* __rest
             double rem[kN];                  // remaining squared column norms
 #pragma unroll
             for (int j = 0; j < kN; j++) rem[j] = Aat(j, j);
+#pragma unroll 1
             for (int q = 0; q < kN * kN; q++) r[q] = 0.0;
+#pragma unroll 1
             for (int j = 0; j < kN; j++) {
                 int kmax = j;
+#pragma unroll 1
                 for (int k = j; k < kN; k++)
                     if (rem[k] > rem[kmax]) kmax = k;
                 if (kmax != j) {
                     // swap pivot columns j <-> kmax: permutation, remaining norms, computed rows
                     const int t = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = t;
                     const double tr = rem[j]; rem[j] = rem[kmax]; rem[kmax] = tr;
+#pragma unroll 1
                     for (int l = 0; l < j; l++) {
                         const double tv = r[l + kN * j]; r[l + kN * j] = r[l + kN * kmax];
                         r[l + kN * kmax] = tv;
@@ -614,10 +649,12 @@ __global__ void __launch_bounds__(kThreads) lq_fit_ne_kernel(const float* __rest
                 const double d = rem[j];
                 const double rjj = d > 0.0 ? sqrt(d) : 0.0;
                 r[j + kN * j] = rjj;
+#pragma unroll 1
                 for (int k = j + 1; k < kN; k++) {
                     double v = 0.0;
                     if (rjj > 0.0) {
                         v = Aat(ipvt[j], ipvt[k]);
+#pragma unroll 1
                         for (int l = 0; l < j; l++) v -= r[l + kN * j] * r[l + kN * k];
                         v /= rjj;
                     }
@@ -627,13 +664,17 @@ __global__ void __launch_bounds__(kThreads) lq_fit_ne_kernel(const float* __rest
             }
         }
         // qtf = R^-T P^T (J^T f)
+#pragma unroll 1
         for (int j = 0; j < kN; j++) {
             double v = g[ipvt[j]];
+#pragma unroll 1
             for (int l = 0; l < j; l++) v -= r[l + kN * j] * qtf[l];
             qtf[j] = (r[j + kN * j] != 0.0) ? v / r[j + kN * j] : 0.0;
         }
         if (iter == 1) {
+#pragma unroll 1
             for (int j = 0; j < kN; j++) diag[j] = (acn[j] == 0.0) ? 1.0 : acn[j];
+#pragma unroll 1
             for (int j = 0; j < kN; j++) wa3[j] = diag[j] * x[j];
             xnorm = lq_enorm(kN, wa3);
             delta = factor * xnorm;
@@ -641,21 +682,25 @@ __global__ void __launch_bounds__(kThreads) lq_fit_ne_kernel(const float* __rest
         }
         gnorm = 0.0;
         if (fnorm != 0.0) {
+#pragma unroll 1
             for (int j = 0; j < kN; j++) {
                 const int l = ipvt[j];
                 if (acn[l] != 0.0) {
                     double sum = 0.0;
+#pragma unroll 1
                     for (int i = 0; i <= j; i++) sum += r[i + kN * j] * (qtf[i] / fnorm);
                     gnorm = fmax(gnorm, fabs(sum / acn[l]));
                 }
             }
         }
         if (gnorm <= gtol) { info = 4; break; }
+#pragma unroll 1
         for (int j = 0; j < kN; j++) diag[j] = fmax(diag[j], acn[j]);
 
         double ratio = 0.0;
         do {
             lq_lmpar(r, kN, ipvt, diag, qtf, delta, par, wa1, wa2, wa3, wa4);
+#pragma unroll 1
             for (int j = 0; j < kN; j++) {
                 wa1[j] = -wa1[j];
                 wa2[j] = x[j] + wa1[j];
@@ -667,9 +712,11 @@ __global__ void __launch_bounds__(kThreads) lq_fit_ne_kernel(const float* __rest
             nfev++;
             double actred = -1.0;
             if (0.1 * fnorm1 < fnorm) actred = 1.0 - sq(fnorm1 / fnorm);
+#pragma unroll 1
             for (int j = 0; j < kN; j++) {
                 wa3[j] = 0.0;
                 const double temp = wa1[ipvt[j]];
+#pragma unroll 1
                 for (int i = 0; i <= j; i++) wa3[i] += r[i + kN * j] * temp;
             }
             const double temp1 = lq_enorm(kN, wa3) / fnorm;
@@ -687,6 +734,7 @@ __global__ void __launch_bounds__(kThreads) lq_fit_ne_kernel(const float* __rest
                 par = 0.5 * par;
             }
             if (ratio >= 1e-4) {
+#pragma unroll 1
                 for (int j = 0; j < kN; j++) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
                 xnorm = lq_enorm(kN, wa2);
                 fnorm = fnorm1;
