@@ -1,0 +1,30 @@
+"""Two-rank NCCL check of the sharded stages (picasso_b200.distributed) -- runs only where at
+least two GPUs are visible (`gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`);
+the gloo world-size-2 tests in test_distributed_cpu.py cover the gathers on CPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_stages_agree_with_one_gpu():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "bench_multi.py"),
+           "--small"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["world"] == 2
+    assert out["localize"]["tables_bit_identical"] is True
+    assert out["render"]["n_equal"] is True and out["render"]["max_rel_dev_bright_pixels"] < 1e-4
+    assert out["undrift"]["max_abs_drift_dev"] < 1e-5
