@@ -164,10 +164,11 @@ struct Pipeline {
     Buf ids;        // unsorted frame,x,y (i64) + ng | sorted frame,x,y + ng
     Buf keys;       // keys in/out (u64), idx in/out (u32)
     Buf cubtmp, spots, fit, cols, counter;
+    Buf hcols[2];   // pinned landing buffers of the finished columns (copied out one chunk later)
     Buf hcount;     // pinned 8 bytes
     cudaStream_t copy = nullptr, comp = nullptr;
     cudaEvent_t up[2] = {nullptr, nullptr}, staged[2] = {nullptr, nullptr},
-                cut[2] = {nullptr, nullptr}, cnt = nullptr;
+                cut[2] = {nullptr, nullptr}, d2h[2] = {nullptr, nullptr}, cnt = nullptr;
     int init() {
         if (copy) return PB_OK;
         PB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
@@ -176,7 +177,9 @@ struct Pipeline {
             PB_CUDA_CHECK(cudaEventCreateWithFlags(&up[s], cudaEventDisableTiming));
             PB_CUDA_CHECK(cudaEventCreateWithFlags(&staged[s], cudaEventDisableTiming));
             PB_CUDA_CHECK(cudaEventCreateWithFlags(&cut[s], cudaEventDisableTiming));
+            PB_CUDA_CHECK(cudaEventCreateWithFlags(&d2h[s], cudaEventDisableTiming));
             stage[s].pinned = true;
+            hcols[s].pinned = true;
         }
         PB_CUDA_CHECK(cudaEventCreateWithFlags(&cnt, cudaEventDisableTiming));
         hcount.pinned = true;
@@ -351,6 +354,19 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
     if ((rc = upload(0))) return rc;
     size_t total = 0;
     bool overflow = false;
+    // finished columns land in pinned memory and are copied to the caller one chunk later, so the
+    // host never blocks on a pageable D2H while the next chunk could be staged
+    struct Pending { bool on = false; size_t at = 0, n = 0, pitch = 0; } pend[2];
+    auto drain = [&](int s) -> int {
+        if (!pend[s].on) return PB_OK;
+        PB_CUDA_CHECK(cudaEventSynchronize(P->d2h[s]));
+        const char* h = static_cast<const char*>(P->hcols[s].p);
+        for (int k = 0; k < ncols; k++)
+            memcpy(static_cast<char*>(columns) + ((size_t)k * capacity + pend[s].at) * 4,
+                   h + (size_t)k * pend[s].pitch * 4, pend[s].n * 4);
+        pend[s].on = false;
+        return PB_OK;
+    };
     volatile unsigned long long* hcount = static_cast<unsigned long long*>(P->hcount.p);
     const cudaStream_t cs = P->comp;
     for (size_t c = 0; c < nchunks; c++) {
@@ -400,8 +416,13 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
             if ((rc = pb_locs_from_fits_dev(n, fit == 3 ? 4 : fit, box, em, sf, sx, sy, sng, d_th, d_cr, d_ll, d_it,
                                             P->cols.p, dcap, cs)))
                 return rc;
-            PB_CUDA_CHECK(cudaMemcpy2DAsync(static_cast<char*>(columns) + total * 4, capacity * 4, P->cols.p,
-                                            dcap * 4, (size_t)n * 4, ncols, cudaMemcpyDeviceToHost, cs));
+            if ((rc = drain(s))) return rc;                       // chunk c-2 used this landing buffer
+            if ((rc = P->hcols[s].grow((size_t)ncols * n * 4))) return rc;
+            PB_CUDA_CHECK(cudaMemcpy2DAsync(P->hcols[s].p, (size_t)n * 4, P->cols.p, dcap * 4, (size_t)n * 4,
+                                            ncols, cudaMemcpyDeviceToHost, cs));
+            PB_CUDA_CHECK(cudaEventRecord(P->d2h[s], cs));
+            pend[s].on = true; pend[s].at = total; pend[s].n = n; pend[s].pitch = n;
+            if ((rc = drain(s ^ 1))) return rc;                   // previous chunk: long finished
             // the id / fit / column buffers are reused by the next chunk on the same stream: in order
         } else {
             PB_CUDA_CHECK(cudaEventRecord(P->cut[s], cs));
@@ -411,6 +432,7 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
     PB_CUDA_CHECK(cudaStreamSynchronize(cs));
     PB_CUDA_CHECK(cudaStreamSynchronize(P->copy));
     PB_CUDA_CHECK(cudaGetLastError());
+    if ((rc = drain(0)) || (rc = drain(1))) return rc;
     *n_found = total;
     if (overflow) {
         pb_set_error("pb_localize: found %zu spots, capacity %zu", total, capacity);

@@ -6,6 +6,7 @@
 // cut into 32 MB chunks that alternate between two pinned staging buffers: several host
 // threads copy chunk c+1 into (out of) its buffer while the DMA engine moves chunk c.
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <stdlib.h>
 #include <thread>
@@ -47,20 +48,73 @@ bool pb_host_is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
+// Persistent copy workers: spawning ~11 threads per 32 MB chunk cost ~1 ms per fit chunk
+// (44 thread creations); the pool is created on first use and lives for the process (heap
+// allocated and never destroyed, so no static-destruction race with blocked workers).
+namespace {
+struct CopyPool {
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    std::vector<std::thread> workers;
+    // current job
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t bytes = 0, per = 0;
+    unsigned parts = 0, next = 0, done = 0;
+    unsigned long long generation = 0;
+    std::mutex submit;      // one job at a time
+
+    void worker() {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m);
+            cv_job.wait(lk, [&] { return generation != seen && next < parts; });
+            const unsigned long long gen = generation;
+            while (next < parts) {
+                const unsigned k = next++;
+                lk.unlock();
+                const size_t o = (size_t)k * per;
+                memcpy(dst + o, src + o, std::min(per, bytes - o));
+                lk.lock();
+                if (++done == parts) cv_done.notify_all();
+            }
+            seen = gen;
+        }
+    }
+    void run(void* d, const void* s_, size_t n, unsigned nt) {
+        std::lock_guard<std::mutex> one(submit);
+        if (workers.size() + 1 < nt) {
+            std::lock_guard<std::mutex> lk(m);
+            while (workers.size() + 1 < nt) {
+                workers.emplace_back([this] { worker(); });
+                workers.back().detach();
+            }
+        }
+        const size_t p = ((n + nt - 1) / nt + 4095) / 4096 * 4096;
+        const unsigned np_ = (unsigned)((n + p - 1) / p);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            dst = static_cast<char*>(d); src = static_cast<const char*>(s_);
+            bytes = n; per = p; parts = np_; next = 1; done = 0;     // part 0 is copied by the caller
+            generation++;
+        }
+        cv_job.notify_all();
+        memcpy(d, s_, std::min(p, n));
+        std::unique_lock<std::mutex> lk(m);
+        if (++done != parts) cv_done.wait(lk, [&] { return done == parts; });
+        parts = 0;
+    }
+};
+CopyPool* copy_pool() {
+    static CopyPool* p = new CopyPool();
+    return p;
+}
+}  // namespace
+
 void pb_parallel_memcpy(void* dst, const void* src, size_t bytes) {
     const unsigned nt = copy_threads();
-    if (bytes < ((size_t)4 << 20) || nt == 1) { memcpy(dst, src, bytes); return; }
-    const size_t per = ((bytes + nt - 1) / nt + 4095) / 4096 * 4096;
-    std::vector<std::thread> th;
-    th.reserve(nt);
-    for (unsigned t = 1; t < nt; t++) {
-        const size_t o = (size_t)t * per;
-        if (o >= bytes) break;
-        const size_t len = std::min(per, bytes - o);
-        th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, len); });
-    }
-    memcpy(dst, src, std::min(per, bytes));
-    for (auto& t : th) t.join();
+    if (bytes < ((size_t)2 << 20) || nt == 1) { memcpy(dst, src, bytes); return; }
+    copy_pool()->run(dst, src, bytes, nt);
 }
 
 int pb_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
