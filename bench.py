@@ -309,9 +309,46 @@ def main():
     # fit of step i+1, which writes the other buffer (the kernel's dynamic tile scheduler
     # absorbs the SMs NCCL borrows); a buffer is reused only after its gather completed.
     flats = [torch.empty(14 * n, dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
-    gathered = torch.empty(14 * n * world, dtype=torch.float32, device=dev) if world > 1 else None
     works = [None, None]
     stream = torch.cuda.current_stream()
+    # The gather itself: "p2p" (default) = copy-engine peer writes into IPC-shared buffers
+    # (picasso_b200.distributed.PeerGather: no SM taken from the running fit, no host blocking),
+    # "nccl" = one NCCL all-gather per step (PB_GATHER=nccl).  If the peer mapping cannot be set up
+    # on every rank the run falls back to NCCL.
+    gather_mode = os.environ.get("PB_GATHER", "p2p") if world > 1 else "none"
+    gathered, pg = None, None
+    if world > 1 and gather_mode == "p2p":
+        from picasso_b200.distributed import PeerGather
+        ok = torch.ones(1, device=dev)
+        try:
+            pg = PeerGather(dist, torch, 14 * n * 4, dev)
+        except Exception as exc:      # noqa: BLE001
+            print(f"[bench] rank {rank}: peer gather unavailable ({exc}); using NCCL", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            if pg is not None:
+                pg.close()
+            pg, gather_mode = None, "nccl"
+    if world > 1 and gather_mode != "p2p":
+        gather_mode = "nccl"
+        gathered = torch.empty(14 * n * world, dtype=torch.float32, device=dev)
+
+    class _Pending:
+        """Uniform handle: NCCL work object (host wait) or peer-gather events (device wait)."""
+        def __init__(self, work=None, events=None):
+            self.work, self.events = work, events
+
+        def wait(self):
+            if self.work is not None:
+                self.work.wait()
+            if self.events is not None:
+                PeerGather.wait(self.events, stream)
+
+    def launch_gather(flat):
+        if gather_mode == "p2p":
+            return _Pending(events=pg.gather_async(flat, stream))
+        return _Pending(work=dist.all_gather_into_tensor(gathered, flat, async_op=True))
 
     def views(flat):
         return (flat[: 6 * n], flat[6 * n: 12 * n], flat[12 * n: 13 * n],
@@ -327,7 +364,7 @@ def main():
                                       cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
                                       stream.cuda_stream))
         if world > 1:
-            works[b] = dist.all_gather_into_tensor(gathered, flats[b], async_op=True)
+            works[b] = launch_gather(flats[b])
 
     def drain():
         for b in range(2):
@@ -366,10 +403,23 @@ def main():
                                       stream.cuda_stream))
         k1[i].record()
         if world > 1:
-            works[b] = dist.all_gather_into_tensor(gathered, flats[b], async_op=True)
-    drain()          # every step's all-gather has completed inside the timed region
+            works[b] = launch_gather(flats[b])
+    drain()          # every step's gather has left this rank inside the timed region (max over ranks)
     e1.record()
     barrier()
+    gather_ok = None
+    if world > 1:
+        # the gathered array is complete and correct: per-rank checksums of the last block
+        mine = flats[(args.steps - 1) % len(flats)].view(torch.int32).to(torch.int64).sum().reshape(1)
+        sums = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sums, mine)
+        if pg is not None:
+            pg.finish()
+            full = pg.to_tensor(torch.int32)
+        else:
+            full = gathered.view(torch.int32)
+        got = full.view(world, -1).to(torch.int64).sum(1)
+        gather_ok = bool((got == sums).all().item())
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
@@ -461,8 +511,13 @@ def main():
                        "mle_impl": int(lib.pb_mle_get_impl()),
                        "l2": "input 1.96 GB per step >> 126 MB L2 (no flush needed)",
                        "parallelism": f"spots sharded by index over {world} GPU(s)"
-                                      + ("; one NCCL all-gather of the packed outputs per step, "
-                                         "overlapped with the next step's fit" if world > 1 else "")},
+                                      + ({"nccl": "; one NCCL all-gather of the packed outputs per step, "
+                                                  "overlapped with the next step's fit",
+                                          "p2p": "; all-gather of the packed outputs per step by copy-engine "
+                                                 "peer writes into IPC-shared buffers over NVLink "
+                                                 "(PeerGather; PB_GATHER=nccl selects one NCCL all-gather), "
+                                                 "overlapped with the next step's fit"}.get(gather_mode, "")),
+                       "gather": gather_mode, "gather_verified": gather_ok},
             "roofline": roof,
             # instruction-side view of the dominant kernel from the committed ncu --set full
             # capture (profiles/r01_mle_tps_ncu.md): what actually bounds the fit
@@ -480,6 +535,8 @@ def main():
                 "sample": f"{d} spots in {el:.1f} s (same distribution), oracle C port of "
                           "picasso.gaussmle._mlefit_sigmaxy, bit-identical to the numba reference"}
         _emit(line)
+    if pg is not None:
+        pg.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -57,6 +57,17 @@ int pb_host_free(void* ptr);
  * pb_copy_d2h is blocking.  Every host-pointer entry point below uses these internally. */
 int pb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
 int pb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+/* Peer-to-peer gather plumbing (one process per GPU on an NVLink box, csrc/p2p.cu): device
+ * buffers allocated here can be exported as CUDA IPC handles (pb_ipc_handle_bytes() bytes),
+ * opened by the other ranks and written with pb_copy_d2d_async -- copy-engine transfers that
+ * take no SM from a running fit, unlike an NCCL all-gather kernel. */
+int pb_dev_alloc(void** ptr, size_t bytes);
+int pb_dev_free(void* ptr);
+int pb_ipc_handle_bytes(void);
+int pb_ipc_export(const void* d_ptr, void* handle);
+int pb_ipc_open(const void* handle, void** d_ptr);
+int pb_ipc_close(void* d_ptr);
+int pb_copy_d2d_async(void* dst, const void* src, size_t bytes, void* stream);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 long long pb_launch_count(void);
 

@@ -239,3 +239,108 @@ def undrift_sharded(dist, torch, locs, info, segmentation, device="cuda"):
     return postprocess.undrift(locs, info, segmentation, display=False,
                                segmentation_callback=lambda i: None, rcc_callback=lambda i: None,
                                _shifts_fn=shifts)
+
+
+class PeerGather:
+    """All-gather of equally sized per-rank device blocks WITHOUT a kernel: every rank owns a
+    gather buffer allocated by the library (``pb_dev_alloc``), shares it with the other ranks of the
+    box through CUDA IPC handles (exchanged once over ``torch.distributed``) and receives the
+    blocks by copy-engine peer writes (``pb_copy_d2d_async`` over NVLink / NVSwitch).  Unlike an
+    NCCL all-gather no SM is taken from the fit kernel that runs at the same time, and nothing
+    blocks the host: ``gather_async`` returns CUDA events, ``wait`` makes a stream wait for them.
+
+    The block of rank r lands at byte offset ``r * block_bytes`` of every rank's buffer."""
+
+    def __init__(self, dist, torch, block_bytes: int, device, n_streams: int = 4):
+        import ctypes as C
+
+        from . import _lib
+
+        self.dist, self.torch, self.C, self._lib = dist, torch, C, _lib
+        self.l = l = _lib.load()
+        vp, sz = C.c_void_p, C.c_size_t
+        l.pb_dev_alloc.argtypes = [C.POINTER(vp), sz]
+        l.pb_dev_free.argtypes = [vp]
+        l.pb_ipc_export.argtypes = [vp, vp]
+        l.pb_ipc_open.argtypes = [vp, C.POINTER(vp)]
+        l.pb_ipc_close.argtypes = [vp]
+        l.pb_copy_d2d_async.argtypes = [vp, vp, sz, vp]
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.block_bytes = int(block_bytes)
+        self.device = device
+        buf = vp()
+        _lib.check(l.pb_dev_alloc(C.byref(buf), self.block_bytes * self.world))
+        self.buf = buf.value
+        hb = l.pb_ipc_handle_bytes()
+        handle = np.zeros(hb, np.uint8)
+        _lib.check(l.pb_ipc_export(self.buf, handle.ctypes.data))
+        mine = torch.from_numpy(handle).to(device)
+        everyone = torch.empty(hb * self.world, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(everyone, mine)
+        handles = everyone.cpu().numpy().reshape(self.world, hb)
+        self.peers = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.peers.append(self.buf)
+            else:
+                p = vp()
+                h = np.ascontiguousarray(handles[r])
+                _lib.check(l.pb_ipc_open(h.ctypes.data, C.byref(p)))
+                self.peers.append(p.value)
+        self.streams = [torch.cuda.Stream(device) for _ in range(max(1, min(n_streams, self.world)))]
+        dist.barrier()
+
+    def gather_async(self, block, stream=None):
+        """Enqueue the copies of ``block`` (a contiguous device tensor of block_bytes) into every
+        rank's buffer, ordered after the work already enqueued on ``stream``; returns the events
+        that complete when the block has left this rank."""
+        torch = self.torch
+        stream = stream or torch.cuda.current_stream(self.device)
+        assert block.is_contiguous() and block.numel() * block.element_size() == self.block_bytes
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        for k in range(self.world):
+            r = (self.rank + 1 + k) % self.world           # start with the neighbour: spread the links
+            st = self.streams[k % len(self.streams)]
+            st.wait_event(ready)
+            self._lib.check(self.l.pb_copy_d2d_async(self.peers[r] + self.rank * self.block_bytes,
+                                                     block.data_ptr(), self.block_bytes, st.cuda_stream))
+        done = []
+        for st in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            done.append(ev)
+        return done
+
+    @staticmethod
+    def wait(events, stream):
+        """Make ``stream`` wait (on the device, the host does not block) for a gather's events."""
+        for ev in events or ():
+            stream.wait_event(ev)
+
+    def finish(self):
+        """All outgoing copies of this rank done, then a barrier: every rank's buffer is complete."""
+        for st in self.streams:
+            st.synchronize()
+        self.dist.barrier()
+
+    def to_tensor(self, dtype):
+        """Copy of this rank's gather buffer as a torch tensor (for checks / consumers)."""
+        torch = self.torch
+        out = torch.empty(self.block_bytes * self.world // torch.empty(0, dtype=dtype).element_size(),
+                          dtype=dtype, device=self.device)
+        st = torch.cuda.current_stream(self.device)
+        self._lib.check(self.l.pb_copy_d2d_async(out.data_ptr(), self.buf, self.block_bytes * self.world,
+                                                 st.cuda_stream))
+        st.synchronize()
+        return out
+
+    def close(self):
+        if self.buf is None:
+            return
+        for r, p in enumerate(self.peers):
+            if r != self.rank:
+                self.l.pb_ipc_close(p)
+        self.dist.barrier()                  # nobody frees while a peer still has the mapping open
+        self.l.pb_dev_free(self.buf)
+        self.buf = None
