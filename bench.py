@@ -330,6 +330,7 @@ def main():
             if pg is not None:
                 pg.close()
             pg, gather_mode = None, "nccl"
+    gathered_parts = {}
     if world > 1 and gather_mode != "p2p":
         gather_mode = "nccl"
         gathered = torch.empty(14 * n * world, dtype=torch.float32, device=dev)
@@ -345,32 +346,61 @@ def main():
             if self.events is not None:
                 PeerGather.wait(self.events, stream)
 
-    def launch_gather(flat):
+    def launch_gather(part, offset_bytes):
         if gather_mode == "p2p":
-            return _Pending(events=pg.gather_async(flat, stream))
-        return _Pending(work=dist.all_gather_into_tensor(gathered, flat, async_op=True))
+            return _Pending(events=pg.gather_async(part, stream, offset_bytes))
+        # NCCL: one all-gather per part into the part's own gather buffer (part-major as well)
+        return _Pending(work=dist.all_gather_into_tensor(
+            gathered_parts[offset_bytes], part, async_op=True))
 
-    def views(flat):
-        return (flat[: 6 * n], flat[6 * n: 12 * n], flat[12 * n: 13 * n],
-                flat[13 * n:].view(torch.int32))
+    # With N > 1 the batch is fitted in PARTS sub-batches whose packed outputs are gathered as soon
+    # as each is done: the exchange overlaps the fit of the next sub-batch, and only the last
+    # quarter's gather remains after the last fit of a step (PB_BENCH_PARTS overrides; 1 = whole batch).
+    # The rank's block is part-major: for each part [thetas 6m | crlbs 6m | logliks m | iterations m].
+    parts = int(os.environ.get("PB_BENCH_PARTS", "4" if world > 1 else "1"))
+    parts = max(1, min(parts, 64))
+    pb = [((n * q) // parts) // 4096 * 4096 for q in range(parts)] + [n]     # part edges, 4096-spot aligned
+
+    def views(flat, q=None):
+        if q is None:                      # all parts: only meaningful for parts == 1
+            q = 0
+        lo, hi = pb[q], pb[q + 1]
+        m = hi - lo
+        base = flat[14 * lo: 14 * hi]
+        return (base[: 6 * m], base[6 * m: 12 * m], base[12 * m: 13 * m], base[13 * m:].view(torch.int32), base, lo, m)
+
+    def fit_and_gather(flat, b):
+        pend = []
+        for q in range(parts):
+            th, cr, ll, it, base, lo, m = views(flat, q)
+            _lib.check(lib.pb_mle_fit_dev(m, BOX, spots[lo:].data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
+                                          cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
+                                          stream.cuda_stream))
+            if world > 1:
+                pend.append(launch_gather(base, 14 * lo * 4))
+        return pend
+
+    if gather_mode == "nccl":
+        # NCCL receives each part in its own buffer [world x part]; offsets key the buffers
+        off = 0
+        for q in range(parts):
+            m = pb[q + 1] - pb[q]
+            gathered_parts[14 * pb[q] * 4] = gathered[off: off + 14 * m * world]
+            off += 14 * m * world
+
+    def wait_all(pend):
+        for p_ in pend or ():
+            p_.wait()
 
     def step(i):
         b = i % len(flats)
-        if works[b] is not None:
-            works[b].wait()
-            works[b] = None
-        th, cr, ll, it = views(flats[b])
-        _lib.check(lib.pb_mle_fit_dev(n, BOX, spots.data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
-                                      cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
-                                      stream.cuda_stream))
-        if world > 1:
-            works[b] = launch_gather(flats[b])
+        wait_all(works[b])
+        works[b] = fit_and_gather(flats[b], b)
 
     def drain():
         for b in range(2):
-            if works[b] is not None:
-                works[b].wait()
-                works[b] = None
+            wait_all(works[b])
+            works[b] = None
 
     def barrier():
         if world > 1:
@@ -393,17 +423,10 @@ def main():
     e0.record()
     for i in range(args.steps):
         b = i % len(flats)
-        if works[b] is not None:
-            works[b].wait()
-            works[b] = None
-        th, cr, ll, it = views(flats[b])
+        wait_all(works[b])
         k0[i].record()
-        _lib.check(lib.pb_mle_fit_dev(n, BOX, spots.data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
-                                      cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
-                                      stream.cuda_stream))
+        works[b] = fit_and_gather(flats[b], b)
         k1[i].record()
-        if world > 1:
-            works[b] = launch_gather(flats[b])
     drain()          # every step's gather has left this rank inside the timed region (max over ranks)
     e1.record()
     barrier()
@@ -417,8 +440,13 @@ def main():
             pg.finish()
             full = pg.to_tensor(torch.int32)
         else:
-            full = gathered.view(torch.int32)
-        got = full.view(world, -1).to(torch.int64).sum(1)
+            full = None
+        if full is not None:
+            got = full.view(world, -1).to(torch.int64).sum(1)
+        else:                                  # NCCL: one [world x part] buffer per part
+            got = torch.zeros(world, dtype=torch.int64, device=dev)
+            for gp in gathered_parts.values():
+                got += gp.view(torch.int32).view(world, -1).to(torch.int64).sum(1)
         gather_ok = bool((got == sums).all().item())
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
@@ -432,7 +460,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_kernel, ms_init, ms_iter, ms_crlb = t.tolist()
-    th, cr, ll, it = views(flats[0])
+    it = torch.cat([views(flats[0], q)[3] for q in range(parts)])      # iterations in spot order
     mean_it = float(it.float().mean().item())
     value = n * world * args.steps / (ms_total * 1e-3)
 
@@ -475,13 +503,14 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         tps = ms_iter > 0
+        n_launch = pb[parts] - pb[parts - 1]     # spots of the last pb_mle_fit_dev call (profiled one)
         if tps:
-            ach = ITER_BYTES_PER_SPOT * n / (ms_iter * 1e-3) / 1e9
+            ach = ITER_BYTES_PER_SPOT * n_launch / (ms_iter * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "tps_iter_kernel<7,1,float> (Newton iterations)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": NCU_ITER_DRAM_BYTES_PER_SPOT * n,
+                    "traffic": NCU_ITER_DRAM_BYTES_PER_SPOT * n_launch, "spots_per_launch": n_launch,
                     "traffic_source": "ncu --set full, profiles/r01_mle_tps_ncu.md (bytes/spot x spots per launch)",
-                    "algorithmic_bytes": ITER_BYTES_PER_SPOT * n, "peak_source": peak_src,
+                    "algorithmic_bytes": ITER_BYTES_PER_SPOT * n_launch, "peak_source": peak_src,
                     "kernel_ms": ms_iter,
                     "step_kernels_ms": {"tps_init_kernel": ms_init, "tps_iter_kernel": ms_iter,
                                         "tps_crlb_kernel": ms_crlb, "step": ms_kernel},
@@ -517,7 +546,7 @@ def main():
                                                  "peer writes into IPC-shared buffers over NVLink "
                                                  "(PeerGather; PB_GATHER=nccl selects one NCCL all-gather), "
                                                  "overlapped with the next step's fit"}.get(gather_mode, "")),
-                       "gather": gather_mode, "gather_verified": gather_ok},
+                       "gather": gather_mode, "gather_verified": gather_ok, "parts_per_step": parts},
             "roofline": roof,
             # instruction-side view of the dominant kernel from the committed ncu --set full
             # capture (profiles/r01_mle_tps_ncu.md): what actually bounds the fit

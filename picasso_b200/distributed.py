@@ -290,21 +290,24 @@ class PeerGather:
         self.streams = [torch.cuda.Stream(device) for _ in range(max(1, min(n_streams, self.world)))]
         dist.barrier()
 
-    def gather_async(self, block, stream=None):
-        """Enqueue the copies of ``block`` (a contiguous device tensor of block_bytes) into every
-        rank's buffer, ordered after the work already enqueued on ``stream``; returns the events
-        that complete when the block has left this rank."""
+    def gather_async(self, block, stream=None, offset_bytes: int = 0):
+        """Enqueue the copies of ``block`` (a contiguous device tensor; the whole block of this rank,
+        or the part of it that starts ``offset_bytes`` into the block) into every rank's buffer,
+        ordered after the work already enqueued on ``stream``; returns the events that complete
+        when the data has left this rank."""
         torch = self.torch
         stream = stream or torch.cuda.current_stream(self.device)
-        assert block.is_contiguous() and block.numel() * block.element_size() == self.block_bytes
+        nbytes = block.numel() * block.element_size()
+        assert block.is_contiguous() and offset_bytes + nbytes <= self.block_bytes
         ready = torch.cuda.Event()
         ready.record(stream)
         for k in range(self.world):
             r = (self.rank + 1 + k) % self.world           # start with the neighbour: spread the links
             st = self.streams[k % len(self.streams)]
             st.wait_event(ready)
-            self._lib.check(self.l.pb_copy_d2d_async(self.peers[r] + self.rank * self.block_bytes,
-                                                     block.data_ptr(), self.block_bytes, st.cuda_stream))
+            self._lib.check(self.l.pb_copy_d2d_async(
+                self.peers[r] + self.rank * self.block_bytes + offset_bytes, block.data_ptr(), nbytes,
+                st.cuda_stream))
         done = []
         for st in self.streams:
             ev = torch.cuda.Event()
