@@ -353,11 +353,12 @@ def main():
         return _Pending(work=dist.all_gather_into_tensor(
             gathered_parts[offset_bytes], part, async_op=True))
 
-    # With N > 1 the batch is fitted in PARTS sub-batches whose packed outputs are gathered as soon
-    # as each is done: the exchange overlaps the fit of the next sub-batch, and only the last
-    # quarter's gather remains after the last fit of a step (PB_BENCH_PARTS overrides; 1 = whole batch).
-    # The rank's block is part-major: for each part [thetas 6m | crlbs 6m | logliks m | iterations m].
-    parts = int(os.environ.get("PB_BENCH_PARTS", "4" if world > 1 else "1"))
+    # PB_BENCH_PARTS > 1 fits the batch in sub-batches and gathers each as soon as it is done
+    # (part-major block: per part [thetas 6m | crlbs 6m | logliks m | iterations m]).  Measured:
+    # every extra launch of the persistent iteration kernel costs ~1 ms of drain phase (4 parts:
+    # 21.9 ms instead of 18.0 ms per 10 M spots), far more than the exposed tail of the last
+    # gather it would hide -- so the default stays one launch per step.
+    parts = int(os.environ.get("PB_BENCH_PARTS", "1"))
     parts = max(1, min(parts, 64))
     pb = [((n * q) // parts) // 4096 * 4096 for q in range(parts)] + [n]     # part edges, 4096-spot aligned
 
