@@ -28,3 +28,18 @@ def test_sharded_stages_agree_with_one_gpu():
     assert out["localize"]["tables_bit_identical"] is True
     assert out["render"]["n_equal"] is True and out["render"]["max_rel_dev_bright_pixels"] < 1e-4
     assert out["undrift"]["max_abs_drift_dev"] < 1e-5
+
+
+def test_peer_gather_equals_nccl_all_gather():
+    """PeerGather (copy-engine peer writes into IPC-shared buffers) delivers what an NCCL all-gather
+    delivers, whole blocks and parts at an offset."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tools", "check_peer_gather.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out == {"world": 2, "peer_gather_equals_nccl": True}
