@@ -211,6 +211,9 @@ int pb_locs_from_fits_dev(size_t n, int fit, int box, int em, const long long* d
 int pb_lq_fit(size_t n, int box, const float* spots, float* thetas, int* infos, int* nfevs);
 int pb_lq_fit_dev(size_t n, int box, const float* d_spots, float* d_thetas, int* d_infos,
                   int* d_nfevs, void* stream);
+/* measurement hook (process-wide): 0 = register-resident factorisation of J^T J (default),
+ * 1 = MINPACK-order Householder qrfac on the m x 6 Jacobian (A/B parity and speed runs) */
+int pb_lq_set_impl(int impl);
 
 /* ---- astigmatic z fit ----------------------------------------------------------
  * Replaces the per-localization loop and column arithmetic of picasso.zfit._fit_z

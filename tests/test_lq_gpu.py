@@ -2,9 +2,11 @@
 vectors from the real reference (scipy.optimize.leastsq) and vs the CPU oracle.
 
 Stated LQ tolerance: the optimiser stops after ~3 LM iterations at ftol=xtol=1e-2,
-so parity means following the same trajectory: >= 99 % of spots with the same number
-of residual evaluations (nfev) and, on those, x/y/sigma within 1e-4 px, photons/bg
-within 1e-4 relative."""
+so parity means following the same trajectory.  Measured on a B200 (tools/parity_lq.py,
+profiles/r02_parity_lq.jsonl, 200 k 7x7 spots): identical nfev and info on 100 % of the spots,
+99.9995 % of theta rows bit-identical to scipy's result, all-spot RMS 4e-8 px (x) -- so the bar
+asserted here is north_star's 1e-4 px RMS over ALL spots with two orders of margin: >= 99.99 %
+identical nfev, >= 99.9 % of spots within 1e-4 (px / relative), all-spot RMS <= 1e-5 px."""
 import os
 
 import numpy as np
@@ -15,13 +17,15 @@ from picasso_b200 import gausslq, testing
 pytestmark = pytest.mark.gpu
 
 
-def _check(th, ref, same_frac_min=0.99):
+def _check(th, ref, same_frac_min=0.999):
     d = np.abs(th.astype(np.float64) - ref)
     tol = np.array([1e-4, 1e-4, 0, 0, 1e-4, 1e-4]) + 1e-4 * np.abs(ref) * np.array([0, 0, 1, 1, 0, 0])
     ok = (d <= tol).all(1)
     assert ok.mean() >= same_frac_min, ok.mean()
     rms = np.sqrt((d[:, [0, 1, 4, 5]] ** 2).mean(0))
-    assert rms.max() <= 2e-3, rms          # the few off-trajectory spots stay within LQ's own tolerance
+    assert rms.max() <= 1e-4, rms          # north_star: 1e-4 px RMS over all spots
+    rel = np.sqrt(((d[:, [2, 3]] / np.maximum(np.abs(ref[:, [2, 3]]), 1e-6)) ** 2).mean(0))
+    assert rel.max() <= 1e-4, rel
 
 
 @pytest.mark.parametrize("box", [5, 7, 9, 11, 13])
@@ -36,16 +40,34 @@ def test_lq_matches_reference_golden(golden_dir, box):
 @pytest.mark.parametrize("key", ["float", "movie"])
 def test_lq_float_spots_golden(golden_dir, key):
     g = np.load(os.path.join(golden_dir, "lq.npz"))
-    _check(gausslq.fit_spots(g[f"{key}_spots"]), g[f"{key}_thetas"], 0.97)
+    _check(gausslq.fit_spots(g[f"{key}_spots"]), g[f"{key}_thetas"], 0.98)
 
 
-def test_lq_vs_oracle_trajectory(oracle):
-    spots = testing.synthetic_spots(20000, 7, seed=77)
-    th, info, nfev = gausslq._fit(spots, want_info=True)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_lq_vs_oracle_trajectory(oracle, impl):
+    """Both kernel variants (0 = register-resident factorisation, the default; 1 = MINPACK-order
+    QR) against the oracle, which is bit-identical to scipy.optimize.leastsq."""
+    import ctypes as C
+
+    from picasso_b200 import _lib
+
+    lib = _lib.load()
+    lib.pb_lq_set_impl.argtypes = [C.c_int]
+    spots = testing.synthetic_spots(50000, 7, seed=77)
     oth, oinfo, onfev = oracle.fit_spots_lq(spots, nthreads=8, return_info=True)
-    assert (nfev == onfev).mean() >= 0.99
-    same = nfev == onfev
-    np.testing.assert_allclose(th[same], oth[same], rtol=2e-4, atol=2e-4)
+    _lib.check(lib.pb_lq_set_impl(impl))
+    try:
+        th, info, nfev = gausslq._fit(spots, want_info=True)
+    finally:
+        lib.pb_lq_set_impl(0)
+    assert (nfev == onfev).mean() >= 0.9999, (nfev == onfev).mean()
+    assert (info == oinfo).mean() >= 0.9999
+    d = th.astype(np.float64) - oth
+    rms = np.sqrt((d ** 2).mean(0))
+    assert rms[[0, 1, 4, 5]].max() <= 1e-5, rms                       # px, ALL spots
+    rel = np.sqrt(((d[:, [2, 3]] / oth[:, [2, 3]]) ** 2).mean(0))
+    assert rel.max() <= 1e-5, rel
+    assert (th.view(np.uint32) == oth.view(np.uint32)).all(1).mean() >= 0.999
     assert set(np.unique(info)) <= {1, 2, 3, 4}
 
 

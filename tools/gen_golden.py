@@ -4,7 +4,7 @@ dependencies mocked -- tools/ref_import.py).
 
 Run in the build container only:
 
-    python tools/gen_golden.py [mle] [identify] [lq] [render] [undrift] [testdata]
+    python tools/gen_golden.py [mle] [identify] [lq] [render] [undrift] [undrift_c5] [testdata]
 
 Each fixture stores the inputs and the reference's outputs, so the tests need
 neither the reference nor this script at run time.
@@ -259,6 +259,37 @@ def gen_undrift(ref):
     save("undrift.npz", **out)
 
 
+def gen_undrift_c5(ref):
+    """Reduced instance of BASELINE config 5: 20 segments x 1024^2, the config-5
+    cluster / drift generator scaled to 2 000 frames.  Stores the localizations, the reference's
+    per-pair shifts (get_image_shift on the reference's own float64 segment renders), the segment
+    shifts of rcc and the final drift of postprocess.undrift -- not the 20 x 1024^2 images."""
+    from picasso_b200 import testing
+
+    post, imp = ref["postprocess"], ref["imageprocess"]
+    locs, info, _ = testing.synthetic_drift_locs(2000, 1024, 1024, n_clusters=400, locs_per_frame=40.0,
+                                                 seed=3, jitter=0.05, lp=0.05)
+    out = {c: locs[c].to_numpy() for c in locs.columns}
+    out["info_hwf"] = np.array([1024, 1024, 2000])
+    bounds, segments = post.segment(locs, info, 100,
+                                    {"blur_method": "gaussian", "min_blur_width": 1}, lambda i: None)
+    out["bounds"] = bounds
+    n = len(segments)
+    sy = np.zeros((n, n)); sx = np.zeros((n, n))
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            sy[i, j], sx[i, j] = imp.get_image_shift(segments[i], segments[j], 5, 32)
+    out["pair_shift_y"] = sy; out["pair_shift_x"] = sx
+    shift_y, shift_x = imp.rcc(segments, 32, lambda i: None)
+    out["rcc_shift_y"] = shift_y; out["rcc_shift_x"] = shift_x
+    drift, und = post.undrift(locs, info, 100, display=False, segmentation_callback=lambda i: None,
+                              rcc_callback=lambda i: None)
+    out["drift_x"] = drift["x"].to_numpy(); out["drift_y"] = drift["y"].to_numpy()
+    out["segment_sums"] = segments.sum((1, 2))
+    save("undrift_c5.npz", **out)
+    print("undrift_c5:", len(locs), "locs", n, "segments")
+
+
 def zfit_problem(n=3000, seed=11):
     """Synthetic astigmatism calibration + 2-D fitted localizations (shared with the tests)."""
     from picasso_b200 import testing
@@ -361,7 +392,7 @@ def gen_link(ref):
     save("link.npz", **out)
 
 
-GENERATORS = {"link": gen_link, "aim": gen_aim, "zfit": gen_zfit, "mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift}
+GENERATORS = {"link": gen_link, "aim": gen_aim, "zfit": gen_zfit, "mle": gen_mle, "identify": gen_identify, "testdata": gen_testdata, "lq": gen_lq, "render": gen_render, "undrift": gen_undrift, "undrift_c5": gen_undrift_c5}
 
 
 def main():
