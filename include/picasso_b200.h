@@ -46,6 +46,8 @@ const char* pb_last_error(void);          /* cf. gpufit_get_last_error, gpufit.p
 const char* pb_version(void);
 int pb_device_count(void);                /* number of sm_100 devices visible (cf. gpufit cuda_available) */
 int pb_set_device(int device);            /* cudaSetDevice for the calling thread */
+int pb_get_device(int* device);           /* cudaGetDevice of the calling thread (worker threads inherit it
+                                             through the Python layer: the CUDA current device is per thread) */
 int pb_synchronize(void);                 /* cudaDeviceSynchronize on the current device */
 /* pinned host memory for callers that want full PCIe speed (optional) */
 int pb_host_alloc(void** ptr, size_t bytes);

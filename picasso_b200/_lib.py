@@ -28,6 +28,8 @@ def _declare(lib):
     lib.pb_device_count.restype = i32
     lib.pb_launch_count.restype = i64
     lib.pb_set_device.argtypes = [i32]
+    lib.pb_get_device.argtypes = [C.POINTER(i32)]
+    lib.pb_get_device.restype = i32
     lib.pb_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.pb_host_free.argtypes = [vp]
     lib.pb_mle_fit.argtypes = [sz, i32, vp, f64, i32, i32, vp, vp, vp, vp, vp, vp]
@@ -73,6 +75,27 @@ def require_gpu() -> None:
         raise PicassoB200Error(
             "no sm_100 (B200) device visible: picasso_b200 runs its hot path on the GPU only"
         )
+
+
+def current_device() -> int:
+    """CUDA device of the calling thread."""
+    d = C.c_int(0)
+    check(load().pb_get_device(C.byref(d)))
+    return int(d.value)
+
+
+def on_callers_device(fn):
+    """Wrap ``fn`` for execution on another host thread: the CUDA current device is per thread,
+    so a worker spawned by a rank that selected GPU r (pb_set_device / torch.cuda.set_device) would
+    otherwise run on device 0.  The caller's device is captured now and selected in the worker."""
+    dev = current_device() if device_count() > 0 else None
+
+    def run(*a, **k):
+        if dev is not None:
+            check(load().pb_set_device(dev))
+        return fn(*a, **k)
+
+    return run
 
 
 def ptr(a: np.ndarray):

@@ -20,7 +20,14 @@ void pb_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* pb_last_error(void) { return g_err; }
-extern "C" const char* pb_version(void) { return "picasso_b200 0.1.0 (sm_100a)"; }
+// The SHA-256 of the sources this library was built from (csrc/, include/, flags) is embedded by
+// picasso_b200/build.py: build() rebuilds whenever it differs from the sources on disk.
+#ifndef PB_SOURCE_HASH
+#define PB_SOURCE_HASH "0000000000000000000000000000000000000000000000000000000000000000"
+#endif
+extern "C" const char* pb_version(void) {
+    return "picasso_b200 0.2.0 (sm_100a) PB_SRC_HASH=" PB_SOURCE_HASH;
+}
 extern "C" long long pb_launch_count(void) { return g_pb_launches.load(); }
 
 extern "C" int pb_device_count(void) {
@@ -41,6 +48,12 @@ extern "C" int pb_device_count(void) {
 
 extern "C" int pb_set_device(int device) {
     PB_CUDA_CHECK(cudaSetDevice(device));
+    return PB_OK;
+}
+
+extern "C" int pb_get_device(int* device) {
+    if (!device) { pb_set_error("pb_get_device: null pointer"); return PB_ERR_INVALID; }
+    PB_CUDA_CHECK(cudaGetDevice(device));
     return PB_OK;
 }
 
@@ -82,17 +95,24 @@ struct Slot {
     cudaEvent_t done = nullptr;
 };
 constexpr int kSlots = 3;
+constexpr int kMaxDevices = 64;
 struct DevWs {
     Slot slots[kSlots];
+    std::mutex call_mutex;     // serialises the host-buffer fit calls that share these slots
 };
 std::mutex g_ws_mutex;
-std::vector<DevWs> g_ws;   // indexed by device
+DevWs g_ws[kMaxDevices];       // indexed by device (fixed storage: Slot pointers stay valid)
+
+int ws_device(int* dev) {
+    PB_CUDA_CHECK(cudaGetDevice(dev));
+    if (*dev < 0 || *dev >= kMaxDevices) { pb_set_error("device index %d out of range", *dev); return PB_ERR_INVALID; }
+    return PB_OK;
+}
 
 int ws_get(int slot, size_t bytes, size_t host_bytes, Slot** out) {
-    int dev = 0;
-    PB_CUDA_CHECK(cudaGetDevice(&dev));
+    int dev = 0, rc0 = ws_device(&dev);
+    if (rc0) return rc0;
     std::lock_guard<std::mutex> lk(g_ws_mutex);
-    if ((int)g_ws.size() <= dev) g_ws.resize(dev + 1);
     Slot& s = g_ws[dev].slots[slot];
     if (!s.stream) {
         PB_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -146,6 +166,18 @@ int fit_pipeline(size_t n, size_t in_stride, const void* in, OutSpec* outs, int 
         if ((rc = ws_get(s, total, staged ? total - out0 : 0, &sl[s])) != PB_OK) return rc;
     size_t first_of[kSlots] = {0}, m_of[kSlots] = {0};
     bool busy[kSlots] = {false};
+    // On ANY error the other slots may still have kernels and D2H copies into the caller's arrays
+    // in flight: wait for every slot stream before returning, so that the caller may free or reuse
+    // its buffers as soon as the call is back ("the library never keeps a pointer after the call").
+    struct Quiesce {
+        Slot** sl; bool armed = true;
+        ~Quiesce() {
+            if (!armed) return;
+            for (int s = 0; s < kSlots; s++)
+                if (sl[s] && sl[s]->stream) cudaStreamSynchronize(sl[s]->stream);
+            cudaGetLastError();
+        }
+    } quiesce{sl};
     auto retire = [&](int s) -> int {       // chunk in slot s finished: hand its outputs to the caller
         PB_CUDA_CHECK(cudaEventSynchronize(sl[s]->done));
         if (staged) {
@@ -188,12 +220,18 @@ int fit_pipeline(size_t n, size_t in_stride, const void* in, OutSpec* outs, int 
         if (busy[s] && (rc = retire(s)) != PB_OK) return rc;
     }
     if (progress) *progress = (long long)n;
+    quiesce.armed = false;     // every slot was retired: nothing in flight
     return PB_OK;
 }
-}  // namespace
 
-// Serialises host-buffer calls that share the cached workspaces.
-static std::mutex g_host_call_mutex;
+// Host-buffer fit calls on the same device share that device's cached slots and are serialised;
+// calls on different devices, and the render / identify / undrift entry points, are not.
+std::mutex* device_call_mutex() {
+    int dev = 0;
+    if (ws_device(&dev) != PB_OK) return nullptr;
+    return &g_ws[dev].call_mutex;
+}
+}  // namespace
 
 extern "C" int pb_mle_fit(size_t n, int box, const float* spots, double eps, int max_it, int method,
                           float* thetas, float* crlbs, float* logliks, int* iterations, int* status,
@@ -212,7 +250,9 @@ extern "C" int pb_mle_fit(size_t n, int box, const float* spots, double eps, int
         pb_set_error("pb_mle_fit: null pointer");
         return PB_ERR_INVALID;
     }
-    std::lock_guard<std::mutex> call_lk(g_host_call_mutex);
+    std::mutex* cm = device_call_mutex();
+    if (!cm) return PB_ERR_CUDA;
+    std::lock_guard<std::mutex> call_lk(*cm);
     const size_t pix = (size_t)box * box;
     // chunk: ~64 MB of ROIs (PB_MLE_CHUNK_MB overrides), a multiple of 4096 spots
     size_t chunk_mb = 64;
@@ -243,7 +283,9 @@ extern "C" int pb_lq_fit(size_t n, int box, const float* spots, float* thetas, i
         pb_set_error("unsupported box size %d for LQ fit (odd 5..15)", box);
         return PB_ERR_INVALID;
     }
-    std::lock_guard<std::mutex> call_lk(g_host_call_mutex);
+    std::mutex* cm = device_call_mutex();
+    if (!cm) return PB_ERR_CUDA;
+    std::lock_guard<std::mutex> call_lk(*cm);
     const size_t pix = (size_t)box * box;
     size_t chunk = ((size_t)64 << 20) / (pix * 4);
     chunk = chunk / 4096 * 4096;

@@ -528,31 +528,39 @@ extern "C" int pb_identify(const void* movie, int dtype, size_t n_frames, int Y,
     if ((rc = dfr.alloc(cap * 8)) || (rc = dx.alloc(cap * 8)) || (rc = dy.alloc(cap * 8)) ||
         (rc = dng.alloc(cap * 4)) || (rc = dcnt.alloc(8)))
         return rc;
-    cudaStream_t st[2];
-    cudaEvent_t ev[2];
+    // streams / events are released on every path (no early return between create and destroy)
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t err) { if (err != cudaSuccess && e == cudaSuccess) e = err; return e == cudaSuccess; };
     for (int s = 0; s < 2; s++) {
-        PB_CUDA_CHECK(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
-        PB_CUDA_CHECK(cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming));
+        ck(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+        ck(cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming));
     }
-    PB_CUDA_CHECK(cudaMemsetAsync(dcnt.p, 0, 8, st[0]));
-    PB_CUDA_CHECK(cudaStreamSynchronize(st[0]));
-    size_t c = 0;
     rc = PB_OK;
-    for (size_t f0 = 0; f0 < n_frames && rc == PB_OK; f0 += chunk, c++) {
+    if (e == cudaSuccess) {
+        ck(cudaMemsetAsync(dcnt.p, 0, 8, st[0]));
+        ck(cudaStreamSynchronize(st[0]));
+    }
+    size_t c = 0;
+    for (size_t f0 = 0; f0 < n_frames && rc == PB_OK && e == cudaSuccess; f0 += chunk, c++) {
         const int s = (int)(c & 1);
         const size_t nf = std::min(chunk, n_frames - f0);
-        if (c >= 2) cudaEventSynchronize(ev[s]);
+        if (c >= 2 && !ck(cudaEventSynchronize(ev[s]))) break;
         if ((rc = pb_h2d(mv[s].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz, st[s])) != PB_OK) break;
         rc = pb_identify_dev(mv[s].p, dtype, nf, Y, X, frame_offset + (long long)f0, box, min_ng,
                              roi, static_cast<long long*>(dfr.p), static_cast<long long*>(dx.p),
                              static_cast<long long*>(dy.p), static_cast<float*>(dng.p), capacity,
                              static_cast<unsigned long long*>(dcnt.p), st[s]);
-        cudaEventRecord(ev[s], st[s]);
+        ck(cudaEventRecord(ev[s], st[s]));
     }
-    for (int s = 0; s < 2; s++) cudaStreamSynchronize(st[s]);
+    for (int s = 0; s < 2; s++) if (st[s]) ck(cudaStreamSynchronize(st[s]));
     unsigned long long found = 0;
-    cudaError_t e = cudaMemcpy(&found, dcnt.p, 8, cudaMemcpyDeviceToHost);
-    for (int s = 0; s < 2; s++) { cudaStreamDestroy(st[s]); cudaEventDestroy(ev[s]); }
+    if (e == cudaSuccess && rc == PB_OK) ck(cudaMemcpy(&found, dcnt.p, 8, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < 2; s++) {
+        if (st[s]) cudaStreamDestroy(st[s]);
+        if (ev[s]) cudaEventDestroy(ev[s]);
+    }
     if (rc != PB_OK) return rc;
     if (e != cudaSuccess) { pb_set_error("pb_identify: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
     *n_found = (size_t)found;
@@ -658,13 +666,19 @@ extern "C" int pb_identify_get_spots(const void* movie, int dtype, size_t n_fram
         return PB_OK;
     };
     if ((rc = alloc_ids(dcap)) || (rc = dcnt.alloc(8))) return rc;
-    cudaStream_t st[2];
-    for (int s = 0; s < 2; s++) PB_CUDA_CHECK(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+    // Every CUDA call below is checked; the first failure is latched in (rc, e) and control falls
+    // through to the common clean-up that waits for and destroys the streams -- no early return
+    // leaks them, and a failed copy can never be mistaken for success through stale buffers.
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    rc = PB_OK;
+    auto ck = [&](cudaError_t err) { if (err != cudaSuccess && e == cudaSuccess) e = err; return e == cudaSuccess && rc == PB_OK; };
+    for (int s = 0; s < 2; s++) ck(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
     auto upload = [&](size_t c) {
         const size_t f0 = c * chunk;
-        if (f0 >= n_frames) return;
+        if (f0 >= n_frames || rc != PB_OK || e != cudaSuccess) return;
         const size_t nf = std::min(chunk, n_frames - f0);
-        pb_h2d(mv[c & 1].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz, st[c & 1]);
+        rc = pb_h2d(mv[c & 1].p, static_cast<const char*>(movie) + f0 * fsz, nf * fsz, st[c & 1]);
     };
     upload(0);
     size_t total = 0;
@@ -672,35 +686,35 @@ extern "C" int pb_identify_get_spots(const void* movie, int dtype, size_t n_fram
     std::vector<long long> hf, hx, hy;
     std::vector<float> hn;
     std::vector<size_t> order;
-    rc = PB_OK;
     const size_t nchunks = (n_frames + chunk - 1) / chunk;
-    for (size_t c = 0; c < nchunks && rc == PB_OK; c++) {
+    for (size_t c = 0; c < nchunks && rc == PB_OK && e == cudaSuccess; c++) {
         const int s = (int)(c & 1);
         const size_t f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
         unsigned long long found = 0;
         for (;;) {   // retry loop if the per-chunk device capacity was too small
-            cudaMemsetAsync(dcnt.p, 0, 8, st[s]);
+            if (!ck(cudaMemsetAsync(dcnt.p, 0, 8, st[s]))) break;
             rc = pb_identify_dev(mv[s].p, dtype, nf, Y, X, frame_offset + (long long)f0, box, min_ng,
                                  roi, static_cast<long long*>(dfr.p), static_cast<long long*>(dx.p),
                                  static_cast<long long*>(dy.p), static_cast<float*>(dng.p), dcap,
                                  static_cast<unsigned long long*>(dcnt.p), st[s]);
             if (rc != PB_OK) break;
-            cudaMemcpyAsync(&found, dcnt.p, 8, cudaMemcpyDeviceToHost, st[s]);
-            cudaStreamSynchronize(st[s]);
+            if (!ck(cudaMemcpyAsync(&found, dcnt.p, 8, cudaMemcpyDeviceToHost, st[s]))) break;
+            if (!ck(cudaStreamSynchronize(st[s]))) break;
             if (found <= dcap) break;
             dcap = (size_t)found;
             if ((rc = alloc_ids(dcap))) break;
         }
-        if (rc != PB_OK) break;
+        if (rc != PB_OK || e != cudaSuccess) break;
         upload(c + 1);   // next chunk streams in while this one is post-processed
+        if (rc != PB_OK) break;
         if (total + found > capacity) overflow = true;
         if (!overflow && found) {
             hf.resize(found); hx.resize(found); hy.resize(found); hn.resize(found); order.resize(found);
-            cudaMemcpyAsync(hf.data(), dfr.p, found * 8, cudaMemcpyDeviceToHost, st[s]);
-            cudaMemcpyAsync(hx.data(), dx.p, found * 8, cudaMemcpyDeviceToHost, st[s]);
-            cudaMemcpyAsync(hy.data(), dy.p, found * 8, cudaMemcpyDeviceToHost, st[s]);
-            cudaMemcpyAsync(hn.data(), dng.p, found * 4, cudaMemcpyDeviceToHost, st[s]);
-            cudaStreamSynchronize(st[s]);
+            ck(cudaMemcpyAsync(hf.data(), dfr.p, found * 8, cudaMemcpyDeviceToHost, st[s]));
+            ck(cudaMemcpyAsync(hx.data(), dx.p, found * 8, cudaMemcpyDeviceToHost, st[s]));
+            ck(cudaMemcpyAsync(hy.data(), dy.p, found * 8, cudaMemcpyDeviceToHost, st[s]));
+            ck(cudaMemcpyAsync(hn.data(), dng.p, found * 4, cudaMemcpyDeviceToHost, st[s]));
+            if (!ck(cudaStreamSynchronize(st[s]))) break;
             std::iota(order.begin(), order.end(), 0);
             std::sort(order.begin(), order.end(), [&](size_t p, size_t q) {
                 if (hf[p] != hf[q]) return hf[p] < hf[q];
@@ -711,21 +725,22 @@ extern "C" int pb_identify_get_spots(const void* movie, int dtype, size_t n_fram
                 frame[total + k] = hf[order[k]]; x[total + k] = hx[order[k]];
                 y[total + k] = hy[order[k]]; ng[total + k] = hn[order[k]];
             }
-            cudaMemcpyAsync(dfr.p, frame + total, found * 8, cudaMemcpyHostToDevice, st[s]);
-            cudaMemcpyAsync(dx.p, x + total, found * 8, cudaMemcpyHostToDevice, st[s]);
-            cudaMemcpyAsync(dy.p, y + total, found * 8, cudaMemcpyHostToDevice, st[s]);
+            ck(cudaMemcpyAsync(dfr.p, frame + total, found * 8, cudaMemcpyHostToDevice, st[s]));
+            ck(cudaMemcpyAsync(dx.p, x + total, found * 8, cudaMemcpyHostToDevice, st[s]));
+            if (!ck(cudaMemcpyAsync(dy.p, y + total, found * 8, cudaMemcpyHostToDevice, st[s]))) break;
             rc = pb_get_spots_dev(mv[s].p, dtype, nf, Y, X, frame_offset + (long long)f0, found,
                                   static_cast<long long*>(dfr.p), static_cast<long long*>(dx.p),
                                   static_cast<long long*>(dy.p), box, baseline, sensitivity, gain,
                                   static_cast<float*>(dsp.p), st[s]);
             if (rc != PB_OK) break;
-            cudaMemcpyAsync(spots + total * pix, dsp.p, found * pix * 4, cudaMemcpyDeviceToHost, st[s]);
-            cudaStreamSynchronize(st[s]);
+            ck(cudaMemcpyAsync(spots + total * pix, dsp.p, found * pix * 4, cudaMemcpyDeviceToHost, st[s]));
+            if (!ck(cudaStreamSynchronize(st[s]))) break;
         }
         total += found;
     }
-    for (int s = 0; s < 2; s++) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); }
-    cudaError_t e = cudaGetLastError();
+    for (int s = 0; s < 2; s++)
+        if (st[s]) { ck(cudaStreamSynchronize(st[s])); cudaStreamDestroy(st[s]); }
+    ck(cudaGetLastError());
     if (rc != PB_OK) return rc;
     if (e != cudaSuccess) { pb_set_error("pb_identify_get_spots: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
     *n_found = total;

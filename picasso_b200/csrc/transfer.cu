@@ -30,8 +30,24 @@ struct Stage {
         return PB_OK;
     }
 };
-std::mutex g_stage_mutex;
-Stage g_up, g_down;      // pinned memory is not tied to a device
+// One staging set per device and direction: the pinned buffers are not tied to a device, but the
+// events recorded on the caller's stream are (cudaEventRecord needs event and stream on the same
+// device), and a process may drive several GPUs (pb_set_device).  Uploads and downloads have
+// separate locks so that one thread's H2D overlaps another thread's D2H.
+constexpr int kMaxDevices = 64;
+struct DevStage {
+    std::mutex up_mutex, down_mutex;
+    Stage up, down;
+};
+DevStage g_stage[kMaxDevices];
+
+int current_stage(DevStage** out) {
+    int dev = 0;
+    PB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) { pb_set_error("device index %d out of range", dev); return PB_ERR_INVALID; }
+    *out = &g_stage[dev];
+    return PB_OK;
+}
 
 unsigned copy_threads() {
     static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -123,9 +139,12 @@ int pb_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
         PB_CUDA_CHECK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
         return PB_OK;
     }
-    std::lock_guard<std::mutex> lk(g_stage_mutex);
-    int rc = g_up.init();
+    DevStage* ds = nullptr;
+    int rc = current_stage(&ds);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ds->up_mutex);
+    Stage& g_up = ds->up;
+    if ((rc = g_up.init())) return rc;
     size_t c = 0;
     for (size_t off = 0; off < bytes; off += kStageBytes, c++) {
         const int b = (int)(c & 1);
@@ -146,9 +165,12 @@ int pb_d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
         PB_CUDA_CHECK(cudaStreamSynchronize(s));
         return PB_OK;
     }
-    std::lock_guard<std::mutex> lk(g_stage_mutex);
-    int rc = g_down.init();
+    DevStage* ds = nullptr;
+    int rc = current_stage(&ds);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ds->down_mutex);
+    Stage& g_down = ds->down;
+    if ((rc = g_down.init())) return rc;
     const size_t nchunks = (bytes + kStageBytes - 1) / kStageBytes;
     for (size_t c = 0; c <= nchunks; c++) {
         if (c < nchunks) {

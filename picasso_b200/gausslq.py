@@ -86,7 +86,7 @@ def fit_spots_parallel(spots, asynch: bool = False):
     stacks the results as in the reference)."""
     if asynch:
         ex = _futures.ThreadPoolExecutor(1)
-        fs = [ex.submit(fit_spots, spots)]
+        fs = [ex.submit(_lib.on_callers_device(fit_spots), spots)]
         ex.shutdown(wait=False)
         return fs
     return fit_spots(spots)

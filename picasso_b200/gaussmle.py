@@ -113,7 +113,7 @@ def gaussmle_async(
             current[0] = last
 
     if N:
-        threading.Thread(target=_run, name="picasso_b200-mle", daemon=True).start()
+        threading.Thread(target=_lib.on_callers_device(_run), name="picasso_b200-mle", daemon=True).start()
     return current, thetas, CRLBs, likelihoods, iterations
 
 

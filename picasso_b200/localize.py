@@ -282,7 +282,7 @@ def identify_async(movie, minimum_ng: float, box: int, *, roi=None, frame_bounds
         return out
 
     executor = ThreadPoolExecutor(1)
-    futures = [executor.submit(_work)]
+    futures = [executor.submit(_lib.on_callers_device(_work))]
     executor.shutdown(wait=False)
     return current, futures
 

@@ -185,3 +185,50 @@ def test_identify_async_matches_identify():
     a = sorted(zip(ids["frame"], ids["y"], ids["x"]))
     b = sorted(zip(ids2["frame"], ids2["y"], ids2["x"]))
     assert a == b and len(a) > 10
+
+
+def test_config3_full_size_vs_oracle(oracle):
+    """BASELINE config 3 at its full size (2000 x 512 x 512 uint16, 60 emitters / frame, box 7,
+    min net gradient 5000): identifications equal to the oracle's as sorted
+    (frame, y, x) tuples with bit-equal float32 net gradients, then the LQ fit of the cut-out ROIs
+    within the LQ tolerance.  The movie is generated in 20 chunks of 100 frames (seeds 1..20) on a
+    thread pool, the oracle runs chunk-wise on the same pool."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    nchunk, per = 20, 100
+    with ThreadPoolExecutor(min(nchunk, os.cpu_count() or 1)) as ex:
+        chunks = list(ex.map(lambda k: testing.synthetic_movie(per, 512, 512, emitters_per_frame=60,
+                                                               seed=1 + k), range(nchunk)))
+        movie = np.concatenate(chunks)
+        del chunks
+        assert movie.shape == (2000, 512, 512) and movie.dtype == np.uint16
+        parts = list(ex.map(lambda k: oracle.identify_movie(movie[k * per:(k + 1) * per], 5000, 7),
+                            range(nchunk)))
+    ofr = np.concatenate([p[0] + k * per for k, p in enumerate(parts)])
+    ox = np.concatenate([p[1] for p in parts]); oy = np.concatenate([p[2] for p in parts])
+    ong = np.concatenate([p[3] for p in parts])
+    ids = localize.identify(movie, 5000, 7, return_info=False)
+    assert len(ids) == len(ofr) and len(ids) > 100_000
+    a = np.lexsort((ids["x"].to_numpy(), ids["y"].to_numpy(), ids["frame"].to_numpy()))
+    b = np.lexsort((ox, oy, ofr))
+    for c, o in (("frame", ofr), ("y", oy), ("x", ox)):
+        np.testing.assert_array_equal(ids[c].to_numpy()[a], o[b])
+    assert (_bits(ids["net_gradient"].to_numpy()[a]) == _bits(ong[b])).all()
+    # ROIs + LQ fit of a 20 k sub-sample against the oracle (bit-exact ROIs, LQ tolerance)
+    cam = {"Baseline": 100, "Sensitivity": 1.0, "Gain": 1, "Pixelsize": 130}
+    sub = ids.iloc[:: max(1, len(ids) // 20000)]
+    spots = localize.get_spots(movie, sub, 7, cam)
+    ospots = oracle.get_spots(movie, sub["frame"].to_numpy(), sub["x"].to_numpy(), sub["y"].to_numpy(), 7, cam)
+    assert (_bits(spots) == _bits(ospots)).all()
+    from picasso_b200 import gausslq
+
+    th = gausslq.fit_spots(spots)
+    oth = oracle.fit_spots_lq(spots, nthreads=os.cpu_count() or 1)
+    d = th.astype(np.float64) - oth
+    rms = np.sqrt((d ** 2).mean(0))
+    assert rms[[0, 1, 4, 5]].max() <= 1e-4, rms
+    # the fused movie -> table path finds the same localizations
+    locs = localize.localize(movie, cam, {"Min. Net Gradient": 5000, "Box Size": 7},
+                             fitting_method="gausslq", return_info=False)
+    assert len(locs) == len(ids)
+    np.testing.assert_array_equal(np.sort(locs["frame"].to_numpy()), np.sort(ofr).astype(np.uint32))

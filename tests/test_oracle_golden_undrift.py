@@ -66,3 +66,19 @@ def test_zero_image_and_edge_window():
     y, x = uo.minimize_shifts(sx, sy)
     np.testing.assert_allclose(x, true, atol=1e-9)
     np.testing.assert_allclose(y, 2 * true, atol=1e-9)
+
+
+def test_config5_reduced_instance_matches_reference(oracle, golden_dir):
+    """Reduced BASELINE config 5 (20 segments x 1024^2, tools/gen_golden.py undrift_c5): the
+    oracle's segment renders and a sample of its per-pair shifts against the real reference."""
+    g = np.load(os.path.join(golden_dir, "undrift_c5.npz"))
+    locs = {k: g[k] for k in ("frame", "x", "y", "lpx", "lpy")}
+    H, W, F = (int(v) for v in g["info_hwf"])
+    info = [{"Height": H, "Width": W, "Frames": F, "Pixelsize": 130}]
+    bounds, segs = uo.segment(locs, info, 100, oracle.render,
+                              {"blur_method": "gaussian", "min_blur_width": 1})
+    np.testing.assert_array_equal(bounds, g["bounds"])
+    np.testing.assert_allclose(segs.sum((1, 2)), g["segment_sums"], rtol=1e-9)
+    for (i, j) in ((0, 1), (0, 19), (7, 12), (18, 19)):
+        sy, sx = uo.get_image_shift(segs[i], segs[j], 5, 32)
+        assert abs(sy - g["pair_shift_y"][i, j]) < 1e-9 and abs(sx - g["pair_shift_x"][i, j]) < 1e-9

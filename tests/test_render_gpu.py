@@ -105,3 +105,27 @@ def test_render_api_contract():
                          "lpx": np.float32([0.1] * 3), "lpy": np.float32([0.1] * 3)})
     n3, _ = pbrender.render(edge, info, disp_px_size=25)
     assert n3 == 1
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+def test_render_config4_subsample_vs_oracle(oracle):
+    """BASELINE config 4 geometry (512 x 512 camera pixels at oversampling 20 -> 10240 x 10240,
+    x, y ~ U(0, 512), lp ~ U(0.02, 0.08), seed 2) on a 2 M-localization sub-sample
+    against the oracle: exact n, rtol 1e-4 on pixels above 1e-3 of the maximum."""
+    rng = np.random.default_rng(2)
+    n = 2_000_000
+    locs = pd.DataFrame({"x": rng.uniform(0, 512, n).astype(np.float32),
+                         "y": rng.uniform(0, 512, n).astype(np.float32),
+                         "lpx": rng.uniform(0.02, 0.08, n).astype(np.float32),
+                         "lpy": rng.uniform(0.02, 0.08, n).astype(np.float32)})
+    info = [{"Height": 512, "Width": 512, "Frames": 1, "Pixelsize": 130}]
+    k, img = pbrender.render(locs, info, oversampling=20, blur_method="gaussian")
+    ok, oimg = oracle.render(locs, info, oversampling=20, blur_method="gaussian")
+    assert k == ok and img.shape == (10240, 10240) and img.dtype == np.float32
+    big = oimg > 1e-3 * oimg.max()
+    np.testing.assert_allclose(img[big], oimg[big], rtol=1e-4)
+    assert abs(float(img.sum(dtype=np.float64)) - float(oimg.sum(dtype=np.float64))) <= 1e-5 * float(oimg.sum(dtype=np.float64))
+    kh, hist = pbrender.render(locs, info, oversampling=20, blur_method=None)
+    okh, ohist = oracle.render(locs, info, oversampling=20, blur_method=None)
+    assert kh == okh
+    np.testing.assert_array_equal(hist, ohist)

@@ -218,3 +218,30 @@ def test_device_peak_fit_edge_cases():
     sy, sx = imageprocess._shifts_of_locs(locs, info, bounds, 1, 32)
     pi, pj = np.triu_indices(6, 1)
     assert (sy[(pi == 2) | (pj == 2)] == 0).all() and (sx[(pi == 2) | (pj == 2)] == 0).all()
+
+
+def test_config5_reduced_instance_golden(golden_dir):
+    """Reduced BASELINE config 5 (20 segments x 1024^2, 190 pairs; the golden
+    per-pair shifts, segment shifts and drift come from the REAL reference run by
+    tools/gen_golden.py undrift_c5).  1024^2 images with a 32 x 32 window take the production
+    path of the full-size configuration: device render of the segments, batched R2C, the
+    FFT-structured pruned inverse transform, device peak fits.  Bar: 1e-3 px."""
+    g = np.load(os.path.join(golden_dir, "undrift_c5.npz"))
+    locs = pd.DataFrame({k: g[k] for k in ("frame", "x", "y", "lpx", "lpy")})
+    H, W, F = (int(v) for v in g["info_hwf"])
+    info = [{"Height": H, "Width": W, "Frames": F, "Pixelsize": 130}]
+    bounds = g["bounds"]
+    n_seg = len(bounds) - 1
+    assert n_seg == 20
+    sy, sx = imageprocess._shifts_of_locs(locs, info, bounds, 1, 32)
+    pi, pj = np.triu_indices(n_seg, 1)
+    np.testing.assert_allclose(sy, g["pair_shift_y"][pi, pj], atol=1e-3)
+    np.testing.assert_allclose(sx, g["pair_shift_x"][pi, pj], atol=1e-3)
+    # the window path (host peak fits) agrees as well
+    ry, rx = imageprocess._rcc_of_locs_windows(locs, info, bounds, 1, 32, lambda i: None)
+    np.testing.assert_allclose(ry, g["rcc_shift_y"], atol=1e-3)
+    np.testing.assert_allclose(rx, g["rcc_shift_x"], atol=1e-3)
+    drift, und = postprocess.undrift(locs, info, 100, display=False,
+                                     segmentation_callback=lambda i: None, rcc_callback=lambda i: None)
+    np.testing.assert_allclose(drift["x"].to_numpy(), g["drift_x"], atol=1e-3)
+    np.testing.assert_allclose(drift["y"].to_numpy(), g["drift_y"], atol=1e-3)
