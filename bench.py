@@ -15,12 +15,21 @@ sigmaxy, eps 1e-3, max_it 100) over one batch of synthetic 7x7 spots
   roofline  algorithmic HBM bytes (252 B/spot) / kernel time vs the measured
             copy bandwidth (the metric asks for HBM GB/s; the fit is FP64-pipe
             bound, see `compute`)
-  cpu_baseline  the CPU oracle (C port of the reference's numba kernel, same
-            arithmetic, bit-identical results) on the host cores, bounded sample
+  e2e_python  the same metric through the signature a picasso caller uses:
+            picasso_b200.gaussmle.gaussmle(pageable numpy array)
+  cpu_baseline  picasso's OWN numba path (gaussmle_async, threads = min(60,
+            0.75 * cores)) from the staged reference module oracle/_ref
+            (kind "reference"), with the oracle C port (same arithmetic,
+            bit-identical results) beside it; the port alone when oracle/_ref or
+            numba is missing (kind "port"); bounded sample
+  stages    BASELINE configs 3 / 4 / 5 (fused localize, 50 M-loc render, 200 x 4096^2
+            undrift) at this world size through picasso_b200.distributed:
+            device-resident and end-to-end seconds, per-phase ms, roofline entry,
+            parity vs a 1-GPU run (tools/stage_bench.py)
 
---impl reference times the reference algorithm on the host CPU (the oracle
-port with all host threads; the Python reference itself cannot travel to the
-GPU box) and prints the same JSON line with "impl": "reference".
+--impl reference times the reference's CPU implementation on the host cores
+(oracle/_ref = picasso's own gaussmle.py staged by oracle/make_ref.py, numba;
+else the oracle port) and prints the same JSON line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -47,17 +56,35 @@ BYTES_PER_SPOT = BOX * BOX * 4 + 56   # 196 B ROI read + 56 B results written (S
 # ~75 % of the step), CRLB + log-likelihood.  Algorithmic bytes of the dominant kernel per spot:
 # ROI 196 + start theta 24 read, theta 24 + iterations 4 written.
 ITER_BYTES_PER_SPOT = BOX * BOX * 4 + 24 + 28
-# dram__bytes_read.sum + dram__bytes_write.sum of tps_iter_kernel<7,1,float> for 4 M spots from
-# the committed `ncu --set full` capture (profiles/r01_mle_tps_ncu.md, v4): 881.3 MB + 103.7 MB
-NCU_ITER_DRAM_BYTES_PER_SPOT = 246.3
+# dram__bytes_read.sum + dram__bytes_write.sum per spot of the dominant kernel come from the committed
+# `ncu --set full` capture (profiles/mle_ncu_compute.json, written by tools/ncu_compute_json.py)
 # all three kernels: 3 ROI reads + 2 theta reads + theta x2, iterations x2, crlb, logL written
 PIPELINE_DRAM_BYTES_PER_SPOT = 3 * BOX * BOX * 4 + 2 * 24 + (24 + 4) * 2 + 28
 
 
-# from profiles/r01_mle_tps_ncu.md (tps_iter_kernel<7,1,float>, 4 M spots)
-COMPUTE_NCU = {"source": "ncu --set full, profiles/r01_mle_tps_ncu.md",
-               "issue_slots_busy_pct": 71.4, "fp64_pipe_busy_pct": 41.9, "fma_pipe_busy_pct": 27.7,
-               "xu_pipe_busy_pct": 33.6, "warp_instructions_per_spot": 1119}
+
+def compute_from_profile():
+    """Instruction-side view of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/mle_ncu_compute.json).  The capture records the SHA-256 of the MLE kernel sources it
+    was taken at; `stale` says whether the sources on disk still are those."""
+    path = os.path.join(ROOT, "profiles", "mle_ncu_compute.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except Exception as exc:        # noqa: BLE001
+        return {"source": None, "note": f"no ncu capture committed ({exc})"}
+    d["stale"] = d.get("kernel_source_sha256") != mle_kernel_source_hash()
+    return d
+
+
+def mle_kernel_source_hash():
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in ("mle_tps.cu", "mle_tps_core.cuh"):
+        with open(os.path.join(ROOT, "picasso_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 def parse():
@@ -70,6 +97,8 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-stages", action="store_true", help="skip the configs 3/4/5 stage block")
+    p.add_argument("--stages", default="localize,render,undrift")
     return p.parse_args()
 
 
@@ -193,21 +222,88 @@ def cpu_oracle_rate(seconds: float, threads: int):
     return done / el, done, el, use
 
 
+_REF = {}
+
+
+def numba_reference():
+    """picasso's own gaussmle module staged under oracle/_ref (None when unavailable)."""
+    if "gm" not in _REF:
+        try:
+            from oracle import make_ref
+
+            make_ref.build()          # no-op on the GPU box (no /root/reference there)
+            gm = make_ref.import_gaussmle()
+            from picasso_b200 import testing
+
+            t0 = time.perf_counter()
+            gm.gaussmle(testing.synthetic_spots(64, BOX, seed=1), EPS, MAX_IT, METHOD)      # JIT warm-up
+            _REF["jit_s"] = time.perf_counter() - t0
+            _REF["gm"] = gm
+        except Exception as exc:      # noqa: BLE001
+            print(f"[bench] numba reference unavailable: {exc}", file=sys.stderr)
+            _REF["gm"] = None
+            _REF["why"] = str(exc)
+    return _REF["gm"]
+
+
+def cpu_numba_rate(seconds: float):
+    """Time the reference's gaussmle_async (numba, nogil threads = min(60, 0.75 * cores),
+    gaussmle.py:478-530) to completion on a bounded sample of the same workload."""
+    import multiprocessing
+
+    from picasso_b200 import testing
+
+    gm = numba_reference()
+    workers = min(60, max(1, int(0.75 * multiprocessing.cpu_count())))
+
+    def run(spots):
+        t0 = time.perf_counter()
+        cur, th, cr, ll, it = gm.gaussmle_async(spots, EPS, MAX_IT, METHOD)
+        while not bool((it != 0).all()):           # every fit takes >= 1 iteration
+            time.sleep(0.002)
+        return time.perf_counter() - t0
+
+    probe = testing.synthetic_spots(4000, BOX, seed=777)
+    rate = len(probe) / run(probe)
+    per_call = int(max(4000, min(2_000_000, rate * max(seconds, 1.0) / 3)))
+    spots = testing.synthetic_spots(per_call, BOX, seed=12345)
+    done, el = 0, 0.0
+    while el < seconds:
+        el += run(spots)
+        done += per_call
+    return done / el, done, el, workers
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm on the host CPU (oracle port)."""
+    """--impl reference: the reference's CPU implementation on the host cores -- picasso's own
+    numba gaussmle_async from oracle/_ref when it is staged, else the oracle C port."""
     if rank != 0:
         return
     cpu = host_cpu_info()
     threads = cpu["threads_used"]
     per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    use_numba = numba_reference() is not None
     rates, n_done, t_tot = [], 0, 0.0
     for i in range(args.warmup + args.steps):
-        r, d, el, used = cpu_oracle_rate(per_step_budget, threads)
+        if use_numba:
+            r, d, el, used = cpu_numba_rate(per_step_budget)
+        else:
+            r, d, el, used = cpu_oracle_rate(per_step_budget, threads)
         if i >= args.warmup:
             rates.append(r)
             n_done += d
             t_tot += el
     value = n_done / t_tot
+    if use_numba:
+        kind = "reference"
+        sample = (f"{n_done} spots in {t_tot:.1f} s: picasso.gaussmle.gaussmle_async (the reference's own "
+                  f"numba code from oracle/_ref, {used} nogil threads = min(60, 0.75 * cpu_count), "
+                  f"after a {_REF.get('jit_s', 0):.0f} s JIT warm-up)")
+    else:
+        kind = "port"
+        sample = (f"{n_done} spots in {t_tot:.1f} s, oracle C port of picasso.gaussmle._mlefit_sigmaxy "
+                  "(bit-identical to the numba reference), pthreads; oracle/_ref unavailable: "
+                  + _REF.get("why", "?"))
     line = {
         "impl": "reference", "metric": "MLE spot-fits/sec (7x7 ROI)", "value": value,
         "unit": "fits/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -216,11 +312,8 @@ def run_reference(args, rank, world):
         "data": "synthetic",
         "config": {"workload": "configs[1]: 7x7 MLE sigmaxy eps=1e-3 max_it=100 (bounded CPU sample)",
                    "box": BOX, "method": METHOD},
-        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": used, "kind": "port",
-                         "host": cpu,
-                         "sample": f"{n_done} spots in {t_tot:.1f} s, oracle C port of "
-                                   "picasso.gaussmle._mlefit_sigmaxy (bit-identical to the numba "
-                                   "reference), pthreads"},
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": used, "kind": kind,
+                         "host": cpu, "sample": sample},
         "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -501,16 +594,53 @@ def main():
         for h in (hs, hth, hcr, hll, hit):
             h.free()
 
+        # ---- the signature a picasso caller uses: gaussmle.gaussmle(pageable ndarray) ----
+        from picasso_b200 import gaussmle as pb_gaussmle
+
+        hp = spots.cpu().numpy()              # ordinary pageable memory
+        for _ in range(2):
+            pb_gaussmle.gaussmle(hp, EPS, MAX_IT, METHOD)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pth, pcr, pll, pit = pb_gaussmle.gaussmle(hp, EPS, MAX_IT, METHOD)
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_python = {"value": ne * world * args.steps / tt.item(), "unit": "fits/s",
+                      "call": "picasso_b200.gaussmle.gaussmle(spots: pageable float32 ndarray, 0.001, 100, "
+                              "'sigmaxy') -> 4 ndarrays (page-locked, pooled)",
+                      "h2d_bytes_per_step": ne * BOX * BOX * 4, "d2h_bytes_per_step": ne * 56,
+                      "matches_device_run": bool(np.array_equal(pit, it.cpu().numpy()))}
+        del hp, pth, pcr, pll, pit
+    else:
+        e2e_python = None
+
+    stages = None
+    if not args.no_stages:
+        del spots, flats
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import stage_bench
+
+        stages = stage_bench.run_stages(torch, dist if world > 1 else None, rank, world, dev, measured_peaks()[0],
+                                        which=[w for w in args.stages.split(",") if w])
+
     if rank == 0:
         peak, peak_src = measured_peaks()
+        comp = compute_from_profile()
         tps = ms_iter > 0
         n_launch = pb[parts] - pb[parts - 1]     # spots of the last pb_mle_fit_dev call (profiled one)
         if tps:
             ach = ITER_BYTES_PER_SPOT * n_launch / (ms_iter * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "tps_iter_kernel<7,1,float> (Newton iterations)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": NCU_ITER_DRAM_BYTES_PER_SPOT * n_launch, "spots_per_launch": n_launch,
-                    "traffic_source": "ncu --set full, profiles/r01_mle_tps_ncu.md (bytes/spot x spots per launch)",
+                    "traffic": (comp.get("dram_bytes_per_spot") * n_launch
+                                if comp.get("dram_bytes_per_spot") else None),
+                    "spots_per_launch": n_launch,
+                    "traffic_source": "ncu --set full, profiles/mle_ncu_compute.json (bytes/spot x spots per launch)"
+                                      + (" -- STALE capture" if comp.get("stale") else ""),
                     "algorithmic_bytes": ITER_BYTES_PER_SPOT * n_launch, "peak_source": peak_src,
                     "kernel_ms": ms_iter,
                     "step_kernels_ms": {"tps_init_kernel": ms_init, "tps_iter_kernel": ms_iter,
@@ -551,19 +681,34 @@ def main():
             "roofline": roof,
             # instruction-side view of the dominant kernel from the committed ncu --set full
             # capture (profiles/r01_mle_tps_ncu.md): what actually bounds the fit
-            "compute": COMPUTE_NCU,
+            "compute": comp,
             "clocks": clocks, "gpu_launches": launches,
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if e2e_python is not None:
+            line["e2e_python"] = e2e_python
+        if stages is not None:
+            line["stages"] = stages
         if not args.no_cpu:
             cpu = host_cpu_info()
             threads = cpu["threads_used"]
-            r, d, el, used = cpu_oracle_rate(args.cpu_seconds, threads)
-            line["cpu_baseline"] = {
-                "value": r, "unit": "fits/s", "cores": used, "kind": "port", "host": cpu,
-                "sample": f"{d} spots in {el:.1f} s (same distribution), oracle C port of "
-                          "picasso.gaussmle._mlefit_sigmaxy, bit-identical to the numba reference"}
+            r, d, el, used = cpu_oracle_rate(args.cpu_seconds / 2, threads)
+            port = {"value": r, "unit": "fits/s", "cores": used, "kind": "port",
+                    "sample": f"{d} spots in {el:.1f} s (same distribution), oracle C port of "
+                              "picasso.gaussmle._mlefit_sigmaxy, bit-identical to the numba reference"}
+            if numba_reference() is not None:
+                r2, d2, el2, used2 = cpu_numba_rate(args.cpu_seconds / 2)
+                line["cpu_baseline"] = {
+                    "value": r2, "unit": "fits/s", "cores": used2, "kind": "reference", "host": cpu,
+                    "sample": f"{d2} spots in {el2:.1f} s (same distribution): picasso.gaussmle.gaussmle_async, "
+                              f"the reference's own numba code staged in oracle/_ref, {used2} nogil threads = "
+                              "min(60, 0.75 * cpu_count) (gaussmle.py:503), after a JIT warm-up call",
+                    "port": port}
+            else:
+                port["host"] = cpu
+                port["numba_reference_unavailable"] = _REF.get("why", "?")
+                line["cpu_baseline"] = port
         _emit(line)
     if pg is not None:
         pg.close()

@@ -187,6 +187,12 @@ int pb_localize(const void* movie, int dtype, size_t n_frames, int Y, int X, lon
                 int box, double min_ng, const int* roi, float baseline, float sensitivity,
                 float gain, int fit, double eps, int max_it, int em, void* columns,
                 size_t capacity, size_t* n_found);
+/* Same with the movie and the column block resident in HBM (multi-GPU frame shards, benchmarks
+ * without PCIe); synchronous: the identification count of every chunk is read back. */
+int pb_localize_dev(const void* d_movie, int dtype, size_t n_frames, int Y, int X,
+                    long long frame_offset, int box, double min_ng, const int* roi, float baseline,
+                    float sensitivity, float gain, int fit, double eps, int max_it, int em,
+                    void* d_columns, size_t capacity, size_t* n_found);
 /* The column arithmetic alone (numpy's evaluation order and dtypes, float32 IEEE operations):
  * identifications + fit results -> the columns above.  crlbs / logliks / iterations are read
  * for fit 0/1 only; for fit 3 `thetas` is in the Gpufit layout [photons, x, y, sx, sy, bg].
@@ -307,6 +313,33 @@ int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_l
                   double x_max, double min_blur_width, int mode, float* d_image, int n_pixel_y,
                   int n_pixel_x, unsigned long long* d_count, void* d_workspace,
                   size_t workspace_bytes, void* stream);
+/* Multi-GPU rendering by image row bands (SURVEY.md 8e option B; render.py:1020 _render_gaussian is
+ * what is being sharded).  pb_render_band_dev renders rows [row0, row0 + n_rows) of the image:
+ * d_image holds n_rows x n_pixel_x floats, windows are clipped to the band, *d_count counts the
+ * in-view localisations whose centre row lies in the band (the counts of disjoint bands add up to
+ * the reference's n; the bands concatenate to the full image).  pb_render_band_count_dev /
+ * pb_render_band_scatter_dev bucket a rank's share of the localisations by destination band
+ * (band b = rows [band_rows[b], band_rows[b+1]), host array of n_bands + 1 ints, <= 64 bands): a
+ * localisation goes to every band its 3-sigma window can reach; the scatter writes band b's
+ * records at d_offsets[b] of the four send columns (the exchange itself is an NCCL all-to-all). */
+int pb_render_band_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
+                       const float* d_lpy, double oversampling, double y_min, double x_min,
+                       double y_max, double x_max, double min_blur_width, int mode, float* d_image,
+                       int n_pixel_y, int n_pixel_x, int row0, int n_rows,
+                       unsigned long long* d_count, void* d_workspace, size_t workspace_bytes,
+                       void* stream);
+int pb_render_band_count_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
+                             const float* d_lpy, double oversampling, double y_min, double x_min,
+                             double y_max, double x_max, double min_blur_width, int mode,
+                             int n_pixel_y, int n_pixel_x, int n_bands, const int* band_rows,
+                             unsigned long long* d_counts, void* stream);
+int pb_render_band_scatter_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
+                               const float* d_lpy, double oversampling, double y_min, double x_min,
+                               double y_max, double x_max, double min_blur_width, int mode,
+                               int n_pixel_y, int n_pixel_x, int n_bands, const int* band_rows,
+                               const unsigned long long* d_offsets, unsigned long long* d_cursor,
+                               float* d_out_x, float* d_out_y, float* d_out_lpx, float* d_out_lpy,
+                               void* stream);
 
 /* ---- RCC cross-correlation ----------------------------------------------------
  * Replaces the FFT work of picasso.imageprocess.xcorr / get_image_shift / rcc
@@ -332,6 +365,13 @@ int pb_rcc_spectra_dev(int n_seg, int Y, int X, const float* d_segments, void* d
 int pb_rcc_windows_dev(int n_pairs, const int* d_pair_i, const int* d_pair_j, int Y, int X,
                        const void* d_spectra, int Y0, int X0, int H, int W, float* d_windows,
                        int batch, void* d_workspace, size_t workspace_bytes, void* stream);
+/* the per-pair body of get_image_shift (imageprocess.py:103-157) on device windows: 32 float64 per
+ * pair = {status (0 fitted, 1 refit on the host, 2 window touches the crop edge -> (0,0), 3 odd
+ * cut-out), arg-max y, arg-max x, xc, yc, the 5 x 5 window, padding} */
+int pb_rcc_peakfit_dev(int n_pairs, const float* d_windows, int H, int W, double* d_records,
+                       void* stream);
+/* segments per L2 pair tile for images of Y rows (pairs sorted by (i / TS, j / TS) run tile by tile) */
+int pb_rcc_tile_segments(int Y);
 
 /* Fused front end of postprocess.undrift (picasso/postprocess.py:2903-2961 = segment
  * :2846-2900 + imageprocess.rcc :160-217): segment images are rendered on the device

@@ -106,6 +106,87 @@ def launch_count() -> int:
     return int(load().pb_launch_count())
 
 
+# ---- pooled pinned output arrays -------------------------------------------------------------
+# The arrays the Python layer RETURNS (thetas, CRLBs, images, column blocks) are allocated by this
+# layer, so they can live in page-locked memory: the device -> host copy is then one direct DMA at
+# PCIe speed instead of a staged copy into freshly mapped pageable pages (first-touch page faults
+# cap that at ~25 GB/s).  cudaHostAlloc itself is slow (page pinning, ~0.2 s / GB), so blocks are
+# recycled through a small pool: when the last numpy view of a block is garbage collected the
+# block goes back to the pool (bounded by PB_PINNED_POOL_MB, default 4096) instead of being freed.
+import threading as _threading
+
+_POOL_LOCK = _threading.Lock()
+_POOL = []                       # [(nbytes, ptr)] free blocks
+_POOL_BYTES = 0
+_POOL_LIMIT = int(os.environ.get("PB_PINNED_POOL_MB", "4096")) << 20
+_PINNED_MAX = int(os.environ.get("PB_PINNED_MAX_MB", "8192")) << 20   # larger outputs stay pageable
+
+
+class _PinnedBlock:
+    """Owner of one page-locked block; numpy views keep it alive through ``__array_interface__``."""
+
+    __slots__ = ("ptr", "nbytes", "__array_interface__", "__weakref__")
+
+    def __init__(self, nbytes: int):
+        global _POOL_BYTES
+        self.ptr = None
+        with _POOL_LOCK:
+            best = None
+            for k, (sz, _) in enumerate(_POOL):
+                if sz >= nbytes and sz <= max(nbytes + (nbytes >> 2), nbytes + (1 << 20)):
+                    if best is None or sz < _POOL[best][0]:
+                        best = k
+            if best is not None:
+                sz, p = _POOL.pop(best)
+                _POOL_BYTES -= sz
+                self.ptr, self.nbytes = p, sz
+        if self.ptr is None:
+            p = C.c_void_p()
+            check(load().pb_host_alloc(C.byref(p), max(nbytes, 1)))
+            self.ptr, self.nbytes = p.value, max(nbytes, 1)
+        self.__array_interface__ = {"shape": (max(nbytes, 1),), "typestr": "|u1",
+                                    "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        global _POOL_BYTES
+        try:
+            p, self.ptr = self.ptr, None
+            if p is None:
+                return
+            with _POOL_LOCK:
+                if _POOL_BYTES + self.nbytes <= _POOL_LIMIT:
+                    _POOL.append((self.nbytes, p))
+                    _POOL_BYTES += self.nbytes
+                    return
+            load().pb_host_free(C.c_void_p(p))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """``np.empty(shape, dtype)`` backed by pooled page-locked memory (plain ``np.empty`` for empty or
+    very large arrays, or when PB_PINNED_OUTPUTS=0).  The block returns to the pool when the array
+    and all its views are gone."""
+    dtype = np.dtype(dtype)
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape)) if shape else 1
+    nbytes = n * dtype.itemsize
+    if nbytes == 0 or nbytes > _PINNED_MAX or os.environ.get("PB_PINNED_OUTPUTS", "1") == "0":
+        return np.empty(shape, dtype)
+    blk = _PinnedBlock(nbytes)
+    return np.asarray(blk)[:nbytes].view(dtype).reshape(shape)
+
+
+def pinned_pool_trim() -> None:
+    """Free every cached block of the pinned pool."""
+    global _POOL_BYTES
+    with _POOL_LOCK:
+        blocks, _POOL[:] = list(_POOL), []
+        _POOL_BYTES = 0
+    for _, p in blocks:
+        load().pb_host_free(C.c_void_p(p))
+
+
 class PinnedArray:
     """A numpy array backed by pinned (page-locked) host memory from pb_host_alloc."""
 

@@ -267,10 +267,12 @@ extern "C" int pb_locs_from_fits(size_t n, int fit, int box, int em, const long 
     return PB_OK;
 }
 
-extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y, int X,
-                           long long frame_offset, int box, double min_ng, const int* roi,
-                           float baseline, float sensitivity, float gain, int fit, double eps,
-                           int max_it, int em, void* columns, size_t capacity, size_t* n_found) {
+// on_device: `movie` and `columns` are device pointers (pb_localize_dev): no upload, the finished
+// columns are copied device -> device; everything else is the same pipeline.
+static int localize_impl(bool on_device, const void* movie, int dtype, size_t n_frames, int Y, int X,
+                         long long frame_offset, int box, double min_ng, const int* roi,
+                         float baseline, float sensitivity, float gain, int fit, double eps,
+                         int max_it, int em, void* columns, size_t capacity, size_t* n_found) {
     if (!n_found) { pb_set_error("pb_localize: n_found is null"); return PB_ERR_INVALID; }
     *n_found = 0;
     if (fit < 0 || fit > 3) { pb_set_error("pb_localize: fit must be 0 (MLE sigma), 1 (MLE sigmaxy), 2 (LQ) or 3 (LQ, Gpufit layout)"); return PB_ERR_INVALID; }
@@ -293,8 +295,8 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
         if (v >= 1) chunk = (size_t)v;
     }
     chunk = std::min(chunk, std::min<size_t>(n_frames, (size_t)1 << 22));
-    const bool pinned_src = pb_host_is_pinned(movie);
-    for (int s = 0; s < 2; s++) {
+    const bool pinned_src = on_device || pb_host_is_pinned(movie);
+    for (int s = 0; s < 2 && !on_device; s++) {
         if ((rc = P->mv[s].grow(chunk * fsz))) return rc;
         if (!pinned_src && (rc = P->stage[s].grow(chunk * fsz))) return rc;
     }
@@ -336,7 +338,7 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
 
     const size_t nchunks = (n_frames + chunk - 1) / chunk;
     auto upload = [&](size_t c) -> int {
-        if (c >= nchunks) return PB_OK;
+        if (c >= nchunks || on_device) return PB_OK;
         const int s = (int)(c & 1);
         const size_t f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
         const char* src = static_cast<const char*>(movie) + f0 * fsz;
@@ -373,12 +375,14 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
         const int s = (int)(c & 1);
         const size_t f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
         const long long foff = frame_offset + (long long)f0;
-        PB_CUDA_CHECK(cudaStreamWaitEvent(cs, P->up[s], 0));
+        const void* mvp = on_device ? static_cast<const void*>(static_cast<const char*>(movie) + f0 * fsz)
+                                    : P->mv[s].p;
+        if (!on_device) PB_CUDA_CHECK(cudaStreamWaitEvent(cs, P->up[s], 0));
         bool next_uploaded = false;
         unsigned long long found = 0;
         for (;;) {   // retried only when the per-chunk device capacity was too small
             PB_CUDA_CHECK(cudaMemsetAsync(P->counter.p, 0, 8, cs));
-            rc = pb_identify_dev(P->mv[s].p, dtype, nf, Y, X, foff, box, min_ng, roi, uf, ux, uy, ung,
+            rc = pb_identify_dev(mvp, dtype, nf, Y, X, foff, box, min_ng, roi, uf, ux, uy, ung,
                                  dcap, static_cast<unsigned long long*>(P->counter.p), cs);
             if (rc != PB_OK) return rc;
             PB_CUDA_CHECK(cudaMemcpyAsync((void*)hcount, P->counter.p, 8, cudaMemcpyDeviceToHost, cs));
@@ -406,7 +410,7 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
             }
             gather_ids_kernel<<<g, 256, 0, cs>>>(i_out, n, uf, ux, uy, ung, sf, sx, sy, sng);
             g_pb_launches += 3;
-            if ((rc = pb_get_spots_dev(P->mv[s].p, dtype, nf, Y, X, foff, n, sf, sx, sy, box, baseline,
+            if ((rc = pb_get_spots_dev(mvp, dtype, nf, Y, X, foff, n, sf, sx, sy, box, baseline,
                                        sensitivity, gain, d_sp, cs)))
                 return rc;
             PB_CUDA_CHECK(cudaEventRecord(P->cut[s], cs));
@@ -416,6 +420,10 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
             if ((rc = pb_locs_from_fits_dev(n, fit == 3 ? 4 : fit, box, em, sf, sx, sy, sng, d_th, d_cr, d_ll, d_it,
                                             P->cols.p, dcap, cs)))
                 return rc;
+            if (on_device) {
+                PB_CUDA_CHECK(cudaMemcpy2DAsync(static_cast<char*>(columns) + total * 4, capacity * 4, P->cols.p,
+                                                dcap * 4, (size_t)n * 4, ncols, cudaMemcpyDeviceToDevice, cs));
+            } else {
             if ((rc = drain(s))) return rc;                       // chunk c-2 used this landing buffer
             if ((rc = P->hcols[s].grow((size_t)ncols * n * 4))) return rc;
             PB_CUDA_CHECK(cudaMemcpy2DAsync(P->hcols[s].p, (size_t)n * 4, P->cols.p, dcap * 4, (size_t)n * 4,
@@ -423,6 +431,7 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
             PB_CUDA_CHECK(cudaEventRecord(P->d2h[s], cs));
             pend[s].on = true; pend[s].at = total; pend[s].n = n; pend[s].pitch = n;
             if ((rc = drain(s ^ 1))) return rc;                   // previous chunk: long finished
+            }
             // the id / fit / column buffers are reused by the next chunk on the same stream: in order
         } else {
             PB_CUDA_CHECK(cudaEventRecord(P->cut[s], cs));
@@ -439,4 +448,22 @@ extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y,
         return PB_ERR_CAPACITY;
     }
     return PB_OK;
+}
+
+extern "C" int pb_localize(const void* movie, int dtype, size_t n_frames, int Y, int X,
+                           long long frame_offset, int box, double min_ng, const int* roi,
+                           float baseline, float sensitivity, float gain, int fit, double eps,
+                           int max_it, int em, void* columns, size_t capacity, size_t* n_found) {
+    return localize_impl(false, movie, dtype, n_frames, Y, X, frame_offset, box, min_ng, roi, baseline,
+                         sensitivity, gain, fit, eps, max_it, em, columns, capacity, n_found);
+}
+
+// Device-resident variant: `d_movie` (n_frames, Y, X) and `d_columns` (ncols, capacity) live in
+// HBM.  Synchronous like pb_localize (the identification count of every chunk is read back).
+extern "C" int pb_localize_dev(const void* d_movie, int dtype, size_t n_frames, int Y, int X,
+                               long long frame_offset, int box, double min_ng, const int* roi,
+                               float baseline, float sensitivity, float gain, int fit, double eps,
+                               int max_it, int em, void* d_columns, size_t capacity, size_t* n_found) {
+    return localize_impl(true, d_movie, dtype, n_frames, Y, X, frame_offset, box, min_ng, roi, baseline,
+                         sensitivity, gain, fit, eps, max_it, em, d_columns, capacity, n_found);
 }

@@ -679,6 +679,26 @@ int rcc_tile_mb() {
 
 }  // namespace
 
+// Segments per pair tile: 2 * TS spectrum slabs of 32 columns x Y rows stay L2 resident while the
+// TS^2 pairs of a tile read them.  Multi-GPU callers hand each rank whole tiles (contiguous ranges
+// of the pair list sorted by (i / TS, j / TS)) so the L2 reuse survives the partition.
+extern "C" int pb_rcc_tile_segments(int Y) {
+    const size_t slab = (size_t)32 * (size_t)std::max(Y, 1) * sizeof(float2);
+    return (int)std::max<size_t>(2, std::min<size_t>(64, ((size_t)rcc_tile_mb() << 20) / (2 * slab)));
+}
+
+// arg-max + 5 x 5 cut-out + Gaussian peak fit of n_pairs correlation windows (H x W float32 each)
+// on the device: 32 doubles per pair (status, arg-max y / x, xc, yc, the 5 x 5 window).
+extern "C" int pb_rcc_peakfit_dev(int n_pairs, const float* d_windows, int H, int W, double* d_records,
+                                  void* stream) {
+    if (n_pairs <= 0) return PB_OK;
+    if (!d_windows || !d_records || H < 1 || W < 1) { pb_set_error("pb_rcc_peakfit_dev: bad argument"); return PB_ERR_INVALID; }
+    rcc_peakfit_kernel<<<(n_pairs + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_windows, n_pairs, H, W, d_records);
+    g_pb_launches++;
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
 extern "C" int pb_rcc_set_mode(int mode) {
     if (mode < -1 || mode > 1) { pb_set_error("pb_rcc_set_mode: mode must be -1, 0 or 1"); return PB_ERR_INVALID; }
     g_rcc_mode.store(mode);
@@ -747,8 +767,7 @@ extern "C" int pb_rcc_windows_dev(int n_pairs, const int* d_pair_i, const int* d
             PB_CUDA_CHECK(cudaMemcpyAsync(hi.data(), d_pair_i, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, s));
             PB_CUDA_CHECK(cudaMemcpyAsync(hj.data(), d_pair_j, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, s));
             PB_CUDA_CHECK(cudaStreamSynchronize(s));
-            const size_t slab = (size_t)32 * Y * sizeof(float2);
-            int TS = (int)std::max<size_t>(2, std::min<size_t>(64, ((size_t)rcc_tile_mb() << 20) / (2 * slab)));
+            const int TS = pb_rcc_tile_segments(Y);
             std::vector<int> order(n_pairs);
             for (int k = 0; k < n_pairs; k++) order[k] = k;
             auto key = [&](int k) { return ((long long)(hi[k] / TS) << 32) | (unsigned)(hj[k] / TS); };

@@ -44,10 +44,19 @@ struct RenderArgs {
     double os, y_min, x_min, y_max, x_max;
     float osf, mbw;
     int mode;              // 0 hist, 1 gaussian, 2 gaussian_iso
-    float* image;
+    float* image;                // rows [row0, row0 + nrows) of the npy x npx image
     int npy, npx;
-    unsigned long long* count;   // localisations in view
+    unsigned long long* count;   // localisations in view (whose centre row lies in the band)
+    int row0, nrows;             // row band held by `image` (full render: 0, npy)
 };
+
+// A localisation is COUNTED by the band that holds its centre pixel row, so that the counts of
+// disjoint bands add up to the reference's n; it is DRAWN by every band its window reaches.
+__device__ __forceinline__ bool centre_in_band(const RenderArgs& a, double y_) {
+    int py = (int)y_;
+    py = min(max(py, 0), a.npy - 1);
+    return py >= a.row0 && py < a.row0 + a.nrows;
+}
 
 struct Splat {            // everything _draw_gaussian_loc derives for one localisation
     double x_, y_, inv_2sx2, inv_2sy2, norm;
@@ -95,10 +104,10 @@ __global__ void render_hist_kernel(const RenderArgs a) {
          k += (long long)gridDim.x * blockDim.x) {
         const Splat s = make_splat(a, k);
         if (s.in_view) {
-            local++;
+            if (centre_in_band(a, s.y_)) local++;
             const int i = (int)s.x_, j = (int)s.y_;      // x.astype(int32): truncation
-            if (j >= 0 && j < a.npy && i >= 0 && i < a.npx)
-                atomicAdd(a.image + (size_t)j * a.npx + i, 1.0f);
+            if (j >= a.row0 && j < a.row0 + a.nrows && j < a.npy && i >= 0 && i < a.npx)
+                atomicAdd(a.image + (size_t)(j - a.row0) * a.npx + i, 1.0f);
         }
     }
     // block-aggregated count
@@ -126,8 +135,10 @@ __global__ void render_splat_kernel(const RenderArgs a) {
         Splat s;
         s.in_view = false;
         if (k < a.n) s = make_splat(a, k);
-        if (s.in_view && g == 0) local++;
+        if (s.in_view && g == 0 && centre_in_band(a, s.y_)) local++;
         if (!s.in_view) continue;
+        s.i_min = max(s.i_min, a.row0);                 // clip the window rows to the band
+        s.i_max = min(s.i_max, a.row0 + a.nrows);
         const int nx = s.j_max - s.j_min, ny = s.i_max - s.i_min;
         if (nx <= 0 || ny <= 0) continue;
         // lane g evaluates ONE column kernel value and ONE row kernel value per 8x8 chunk;
@@ -142,7 +153,7 @@ __global__ void render_splat_kernel(const RenderArgs a) {
                 for (int rr = 0; rr < nr; rr++) {
                     const float gy = __shfl_sync(gmask, gy_mine, rr, kLanes);
                     if (jok)
-                        atomicAdd(a.image + (size_t)(s.i_min + i0 + rr) * a.npx + j, __fmul_rn(gy, gx));
+                        atomicAdd(a.image + (size_t)(s.i_min + i0 + rr - a.row0) * a.npx + j, __fmul_rn(gy, gx));
                 }
             }
         }
@@ -170,16 +181,23 @@ __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restri
         const bool in_view = (xv > a.x_min) && (yv > a.y_min) && (xv < a.x_max) && (yv < a.y_max);
         int t = -1;
         if (in_view) {
-            local++;
-            int px = (int)(a.os * (xv - a.x_min)), py = (int)(a.os * (yv - a.y_min));
+            const double y_ = a.os * (yv - a.y_min);
+            int px = (int)(a.os * (xv - a.x_min)), py = (int)y_;
             px = min(max(px, 0), a.npx - 1);
             py = min(max(py, 0), a.npy - 1);
+            if (py >= a.row0 && py < a.row0 + a.nrows) local++;
             // bin = (tile, window-size class): threads of a warp then splat windows of similar
             // size (a warp runs as long as its widest window: 3..11 px across at config 4)
             const float sg = __fmul_rn(a.osf, fmaxf(fmaxf(a.lpx[k], a.lpy[k]), a.mbw));
             const int cls = sg < 0.75f ? 0 : sg < 1.05f ? 1 : sg < 1.4f ? 2 : 3;
-            t = ((py / kTile) * tiles_x + (px / kTile)) * kSizeClasses + cls;
-            atomicAdd(tile_count + t, 1u);
+            // row band: localisations centred outside the band whose 3-sigma window reaches into it
+            // (conservative test; the accumulation pass clips exactly) go to the nearest band tile
+            const double reach = 3.0 * (double)sg + 2.0;
+            if (y_ + reach >= (double)a.row0 && y_ - reach <= (double)(a.row0 + a.nrows)) {
+                const int pyb = min(max(py, a.row0), a.row0 + a.nrows - 1) - a.row0;
+                t = ((pyb / kTile) * tiles_x + (px / kTile)) * kSizeClasses + cls;
+                atomicAdd(tile_count + t, 1u);
+            }
         }
         tile_of[k] = t;
     }
@@ -255,7 +273,8 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
     // the tile's localisations: its kSizeClasses consecutive bins, narrow windows first
     const unsigned int first = start[tile * kSizeClasses], last = start[(tile + 1) * kSizeClasses];
     if (first == last) return;
-    const int ty0 = (tile / tiles_x) * kTile, tx0 = (tile % tiles_x) * kTile;
+    const int ty0 = a.row0 + (tile / tiles_x) * kTile, tx0 = (tile % tiles_x) * kTile;
+    const int band_end = a.row0 + a.nrows;
     for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) acc[q] = 0.0f;
     __syncthreads();
     const int tid = threadIdx.x;
@@ -276,6 +295,9 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
         const int j_max = min((int)(x_ + mox) + 1, a.npx);
         const int nx = j_max - j_min, ny = i_max - i_min;
         if (nx <= 0 || ny <= 0) continue;
+        const int ii0 = max(a.row0 - i_min, 0);                   // window rows inside the band
+        const int ii1 = min(band_end - i_min, ny);
+        if (ii0 >= ii1) continue;
         const float inv_2sx2 = 1.0f / (2.0f * sx * sx);
         const float inv_2sy2 = 1.0f / (2.0f * sy * sy);
         const float norm = 1.0f / (6.2831853071795862f * sx * sy);
@@ -288,12 +310,12 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
                 gxs[jj][tid] = expf(-dx * dx * inv_2sx2);
             }
 #pragma unroll 1
-            for (int ii = 0; ii < ny; ii++) {
+            for (int ii = ii0; ii < ii1; ii++) {
                 const float dy = dy0 + (float)ii;
                 const float gy = norm * expf(-dy * dy * inv_2sy2);
                 const int i = i_min + ii;
                 const bool iin = (i >= ty0) && (i < ty0 + kTile);
-                float* grow = a.image + (size_t)i * a.npx;
+                float* grow = a.image + (size_t)(i - a.row0) * a.npx;
                 float* srow = acc + (i - ty0) * kTile - tx0;
 #pragma unroll 1
                 for (int jj = 0; jj < nx; jj++) {
@@ -304,12 +326,12 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
                 }
             }
         } else {   // very wide kernels (sigma > 2.5 display px): no column cache
-            for (int ii = 0; ii < ny; ii++) {
+            for (int ii = ii0; ii < ii1; ii++) {
                 const float dy = dy0 + (float)ii;
                 const float gy = norm * expf(-dy * dy * inv_2sy2);
                 for (int jj = 0; jj < nx; jj++) {
                     const float dx = dx0 + (float)jj;
-                    atomicAdd(a.image + (size_t)(i_min + ii) * a.npx + j_min + jj,
+                    atomicAdd(a.image + (size_t)(i_min + ii - a.row0) * a.npx + j_min + jj,
                               gy * expf(-dx * dx * inv_2sx2));
                 }
             }
@@ -319,11 +341,121 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
     for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) {
         const int i = ty0 + q / kTile, j = tx0 + q % kTile;
         const float v = acc[q];
-        if (v != 0.0f && i < a.npy && j < a.npx) atomicAdd(a.image + (size_t)i * a.npx + j, v);
+        if (v != 0.0f && i < band_end && j < a.npx) atomicAdd(a.image + (size_t)(i - a.row0) * a.npx + j, v);
+    }
+}
+
+// ---- multi-GPU: bucket localisations by destination row band ---------------------------------
+constexpr int kMaxBands = 64;
+struct BandArgs {
+    int n_bands;
+    int rows[kMaxBands + 1];          // band b = image rows [rows[b], rows[b + 1])
+};
+
+// Every in-view localisation goes to each band its window can reach (the same conservative
+// reach as render_bin_kernel: 3 sigma + 2 rows); mode 0 (histogram) has no blur.
+__device__ __forceinline__ void band_range(const RenderArgs& a, const BandArgs& b, long long k, int& b0, int& b1) {
+    const double xv = (double)a.x[k], yv = (double)a.y[k];
+    b0 = 0; b1 = -1;
+    if (!((xv > a.x_min) && (yv > a.y_min) && (xv < a.x_max) && (yv < a.y_max))) return;
+    const double y_ = a.os * (yv - a.y_min);
+    double reach = 0.0;
+    if (a.mode) {
+        const float sg = __fmul_rn(a.osf, fmaxf(fmaxf(a.lpx[k], a.lpy[k]), a.mbw));
+        reach = 3.0 * (double)sg + 2.0;
+    }
+    int py = (int)y_;
+    py = min(max(py, 0), a.npy - 1);
+    b0 = b.n_bands; b1 = -1;
+    for (int q = 0; q < b.n_bands; q++) {
+        const bool owns = py >= b.rows[q] && py < b.rows[q + 1];
+        const bool reaches = b.rows[q + 1] > b.rows[q] && y_ + reach >= (double)b.rows[q] &&
+                             y_ - reach <= (double)b.rows[q + 1];
+        if (owns || reaches) { b0 = min(b0, q); b1 = max(b1, q); }
+    }
+}
+
+__global__ void render_band_count_kernel(const RenderArgs a, const BandArgs b,
+                                         unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int sc[kMaxBands];
+    for (int q = threadIdx.x; q < kMaxBands; q += blockDim.x) sc[q] = 0;
+    __syncthreads();
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
+         k += (long long)gridDim.x * blockDim.x) {
+        int b0, b1;
+        band_range(a, b, k, b0, b1);
+        for (int q = b0; q <= b1; q++) atomicAdd(&sc[q], 1u);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < b.n_bands; q += blockDim.x)
+        if (sc[q]) atomicAdd(counts + q, (unsigned long long)sc[q]);
+}
+
+// warp-aggregated append of (x, y, lpx, lpy) to the destination band's slice of the send buffers
+__global__ void render_band_scatter_kernel(const RenderArgs a, const BandArgs b,
+                                           const unsigned long long* __restrict__ offsets,
+                                           unsigned long long* __restrict__ cursor,
+                                           float* __restrict__ ox, float* __restrict__ oy,
+                                           float* __restrict__ olx, float* __restrict__ oly) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
+         k += (long long)gridDim.x * blockDim.x) {
+        int b0, b1;
+        band_range(a, b, k, b0, b1);
+        for (int q = b0; q <= b1; q++) {
+            const unsigned long long at = offsets[q] + atomicAdd(cursor + q, 1ull);
+            ox[at] = a.x[k]; oy[at] = a.y[k];
+            if (a.mode) { olx[at] = a.lpx[k]; oly[at] = a.lpy[k]; }
+        }
     }
 }
 
 }  // namespace
+
+extern "C" int pb_render_band_count_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
+                                        const float* d_lpy, double oversampling, double y_min, double x_min,
+                                        double y_max, double x_max, double min_blur_width, int mode,
+                                        int n_pixel_y, int n_pixel_x, int n_bands, const int* band_rows,
+                                        unsigned long long* d_counts, void* stream) {
+    if (mode < 0 || mode > 2) { pb_set_error("blur_method not understood."); return PB_ERR_INVALID; }
+    if (n_bands < 1 || n_bands > kMaxBands || !band_rows || !d_counts) { pb_set_error("pb_render_band_count_dev: bad band list"); return PB_ERR_INVALID; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    PB_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 8 * (size_t)n_bands, s));
+    if (n == 0) return PB_OK;
+    RenderArgs a{d_x, d_y, d_lpx, d_lpy, (long long)n, oversampling, y_min, x_min, y_max, x_max,
+                 (float)oversampling, (float)min_blur_width, mode, nullptr, n_pixel_y, n_pixel_x, nullptr, 0, n_pixel_y};
+    BandArgs b;
+    b.n_bands = n_bands;
+    for (int q = 0; q <= n_bands; q++) b.rows[q] = band_rows[q];
+    const int grid = (int)std::min<long long>(((long long)n + 255) / 256, 148 * 16);
+    render_band_count_kernel<<<grid, 256, 0, s>>>(a, b, d_counts);
+    g_pb_launches++;
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_render_band_scatter_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
+                                          const float* d_lpy, double oversampling, double y_min, double x_min,
+                                          double y_max, double x_max, double min_blur_width, int mode,
+                                          int n_pixel_y, int n_pixel_x, int n_bands, const int* band_rows,
+                                          const unsigned long long* d_offsets, unsigned long long* d_cursor,
+                                          float* d_out_x, float* d_out_y, float* d_out_lpx, float* d_out_lpy,
+                                          void* stream) {
+    if (mode < 0 || mode > 2) { pb_set_error("blur_method not understood."); return PB_ERR_INVALID; }
+    if (n_bands < 1 || n_bands > kMaxBands || !band_rows || !d_offsets || !d_cursor) { pb_set_error("pb_render_band_scatter_dev: bad band list"); return PB_ERR_INVALID; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    PB_CUDA_CHECK(cudaMemsetAsync(d_cursor, 0, 8 * (size_t)n_bands, s));
+    if (n == 0) return PB_OK;
+    RenderArgs a{d_x, d_y, d_lpx, d_lpy, (long long)n, oversampling, y_min, x_min, y_max, x_max,
+                 (float)oversampling, (float)min_blur_width, mode, nullptr, n_pixel_y, n_pixel_x, nullptr, 0, n_pixel_y};
+    BandArgs b;
+    b.n_bands = n_bands;
+    for (int q = 0; q <= n_bands; q++) b.rows[q] = band_rows[q];
+    const int grid = (int)std::min<long long>(((long long)n + 255) / 256, 148 * 16);
+    render_band_scatter_kernel<<<grid, 256, 0, s>>>(a, b, d_offsets, d_cursor, d_out_x, d_out_y, d_out_lpx, d_out_lpy);
+    g_pb_launches++;
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
 
 // Workspace (bytes) pb_render_dev needs for the tiled path; 0 => use the direct path.
 extern "C" size_t pb_render_workspace_bytes(size_t n, int n_pixel_y, int n_pixel_x) {
@@ -337,16 +469,33 @@ extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const
                              float* d_image, int n_pixel_y, int n_pixel_x,
                              unsigned long long* d_count, void* d_workspace,
                              size_t workspace_bytes, void* stream) {
+    return pb_render_band_dev(n, d_x, d_y, d_lpx, d_lpy, oversampling, y_min, x_min, y_max, x_max,
+                              min_blur_width, mode, d_image, n_pixel_y, n_pixel_x, 0, n_pixel_y, d_count,
+                              d_workspace, workspace_bytes, stream);
+}
+
+// Row band [row0, row0 + n_rows) of the same image: `d_image` holds n_rows x n_pixel_x floats.
+// Multi-GPU rendering shards the image by such bands (SURVEY.md 8e option B): every rank draws
+// the localisations whose 3-sigma window reaches its band, clipped to the band, and counts those
+// whose centre row it owns -- the bands concatenate to the full image and the counts add up to n.
+extern "C" int pb_render_band_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
+                                  const float* d_lpy, double oversampling, double y_min, double x_min,
+                                  double y_max, double x_max, double min_blur_width, int mode,
+                                  float* d_image, int n_pixel_y, int n_pixel_x, int row0, int n_rows,
+                                  unsigned long long* d_count, void* d_workspace,
+                                  size_t workspace_bytes, void* stream) {
     if (mode < 0 || mode > 2) { pb_set_error("blur_method not understood."); return PB_ERR_INVALID; }
     if (n_pixel_y <= 0 || n_pixel_x <= 0) return PB_OK;
-    if (!d_image || !d_count) { pb_set_error("pb_render_dev: null pointer"); return PB_ERR_INVALID; }
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > n_pixel_y) { pb_set_error("pb_render_band_dev: bad row band"); return PB_ERR_INVALID; }
+    if (!d_count || (n_rows && !d_image)) { pb_set_error("pb_render_dev: null pointer"); return PB_ERR_INVALID; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    PB_CUDA_CHECK(cudaMemsetAsync(d_image, 0, sizeof(float) * (size_t)n_pixel_y * n_pixel_x, s));
     PB_CUDA_CHECK(cudaMemsetAsync(d_count, 0, 8, s));
+    if (n_rows == 0) return PB_OK;
+    PB_CUDA_CHECK(cudaMemsetAsync(d_image, 0, sizeof(float) * (size_t)n_rows * n_pixel_x, s));
     if (n == 0) return PB_OK;
     RenderArgs a{d_x, d_y, d_lpx, d_lpy, (long long)n, oversampling, y_min, x_min, y_max, x_max,
                  (float)oversampling, (float)min_blur_width, mode, d_image, n_pixel_y, n_pixel_x,
-                 d_count};
+                 d_count, row0, n_rows};
     const int threads = 256;
     if (mode == 0) {
         int grid = (int)std::min<long long>(((long long)n + threads - 1) / threads, 148 * 16);
@@ -355,9 +504,9 @@ extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const
         PB_CUDA_CHECK(cudaGetLastError());
         return PB_OK;
     }
-    const int tiles_x = (n_pixel_x + kTile - 1) / kTile, tiles_y = (n_pixel_y + kTile - 1) / kTile;
+    const int tiles_x = (n_pixel_x + kTile - 1) / kTile, tiles_y = (n_rows + kTile - 1) / kTile;
     const long long ntiles = (long long)tiles_x * tiles_y;
-    const size_t need = pb_render_workspace_bytes(n, n_pixel_y, n_pixel_x);
+    const size_t need = pb_render_workspace_bytes(n, n_rows, n_pixel_x);
     const bool tiled = d_workspace && workspace_bytes >= need && n >= 65536 && n < 0xffffffffull &&
                        ntiles >= 64 && ((reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0);
     if (!tiled) {

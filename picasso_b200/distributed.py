@@ -6,10 +6,15 @@ a data-path collective; the only exchanges are the gather of results.
   output buffer ``[thetas 6n | crlbs 6n | logliks n | iterations n]``.
 * identify: frames shard by contiguous range; variable-length results are exchanged by an
   all-gather of counts followed by a padded all-gather.
-* render: localisations shard by index, the partial images are summed (all-reduce).
+* render: the IMAGE shards by row bands (SURVEY.md 8e option B): every rank buckets its index
+  share of the localisations by destination band (3-sigma halo) on its GPU, one NCCL all-to-all
+  moves the records, every rank splats and downloads only its band -- no 419 MB image reduction.
+  (``render_sharded`` keeps the simpler index shard + image all-reduce.)
 * fused localize: frames shard by contiguous block, the finished column blocks are gathered.
-* undrift: every rank renders and transforms all segments (33 ms for 200 x 4096^2), the
-  n(n-1)/2 pairs shard round-robin; only the 4 KB correlation windows are exchanged.
+* undrift: SEGMENTS shard for rendering + forward R2C, one NCCL all-gather leaves every rank with
+  all half-spectra (13.4 GB at 200 x 4096^2), the n(n-1)/2 pairs shard by whole L2 pair tiles
+  incl. their peak fits; two float64 shifts per pair are exchanged.  (``undrift_sharded`` keeps the
+  variant without a spectra exchange: every rank renders and transforms all segments.)
 """
 from __future__ import annotations
 
@@ -347,3 +352,464 @@ class PeerGather:
         self.dist.barrier()                  # nobody frees while a peer still has the mapping open
         self.l.pb_dev_free(self.buf)
         self.buf = None
+
+
+# ---- scalable sharding of render and undrift (device-resident building blocks) -------------------
+def band_rows(n_pixel_y: int, world: int, tile: int = 64):
+    """Row bands of an n_pixel_y-row image for ``world`` ranks: world + 1 boundaries, interior ones
+    aligned to the 64-row render tile (a band may be empty when the image has fewer tiles than
+    ranks)."""
+    rows = [min(n_pixel_y, ((n_pixel_y * r) // world + tile // 2) // tile * tile) for r in range(world)]
+    rows[0] = 0
+    for r in range(1, world):
+        rows[r] = max(rows[r], rows[r - 1])
+    return rows + [n_pixel_y]
+
+
+def exchange_variable(dist, torch, send, in_splits, all_splits):
+    """All-to-all of a 1-D tensor with per-destination split sizes ``in_splits``; ``all_splits`` is
+    the (world, world) matrix of everybody's split sizes (row = source).  Returns the received
+    tensor (source-major).  One ``all_to_all_single`` (NCCL on the GPUs, gloo in the CPU tests)."""
+    rank = dist.get_rank()
+    out_splits = [int(all_splits[src][rank]) for src in range(dist.get_world_size())]
+    recv = torch.empty(sum(out_splits), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send, output_split_sizes=out_splits,
+                           input_split_sizes=[int(v) for v in in_splits])
+    return recv
+
+
+def all_gather_counts(dist, torch, counts, device):
+    """(world, world) int64 matrix of every rank's per-destination counts."""
+    world = dist.get_world_size()
+    mine = torch.as_tensor(np.asarray(counts, dtype=np.int64), device=device)
+    full = torch.empty(world * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(full, mine)
+    return full.cpu().numpy().reshape(world, world)
+
+
+def _render_decl(l):
+    if getattr(l, "_band_declared", False):
+        return
+    import ctypes as C
+
+    vp, i32, f64, sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+    l.pb_render_band_dev.argtypes = [sz, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, i32, vp, i32, i32,
+                                     i32, i32, vp, vp, sz, vp]
+    l.pb_render_band_dev.restype = i32
+    l.pb_render_band_count_dev.argtypes = [sz, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, i32, i32, i32,
+                                           i32, vp, vp, vp]
+    l.pb_render_band_count_dev.restype = i32
+    l.pb_render_band_scatter_dev.argtypes = [sz, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, i32, i32, i32,
+                                             i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    l.pb_render_band_scatter_dev.restype = i32
+    l.pb_render_workspace_bytes.restype = C.c_size_t
+    l.pb_render_workspace_bytes.argtypes = [sz, i32, i32]
+    l._band_declared = True
+
+
+def render_bands_device(dist, torch, x, y, lpx, lpy, *, oversampling, viewport, min_blur_width=0.0,
+                        blur_method="gaussian", timings=None):
+    """Multi-GPU ``render.render`` by image row bands.  ``x, y, lpx, lpy`` are float32 CUDA tensors
+    holding THIS rank's index share of the localizations.  Every rank
+
+    1. buckets its localizations by destination band on its GPU (``pb_render_band_count_dev`` /
+       ``pb_render_band_scatter_dev``: a localization goes to every band its 3-sigma window reaches),
+    2. exchanges the records with ONE all-to-all per column (NCCL over NVLink),
+    3. splats what it received into its own band (``pb_render_band_dev``, windows clipped to the
+       band) -- no image reduction, and every rank downloads only its band.
+
+    Returns ``(n_total, band_image (rows, n_pixel_x) CUDA tensor, (row0, row1))``; the bands
+    concatenate to the single-GPU image (up to float32 summation order) and ``n_total`` is the
+    reference's ``n``.  ``dist=None`` or world size 1 renders the full image locally."""
+    import ctypes as C
+
+    from . import _lib
+    from .render import _MODES
+
+    if blur_method not in _MODES:
+        raise Exception("blur_method not understood.")
+    mode = _MODES[blur_method]
+    l = _lib.load()
+    _render_decl(l)
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    dev = x.device
+    st = torch.cuda.current_stream(dev).cuda_stream
+    (y_min, x_min), (y_max, x_max) = viewport
+    npy = int(np.ceil(oversampling * (y_max - y_min)))
+    npx = int(np.ceil(oversampling * (x_max - x_min)))
+    args = (float(oversampling), float(y_min), float(x_min), float(y_max), float(x_max),
+            float(min_blur_width), mode)
+    n = int(x.numel())
+    p = lambda t: t.data_ptr() if t is not None and t.numel() else None     # noqa: E731
+    rows = band_rows(npy, world)
+    ev = (lambda: torch.cuda.Event(enable_timing=True)) if timings is not None else None
+    marks = []
+
+    def mark(name):
+        if ev is not None:
+            e = ev(); e.record(); marks.append((name, e))
+
+    mark("start")
+    if world > 1:
+        rows_c = (C.c_int * (world + 1))(*rows)
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        _lib.check(l.pb_render_band_count_dev(n, p(x), p(y), p(lpx), p(lpy), *args, npy, npx, world, rows_c,
+                                              counts.data_ptr(), st))
+        all_counts = all_gather_counts(dist, torch, counts.cpu().numpy(), dev)     # one sync
+        mine = all_counts[rank]
+        offsets = torch.as_tensor(np.concatenate([[0], np.cumsum(mine)[:-1]]).astype(np.int64), device=dev)
+        cursor = torch.zeros(world, dtype=torch.int64, device=dev)
+        total = int(mine.sum())
+        send = [torch.empty(max(total, 1), dtype=torch.float32, device=dev) for _ in range(4 if mode else 2)]
+        _lib.check(l.pb_render_band_scatter_dev(n, p(x), p(y), p(lpx), p(lpy), *args, npy, npx, world, rows_c,
+                                                offsets.data_ptr(), cursor.data_ptr(), send[0].data_ptr(),
+                                                send[1].data_ptr(), send[2].data_ptr() if mode else None,
+                                                send[3].data_ptr() if mode else None, st))
+        mark("bucket")
+        recv = [exchange_variable(dist, torch, t[:total], mine, all_counts) for t in send]
+        mark("exchange")
+        x, y = recv[0], recv[1]
+        lpx, lpy = (recv[2], recv[3]) if mode else (None, None)
+        n = int(x.numel())
+    row0, row1 = rows[rank], rows[rank + 1]
+    image = torch.empty((row1 - row0, npx), dtype=torch.float32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    wsb = int(l.pb_render_workspace_bytes(n, max(row1 - row0, 1), npx)) if mode else 0
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+    _lib.check(l.pb_render_band_dev(n, p(x), p(y), p(lpx), p(lpy), *args, p(image), npy, npx, row0, row1 - row0,
+                                    count.data_ptr(), ws.data_ptr() if mode else None, wsb, st))
+    mark("splat")
+    if world > 1:
+        dist.all_reduce(count, op=dist.ReduceOp.SUM)
+    n_total = int(count.item())
+    if timings is not None:
+        torch.cuda.synchronize(dev)
+        for (na, a), (nb, b) in zip(marks[:-1], marks[1:]):
+            timings[nb + "_ms"] = a.elapsed_time(b)
+    return n_total, image, (row0, row1)
+
+
+def render_bands(dist, torch, locs, info, device="cuda", **kwargs):
+    """``render.render`` for a table sharded by index over the ranks: ``locs`` is THIS rank's share
+    (host DataFrame).  Uploads it, renders by row bands (``render_bands_device``) and downloads this
+    rank's band into page-locked memory.  Returns ``(n_total, band ndarray, (row0, row1))``;
+    ``gather_bands`` assembles the full image where one is wanted."""
+    from . import _lib, lib as pblib
+    from .render import image_to_host
+
+    pixelsize = pblib.get_from_metadata(info, "Pixelsize", raise_error=True)
+    disp = kwargs.pop("disp_px_size", None)
+    oversampling = kwargs.pop("oversampling", 1.0)
+    if disp is not None:
+        oversampling = pixelsize / disp
+    viewport = kwargs.pop("viewport", None) or [(0, 0), (info[0]["Height"], info[0]["Width"])]
+    blur = kwargs.pop("blur_method", None)
+    up = lambda c: _to_device(torch, np.ascontiguousarray(locs[c], dtype=np.float32), device)   # noqa: E731
+    x, y = up("x"), up("y")
+    lpx, lpy = (up("lpx"), up("lpy")) if blur is not None else (None, None)
+    n, band, rr = render_bands_device(dist, torch, x, y, lpx, lpy, oversampling=oversampling, viewport=viewport,
+                                      min_blur_width=kwargs.pop("min_blur_width", 0.0), blur_method=blur)
+    return n, image_to_host(torch, band), rr
+
+
+def gather_bands(dist, torch, band, n_pixel_y, device="cpu"):
+    """All-gather the row bands of ``render_bands`` into the full image on every rank."""
+    world = dist.get_world_size()
+    rows = band_rows(n_pixel_y, world)
+    npx = band.shape[1]
+    hmax = max(max(rows[r + 1] - rows[r] for r in range(world)), 1)
+    pad = torch.zeros((hmax, npx), dtype=torch.float32, device=device)
+    pad[: band.shape[0]] = torch.as_tensor(band, device=device)
+    out = torch.empty((world, hmax, npx), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(out.view(-1), pad.view(-1))
+    out = out.cpu().numpy()
+    return np.concatenate([out[r][: rows[r + 1] - rows[r]] for r in range(world)], axis=0)
+
+
+def _to_device(torch, a, device):
+    """Host numpy array -> device tensor through the threaded pinned staging (pb_copy_h2d)."""
+    from . import _lib
+
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, device=device)
+    if a.size:
+        l = _lib.load()
+        st = torch.cuda.current_stream(t.device)
+        _lib.check(l.pb_copy_h2d(t.data_ptr(), a.ctypes.data, a.nbytes, st.cuda_stream))
+        st.synchronize()
+    return t
+
+
+# ---- undrift: segments sharded for render + R2C, spectra all-gathered, pairs sharded by L2 tile ----
+def segment_shards(n_seg: int, world: int):
+    """Contiguous segment ranges per rank (world + 1 boundaries)."""
+    return shard_bounds(n_seg, world)
+
+
+def tile_sorted_pairs(n_seg: int, tile_segments: int):
+    """All i < j pairs ordered by L2 pair tile (i // TS, j // TS) (stable: the reference's pair order
+    inside a tile) and, for each, its index in the reference's pair order."""
+    pi, pj = np.triu_indices(n_seg, 1)
+    key = (pi // tile_segments).astype(np.int64) * (n_seg + 1) + (pj // tile_segments)
+    order = np.argsort(key, kind="stable")
+    return pi[order].astype(np.int32), pj[order].astype(np.int32), order
+
+
+def my_tile_pairs(n_seg: int, tile_segments: int, rank: int, world: int):
+    """This rank's contiguous share of the tile-sorted pair list: whole tiles keep their 2 * TS
+    spectrum slabs L2 resident (a round-robin split would load every tile on every rank).
+    Returns (pair_i, pair_j, index in the reference's pair order)."""
+    pi, pj, order = tile_sorted_pairs(n_seg, tile_segments)
+    b = shard_bounds(len(pi), world)
+    sl = slice(b[rank], b[rank + 1])
+    return pi[sl], pj[sl], order[sl]
+
+
+def _rcc_decl(l):
+    if getattr(l, "_rccdev_declared", False):
+        return
+    import ctypes as C
+
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    l.pb_rcc_spectra_dev.argtypes = [i32, i32, i32, vp, vp, vp, vp]
+    l.pb_rcc_spectra_dev.restype = i32
+    l.pb_rcc_windows_dev.argtypes = [i32, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp, sz, vp]
+    l.pb_rcc_windows_dev.restype = i32
+    l.pb_rcc_peakfit_dev.argtypes = [i32, vp, i32, i32, vp, vp]
+    l.pb_rcc_peakfit_dev.restype = i32
+    l.pb_rcc_tile_segments.argtypes = [i32]
+    l.pb_rcc_tile_segments.restype = i32
+    l.pb_render_dev.argtypes = [sz, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                C.c_double, i32, vp, i32, i32, vp, vp, sz, vp]
+    l.pb_render_dev.restype = i32
+    l.pb_render_workspace_bytes.restype = C.c_size_t
+    l.pb_render_workspace_bytes.argtypes = [sz, i32, i32]
+    l._rccdev_declared = True
+
+
+def undrift_shifts_device(dist, torch, seg_start, x, y, lpx, lpy, n_seg, Y, X, *, min_blur_width=1.0,
+                          max_shift=32, timings=None):
+    """The device part of ``postprocess.undrift`` on ``world`` GPUs.  ``x, y, lpx, lpy`` are float32
+    CUDA tensors with the localizations of THIS rank's segments (``segment_shards``), grouped by
+    segment: local segment k owns ``[seg_start[k], seg_start[k + 1])``.
+
+    1. every rank renders its segments (``pb_render_dev``) and transforms them (one batched R2C,
+       ``pb_rcc_spectra_dev``) straight into its slice of the full spectra buffer;
+    2. ONE in-place NCCL all-gather leaves all ranks with all half-spectra;
+    3. every rank correlates its share of the pairs -- whole L2 pair tiles (``my_tile_pairs``) --
+       with the pruned inverse transform (``pb_rcc_windows_dev``) and fits their peaks on the device
+       (``pb_rcc_peakfit_dev``); fits the device solver does not settle are re-fitted on the host
+       exactly like the reference;
+    4. two float64 shifts per pair are all-gathered into the reference's pair order.
+
+    Returns ``(shift_y, shift_x)`` per pair (length n_seg (n_seg - 1) / 2) on every rank."""
+    from . import _lib, imageprocess
+
+    l = _lib.load()
+    _rcc_decl(l)
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    dev = x.device
+    stream = torch.cuda.current_stream(dev)
+    st = stream.cuda_stream
+    sb = segment_shards(n_seg, world)
+    n_loc = sb[rank + 1] - sb[rank]
+    n_max = max(sb[r + 1] - sb[r] for r in range(world))
+    XH = X // 2 + 1
+    Y_, X_, H, W = imageprocess._crop_geometry(Y, X, max_shift)
+    seg_start = np.asarray(seg_start, dtype=np.int64)
+    assert len(seg_start) == n_loc + 1
+    p = lambda t: t.data_ptr() if t is not None and t.numel() else None     # noqa: E731
+    marks = []
+
+    def mark(name):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
+
+    mark("start")
+    # spectra of all ranks: rank r's segments at padded index r * n_max + k
+    spectra = torch.empty((world * n_max, Y, XH, 2), dtype=torch.float32, device=dev)
+    sums_all = torch.zeros(world * n_max, dtype=torch.float64, device=dev)
+    if n_loc:
+        segs = torch.empty((n_loc, Y, X), dtype=torch.float32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        max_seg = int((seg_start[1:] - seg_start[:-1]).max()) if n_loc else 0
+        wsb = int(l.pb_render_workspace_bytes(max_seg, Y, X))
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+        for k in range(n_loc):
+            a0, m = int(seg_start[k]), int(seg_start[k + 1] - seg_start[k])
+            o = a0 * 4
+            _lib.check(l.pb_render_dev(m, x.data_ptr() + o if m else None, y.data_ptr() + o if m else None,
+                                       lpx.data_ptr() + o if m else None, lpy.data_ptr() + o if m else None,
+                                       1.0, 0.0, 0.0, float(Y), float(X), float(min_blur_width), 1,
+                                       segs[k].data_ptr(), Y, X, cnt.data_ptr(), ws.data_ptr(), wsb, st))
+        mark("render")
+        mine = spectra[rank * n_max: rank * n_max + n_loc]
+        _lib.check(l.pb_rcc_spectra_dev(n_loc, Y, X, segs.data_ptr(), mine.data_ptr(),
+                                        sums_all[rank * n_max:].data_ptr(), st))
+        del segs, ws
+    else:
+        mark("render")
+    mark("r2c")
+    if world > 1:
+        flat = spectra.view(-1)
+        per = n_max * Y * XH * 2
+        dist.all_gather_into_tensor(flat, flat[rank * per: (rank + 1) * per])          # in place
+        s_mine = sums_all[rank * n_max: (rank + 1) * n_max].clone()
+        dist.all_gather_into_tensor(sums_all, s_mine)
+    mark("allgather_spectra")
+    # pairs: whole L2 tiles per rank, indices mapped to the padded spectra layout
+    TS = int(l.pb_rcc_tile_segments(Y))
+    pi, pj, ref_index = my_tile_pairs(n_seg, TS, rank, world)
+    seg_rank = np.searchsorted(np.asarray(sb[1:]), np.arange(n_seg), side="right")
+    padded = (seg_rank * n_max + (np.arange(n_seg) - np.asarray(sb)[seg_rank])).astype(np.int32)
+    n_mine = len(pi)
+    rec = np.zeros((n_mine, 32), dtype=np.float64)
+    win = None
+    if n_mine:
+        dpi = torch.as_tensor(padded[pi], device=dev)
+        dpj = torch.as_tensor(padded[pj], device=dev)
+        win = torch.empty((n_mine, H, W), dtype=torch.float32, device=dev)
+        t_per_pair = H * XH * 8
+        wsb = max(min(n_mine, 32768) * t_per_pair, Y * XH * 8 + Y * X * 4) + 4096
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _lib.check(l.pb_rcc_windows_dev(n_mine, dpi.data_ptr(), dpj.data_ptr(), Y, X, spectra.data_ptr(),
+                                        Y_, X_, H, W, win.data_ptr(), 1, ws.data_ptr(), wsb, st))
+        mark("pairs")
+        drec = torch.empty((n_mine, 32), dtype=torch.float64, device=dev)
+        _lib.check(l.pb_rcc_peakfit_dev(n_mine, win.data_ptr(), H, W, drec.data_ptr(), st))
+        rec = drec.cpu().numpy()
+        del ws
+    else:
+        mark("pairs")
+    mark("peakfit")
+    sums = sums_all.cpu().numpy()[padded]                       # per real segment
+    sy, sx = imageprocess._shifts_from_records(rec, sums, pi, pj, Y, X, Y_, X_,
+                                               (lambda odd: win[torch.as_tensor(odd, device=dev)].cpu().numpy())
+                                               if win is not None else None)
+    n_pairs = n_seg * (n_seg - 1) // 2
+    full = np.zeros((n_pairs, 2))
+    if world > 1:
+        b = shard_bounds(n_pairs, world)
+        cmax = max(max(b[r + 1] - b[r] for r in range(world)), 1)
+        pad = torch.zeros((cmax, 3), dtype=torch.float64, device=dev)
+        if n_mine:
+            pad[:n_mine] = torch.as_tensor(np.stack([sy, sx, ref_index.astype(np.float64)], 1), device=dev)
+        out = torch.empty((world, cmax, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out.view(-1), pad.view(-1))
+        out = out.cpu().numpy()
+        for r in range(world):
+            c = b[r + 1] - b[r]
+            full[out[r, :c, 2].astype(np.int64)] = out[r, :c, :2]
+    else:
+        full[ref_index] = np.stack([sy, sx], 1)
+    mark("gather_shifts")
+    if timings is not None:
+        torch.cuda.synchronize(dev)
+        for (na, a), (nb, b_) in zip(marks[:-1], marks[1:]):
+            timings[nb + "_ms"] = a.elapsed_time(b_)
+    return full[:, 0], full[:, 1]
+
+
+def undrift_segments_sharded(dist, torch, locs, info, segmentation, device="cuda", timings=None):
+    """``postprocess.undrift`` for a table sharded by FRAME RANGE over the ranks: ``locs`` (host
+    DataFrame, frames ascending) holds the localizations of this rank's segments
+    (``segment_shards`` of ``postprocess.n_segments`` segments; ``shard_locs_by_segment`` cuts a full
+    table accordingly).  Device part: ``undrift_shifts_device``; then every rank runs the reference's
+    ``minimize_shifts`` + cubic spline (milliseconds) and subtracts the drift from ITS rows only.
+    Returns ``(drift DataFrame over all frames, undrifted shard)``."""
+    import pandas as pd
+    from scipy import interpolate
+
+    from . import lib, postprocess
+
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    n_frames = info[0]["Frames"]
+    Y, X = info[0]["Height"], info[0]["Width"]
+    n_seg = postprocess.n_segments(info, segmentation)
+    bounds = np.linspace(0, n_frames - 1, n_seg + 1, dtype=np.uint32)
+    sb = segment_shards(n_seg, world)
+    frames = locs["frame"].to_numpy()
+    if len(frames) > 1 and not bool(np.all(frames[1:] >= frames[:-1])):
+        locs = locs.sort_values("frame", kind="stable")
+        frames = locs["frame"].to_numpy()
+    my_bounds = bounds[sb[rank]: sb[rank + 1] + 1]
+    cut = np.searchsorted(frames, my_bounds, side="left")
+    a, b = (int(cut[0]), int(cut[-1])) if len(cut) else (0, 0)
+    seg_start = (cut - cut[0]).astype(np.int64) if len(cut) else np.zeros(1, np.int64)
+    up = lambda c: _to_device(torch, np.ascontiguousarray(locs[c].to_numpy()[a:b], dtype=np.float32), device)   # noqa: E731
+    x, y, lpx, lpy = up("x"), up("y"), up("lpx"), up("lpy")
+    sy, sx = undrift_shifts_device(dist, torch, seg_start, x, y, lpx, lpy, n_seg, Y, X, min_blur_width=1.0,
+                                   max_shift=32, timings=timings)
+    shifts_x = np.zeros((n_seg, n_seg)); shifts_y = np.zeros((n_seg, n_seg))
+    ai, aj = np.triu_indices(n_seg, 1)
+    shifts_y[ai, aj] = sy; shifts_x[ai, aj] = sx
+    shift_y, shift_x = lib.minimize_shifts(shifts_x, shifts_y)
+    t = (bounds[1:] + bounds[:-1]) / 2
+    t_inter = np.arange(n_frames)
+    drift = pd.DataFrame({"x": interpolate.InterpolatedUnivariateSpline(t, shift_x, k=3)(t_inter),
+                          "y": interpolate.InterpolatedUnivariateSpline(t, shift_y, k=3)(t_inter)})
+    out = locs.copy()
+    out = postprocess.apply_drift(out, info, drift=drift)
+    return drift, out
+
+
+def shard_locs_by_segment(locs, info, segmentation, rank, world):
+    """The rows of a (frame-sorted) table that belong to this rank's segments; the last rank also
+    keeps the frames past the final segment bound (the reference drops them from the images but
+    still undrifts them)."""
+    from . import postprocess
+
+    n_frames = info[0]["Frames"]
+    n_seg = postprocess.n_segments(info, segmentation)
+    bounds = np.linspace(0, n_frames - 1, n_seg + 1, dtype=np.uint32)
+    sb = segment_shards(n_seg, world)
+    frames = locs["frame"].to_numpy()
+    lo = np.searchsorted(frames, bounds[sb[rank]], side="left") if rank else 0
+    hi = np.searchsorted(frames, bounds[sb[rank + 1]], side="left") if rank + 1 < world else len(frames)
+    return locs.iloc[int(lo): int(hi)]
+
+
+# ---- fused localize on a device-resident frame block ---------------------------------------------
+def localize_device(torch, movie, frame_offset, camera_info, parameters, *, fitting_method="gausslq",
+                    eps=0.001, max_it=100, mle_method="sigmaxy", roi=None):
+    """``localize.localize`` on a frame block that already lives in HBM (``movie``: (F, Y, X) uint16
+    or float32 CUDA tensor; ``frame_offset`` = index of its first frame in the whole movie):
+    identify -> sort -> cut -> fit -> localization columns without leaving the GPU
+    (``pb_localize_dev``).  Returns the (ncols, n) float32 column block as a CUDA tensor, rows in
+    (frame, y, x) order; ``localize._columns_to_locs`` turns a downloaded block into the DataFrame."""
+    import ctypes as C
+
+    from . import _lib, localize as pbl
+
+    l = _lib.load()
+    vp, i32, sz, f32, f64 = C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_double
+    l.pb_localize_dev.argtypes = [vp, i32, sz, i32, i32, C.c_longlong, i32, f64, vp, f32, f32, f32, i32, f64, i32,
+                                  i32, vp, sz, C.POINTER(sz)]
+    l.pb_localize_dev.restype = i32
+    fit = pbl._FIT_IDS[(fitting_method, mle_method if fitting_method == "gaussmle" else None)]
+    ncols = int(l.pb_locs_columns(fit))
+    F, Y, X = movie.shape
+    if movie.dtype in (torch.int16, getattr(torch, "uint16", torch.int16)):
+        dtype = 0                      # uint16 counts (int16 storage is read as uint16)
+    elif movie.dtype == torch.float32:
+        dtype = 1
+    else:
+        raise ValueError("movie must be a uint16 / int16 or float32 CUDA tensor")
+    roi_arr = pbl._roi_array(roi)
+    capacity = max(4096, 128 * int(F))
+    while True:
+        cols = torch.empty((ncols, capacity), dtype=torch.float32, device=movie.device)
+        found = sz(0)
+        rc = l.pb_localize_dev(movie.data_ptr(), dtype, int(F), int(Y), int(X), int(frame_offset),
+                               int(parameters["Box Size"]), float(parameters["Min. Net Gradient"]),
+                               _lib.ptr(roi_arr) if roi_arr is not None else None,
+                               float(camera_info["Baseline"]), float(camera_info["Sensitivity"]),
+                               float(camera_info["Gain"]), fit, float(eps), int(max_it),
+                               int(camera_info["Gain"] > 1), cols.data_ptr(), capacity, C.byref(found))
+        if rc == 4:
+            capacity = int(found.value)
+            continue
+        _lib.check(rc)
+        return cols[:, : int(found.value)]

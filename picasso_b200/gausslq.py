@@ -42,8 +42,9 @@ def _fit(spots, want_info=False):
     if spots.ndim != 3 or spots.shape[1] != spots.shape[2]:
         raise ValueError("spots must have shape (n_spots, size, size)")
     n, box, _ = spots.shape
-    theta = np.empty((n, 6), dtype=np.float32)
-    theta.fill(np.nan)
+    # the reference pre-fills with NaN (gausslq.py:277-278); here the kernel writes every row, and
+    # the array is backed by pooled page-locked memory so the download is a direct DMA
+    theta = _lib.pinned_empty((n, 6), np.float32)
     infos = np.zeros(n, np.int32) if want_info else None
     nfevs = np.zeros(n, np.int32) if want_info else None
     if n:

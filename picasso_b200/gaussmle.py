@@ -64,11 +64,13 @@ def gaussmle(
     method_id = _method_id(method)
     spots = _as_spots(spots)
     N = len(spots)
-    # every entry is written by the kernel (the reference pre-fills CRLBs with inf, :457)
-    thetas = np.empty((N, 6), dtype=np.float32)
-    CRLBs = np.empty((N, 6), dtype=np.float32)
-    likelihoods = np.empty(N, dtype=np.float32)
-    iterations = np.empty(N, dtype=np.int32)
+    # every entry is written by the kernel (the reference pre-fills CRLBs with inf, :457).  The
+    # returned arrays are backed by pooled page-locked memory (_lib.pinned_empty): the device ->
+    # host copy is a direct DMA, no staging copy and no first-touch page faults.
+    thetas = _lib.pinned_empty((N, 6), np.float32)
+    CRLBs = _lib.pinned_empty((N, 6), np.float32)
+    likelihoods = _lib.pinned_empty((N,), np.float32)
+    iterations = _lib.pinned_empty((N,), np.int32)
     if N:
         _fit_into(spots, eps, max_it, method_id, thetas, CRLBs, likelihoods, iterations)
     if progress_callback == "console":

@@ -365,6 +365,24 @@ def _shifts_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=None, c
     _lib.check(l.pb_undrift_peaks_pairs(n_seg, _lib.ptr(seg_start), _lib.ptr(x), _lib.ptr(y), _lib.ptr(lpx),
                                         _lib.ptr(lpy), Y, X, float(min_blur_width), Y_, X_, H, W, len(pi),
                                         _lib.ptr(pi), _lib.ptr(pj), _lib.ptr(rec), _lib.ptr(sums), None))
+    def odd_windows(odd):
+        win, _, _ = _windows_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=(pi[odd], pj[odd]))
+        return win
+
+    sy, sx = _shifts_from_records(rec, sums, pi, pj, Y, X, Y_, X_, odd_windows)
+    if callback is not None:
+        for flag in range(len(pi)):
+            callback(flag + 1)
+    return sy, sx
+
+
+def _shifts_from_records(rec, sums, pi, pj, Y, X, Y_, X_, odd_windows=None):
+    """(shift_y, shift_x) per pair from the device peak-fit records (32 float64 per pair: status,
+    arg-max y / x, xc, yc, the 5 x 5 window) -- the tail of the reference's ``get_image_shift``
+    (imageprocess.py:83-84, 113-157).  status 1: the device solver did not settle -> scipy's bounded
+    ``curve_fit`` like the reference; status 2: window touches the crop edge -> (0, 0); status 3: the
+    rare square-but-not-5x5 cut-out at the crop corner -> ``odd_windows(indices)`` must return those
+    pairs' full windows for the host path."""
     status = rec[:, 0].astype(np.int64)
     xc, yc = rec[:, 3].copy(), rec[:, 4].copy()
     for k in np.flatnonzero(status == 1):                       # re-fit like the reference
@@ -372,9 +390,11 @@ def _shifts_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=None, c
     odd = np.flatnonzero(status == 3)
     odd_shift = {}
     if len(odd):
-        win, _, _ = _windows_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=(pi[odd], pj[odd]))
+        if odd_windows is None:
+            raise RuntimeError("peak-fit status 3 needs the full correlation windows")
+        win = odd_windows(odd)
         for q, k in enumerate(odd):
-            odd_shift[k] = _shift_from_window(win[q].astype(np.float64), Y, X, Y_, X_, 5)
+            odd_shift[k] = _shift_from_window(np.asarray(win[q], dtype=np.float64), Y, X, Y_, X_, 5)
     zero = (sums[pi] == 0) | (sums[pj] == 0) | (status == 2)
     sx = -(xc + X_ + rec[:, 2] - np.floor(X / 2))
     sy = -(yc + Y_ + rec[:, 1] - np.floor(Y / 2))
@@ -383,9 +403,6 @@ def _shifts_of_locs(locs, info, bounds, min_blur_width, max_shift, pairs=None, c
     for k, (a, b) in odd_shift.items():
         if sums[pi[k]] != 0 and sums[pj[k]] != 0:
             sy[k], sx[k] = a, b
-    if callback is not None:
-        for flag in range(len(pi)):
-            callback(flag + 1)
     return sy, sx
 
 

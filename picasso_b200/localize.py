@@ -469,7 +469,7 @@ def _localize_fused_columns(movie, minimum_ng, box, camera_info, fit, eps, max_i
             F, Y, X = chunk.shape
             capacity = max(4096, 128 * F)
             while True:
-                cols = np.empty((len(names), capacity), np.float32)
+                cols = _lib.pinned_empty((len(names), capacity), np.float32)
                 found = C.c_size_t(0)
                 rc = lib.pb_localize(_lib.ptr(chunk), dtype, F, Y, X, a, int(box), float(minimum_ng),
                                      _lib.ptr(roi_arr) if roi_arr is not None else None, baseline,

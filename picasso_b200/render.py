@@ -102,7 +102,7 @@ def image_to_host(torch, image):
     """Download a device image through the threaded pinned staging (pageable numpy result)."""
     l = _lib.load()
     _declare(l)
-    out = np.empty(tuple(image.shape), dtype=np.float32)
+    out = _lib.pinned_empty(tuple(image.shape), np.float32)
     if out.size:
         st = torch.cuda.current_stream(image.device).cuda_stream
         _lib.check(l.pb_copy_d2h(_lib.ptr(out), image.data_ptr(), out.nbytes, st))
@@ -152,7 +152,11 @@ def render(locs, info, oversampling: float = 1.0, viewport=None, blur_method=Non
     if mode:
         lpx = np.ascontiguousarray(locs["lpx"], dtype=np.float32)
         lpy = np.ascontiguousarray(locs["lpy"], dtype=np.float32)
-    image = np.zeros((max(n_pixel_y, 0), max(n_pixel_x, 0)), dtype=np.float32)
+    # pb_render writes every pixel; page-locked backing makes the 419 MB download of a 10240^2
+    # image one direct DMA
+    image = _lib.pinned_empty((max(n_pixel_y, 0), max(n_pixel_x, 0)), np.float32)
+    if image.size == 0 or len(x) == 0:
+        image[...] = 0
     n = C.c_longlong(0)
     _lib.check(l.pb_render(len(x), _lib.ptr(x), _lib.ptr(y),
                            _lib.ptr(lpx) if mode else None, _lib.ptr(lpy) if mode else None,

@@ -43,3 +43,25 @@ def test_peer_gather_equals_nccl_all_gather():
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert out == {"world": 2, "peer_gather_equals_nccl": True}
+
+
+def test_scalable_sharding_agrees_with_one_gpu():
+    """Row-band render (all-to-all) and segment-sharded undrift (spectra all-gather, tile-sharded
+    pairs) on two ranks against the single-GPU product calls."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(ROOT, "tools", "check_sharded_scalable.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["world"] == 2
+    for bm in ("gaussian", "gaussian_iso", "None"):
+        assert out["render_bands"][bm]["ok"] is True, out["render_bands"][bm]
+        assert out["render_bands"][bm]["n"] == out["render_bands"][bm]["n_ref"]
+    u = out["undrift_segments"]
+    assert u["max_abs_drift_dev_px"] < 1e-5 and u["max_abs_row_dev_px"] < 1e-4
+    assert u["rows_total"] == u["rows_ref"]
