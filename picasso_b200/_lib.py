@@ -32,6 +32,15 @@ def _declare(lib):
     lib.pb_get_device.restype = i32
     lib.pb_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.pb_host_free.argtypes = [vp]
+    # plumbing used from several modules: declared here once (an undeclared ctypes function would
+    # truncate 64-bit pointers passed as Python ints)
+    lib.pb_copy_h2d.argtypes = [vp, vp, sz, vp]
+    lib.pb_copy_d2h.argtypes = [vp, vp, sz, vp]
+    lib.pb_dev_alloc.argtypes = [C.POINTER(vp), sz]
+    lib.pb_dev_free.argtypes = [vp]
+    lib.pb_copy_d2d_async.argtypes = [vp, vp, sz, vp]
+    for name in ("pb_copy_h2d", "pb_copy_d2h", "pb_dev_alloc", "pb_dev_free", "pb_copy_d2d_async"):
+        getattr(lib, name).restype = i32
     lib.pb_mle_fit.argtypes = [sz, i32, vp, f64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.pb_mle_fit_dev.argtypes = [sz, i32, vp, f64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.pb_mle_set_impl.argtypes = [i32]

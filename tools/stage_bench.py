@@ -124,7 +124,7 @@ def stage_localize(ctx, frames=2000, Y=512, X=512, chunk=100):
     torch, dist = ctx.torch, ctx.dist
     from picasso_b200 import _lib, distributed as pbd, localize as pbl
 
-    lib = _lib.load()
+    lib = pbl._lib_ready()           # declares the ctypes signatures of the localize entry points
     nchunks = frames // chunk
     cb = _bounds(nchunks, ctx.world)
     my_chunks = range(cb[ctx.rank], cb[ctx.rank + 1])
