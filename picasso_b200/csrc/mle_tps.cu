@@ -111,6 +111,29 @@ struct Xf3 {
     }
 };
 
+// fast CRLB pass: PSF as double, (d/dmu, d/dsigma) as one float2 per column; same footprint rule
+// (column stride = kThreads) inside the memory of Xf3, which the float64 fallback re-uses
+struct Xf3F {
+    double* p;
+    __host__ __device__ __forceinline__ void put(int c, const double f[5]) {
+        p[(c * 2 + 0) * kThreads] = f[0];
+        reinterpret_cast<float2*>(p)[(c * 2 + 1) * kThreads] = make_float2((float)f[1], (float)f[3]);
+    }
+    __host__ __device__ __forceinline__ void get(int c, double& px, float& c1, float& g1) const {
+        px = p[(c * 2 + 0) * kThreads];
+        const float2 v = reinterpret_cast<const float2*>(p)[(c * 2 + 1) * kThreads];
+        c1 = v.x; g1 = v.y;
+    }
+};
+// ln() table staged in shared memory as (rc, lc) pairs
+struct LogTabSmem {
+    const double2* t;
+    __device__ __forceinline__ void get(int i, double& rc, double& lc) const {
+        const double2 v = t[i];
+        rc = v.x; lc = v.y;
+    }
+};
+
 template <typename T> struct XfSel;
 template <> struct XfSel<float> {
     using type = XfF32;
@@ -343,10 +366,13 @@ struct CrlbSmem {
     static constexpr int PIX = BOX * BOX;
     static constexpr int kRoi = ((kThreads * PIX * 4 + 15) / 16) * 16;
     static constexpr int kXf = kThreads * BOX * 3 * 8;
-    static constexpr int kTotal = kRoi + kXf + 16;
+    static constexpr int kTab = 128 * 16;
+    static constexpr int kTotal = kRoi + kXf + kTab + 16;
 };
 
-template <int BOX, int METHOD>
+// FAST: float32 pair sums + table ln() with the all-float64 pass as per-spot fallback
+// (mle_tps_core.cuh, crlb_loglik_fast); !FAST: the all-float64 pass (pb_mle_set_impl(1)).
+template <int BOX, int METHOD, bool FAST>
 __global__ void __launch_bounds__(kThreads) tps_crlb_kernel(const TpsArgs a, long long seg_first,
                                                             long long seg_n) {
     using SM = CrlbSmem<BOX>;
@@ -354,11 +380,16 @@ __global__ void __launch_bounds__(kThreads) tps_crlb_kernel(const TpsArgs a, lon
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw);
     double* xfp = reinterpret_cast<double*>(smem_raw + SM::kRoi);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::kRoi + SM::kXf);
+    double2* tabp = reinterpret_cast<double2*>(smem_raw + SM::kRoi + SM::kXf);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::kRoi + SM::kXf + SM::kTab);
     const long long first = seg_first + (long long)blockIdx.x * kThreads;
     const long long rem = seg_first + seg_n - first;
     const int count = rem < kThreads ? (int)rem : kThreads;
-    stage_chunk<PIX>(a.spots, first, count, sm, bar);
+    if (FAST) {
+        static_assert(kThreads == 128, "one table entry per thread");
+        tabp[threadIdx.x] = make_double2(tps::kLogRc[threadIdx.x], tps::kLogLc[threadIdx.x]);
+    }
+    stage_chunk<PIX>(a.spots, first, count, sm, bar);      // (its __syncthreads publishes the table)
     if ((int)threadIdx.x < count) {
         const long long s = first + threadIdx.x;
         RoiSlot roi{sm + threadIdx.x * PIX};
@@ -367,7 +398,13 @@ __global__ void __launch_bounds__(kThreads) tps_crlb_kernel(const TpsArgs a, lon
         const float2 v0 = in[0], v1 = in[1], v2 = in[2];
         const float th[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
         float cr[6], ll;
-        const int st = tps::crlb_loglik<BOX, METHOD>(roi, th, xf, cr, &ll);
+        int st = -1;
+        if (FAST) {
+            Xf3F xff{xfp + threadIdx.x};
+            const LogTabSmem tab{tabp};
+            st = tps::crlb_loglik_fast<BOX, METHOD>(roi, th, xff, tab, cr, &ll);
+        }
+        if (st < 0) st = tps::crlb_loglik<BOX, METHOD>(roi, th, xf, cr, &ll);
         float2* out = reinterpret_cast<float2*>(a.crlbs + s * 6);
         out[0] = make_float2(cr[0], cr[1]);
         out[1] = make_float2(cr[2], cr[3]);
@@ -426,7 +463,7 @@ int launch_tps(const TpsArgs& a0, cudaStream_t stream) {
     using CSM = CrlbSmem<BOX>;
     auto k_init = tps_init_kernel<BOX, METHOD>;
     auto k_iter = tps_iter_kernel<BOX, METHOD, T>;
-    auto k_crlb = tps_crlb_kernel<BOX, METHOD>;
+    auto k_crlb = tps_crlb_kernel<BOX, METHOD, sizeof(T) == 4>;
     constexpr int init_smem = kThreads * PIX * 4 + 16;
     int dev = 0;
     PB_CUDA_CHECK(cudaGetDevice(&dev));

@@ -21,6 +21,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 // Under nvcc these are DEVICE functions (tables live in __constant__ memory, so the FP64
 // instructions take their coefficients straight from the constant bank); under g++ they
@@ -169,6 +170,110 @@ PB_HD double log_pos(double x) {
     for (int k = 7; k >= 0; k--) p = fma(p, s2, kLogPoly[k]);
     const double de = (double)e;
     return fma(de, 0.6931471805598903, fma(s, p, de * 5.497923018708371e-14));
+}
+
+// Table-driven ln(x) for a positive, finite, normal x (tools/gen_log_table.py; max abs error
+// 1.8e-15 for x < 1e5):  x = m 2^e, m in [1, 2);  i = top 7 mantissa bits;  r = fma(m, rc_i, -1),
+// |r| < 2^-8;  ln x = e ln2 + lc_i + log1p(r) with a degree-5 Taylor sum -- 8 FP64 instructions
+// plus two table loads (log_pos above: 20 FP64 + a reciprocal).  `tab(i)` returns (rc_i, lc_i);
+// on the device the table is staged in shared memory (the index diverges across lanes, which
+// would serialise constant-bank reads).
+PB_TABLE double kLogRc[128] = {
+    0x1.fe01fe01fe020p-1, 0x1.fa11caa01fa12p-1, 0x1.f6310aca0dbb5p-1, 0x1.f25f644230ab5p-1,
+    0x1.ee9c7f8458e02p-1, 0x1.eae807aba01ebp-1, 0x1.e741aa59750e4p-1, 0x1.e3a9179dc1a73p-1,
+    0x1.e01e01e01e01ep-1, 0x1.dca01dca01dcap-1, 0x1.d92f2231e7f8ap-1, 0x1.d5cac807572b2p-1,
+    0x1.d272ca3fc5b1ap-1, 0x1.cf26e5c44bfc6p-1, 0x1.cbe6d9601cbe7p-1, 0x1.c8b265afb8a42p-1,
+    0x1.c5894d10d4986p-1, 0x1.c26b5392ea01cp-1, 0x1.bf583ee868d8bp-1, 0x1.bc4fd65883e7bp-1,
+    0x1.b951e2b18ff23p-1, 0x1.b65e2e3beee05p-1, 0x1.b37484ad806cep-1, 0x1.b094b31d922a4p-1,
+    0x1.adbe87f94905ep-1, 0x1.aaf1d2f87ebfdp-1, 0x1.a82e65130e159p-1, 0x1.a574107688a4ap-1,
+    0x1.a2c2a87c51ca0p-1, 0x1.a01a01a01a01ap-1, 0x1.9d79f176b682dp-1, 0x1.9ae24ea5510dap-1,
+    0x1.9852f0d8ec0ffp-1, 0x1.95cbb0be377aep-1, 0x1.934c67f9b2ce6p-1, 0x1.90d4f120190d5p-1,
+    0x1.8e6527af1373fp-1, 0x1.8bfce8062ff3ap-1, 0x1.899c0f601899cp-1, 0x1.87427bcc092b9p-1,
+    0x1.84f00c2780614p-1, 0x1.82a4a0182a4a0p-1, 0x1.8060180601806p-1, 0x1.7e225515a4f1dp-1,
+    0x1.7beb3922e017cp-1, 0x1.79baa6bb6398bp-1, 0x1.77908119ac60dp-1, 0x1.756cac201756dp-1,
+    0x1.734f0c541fe8dp-1, 0x1.713786d9c7c09p-1, 0x1.6f26016f26017p-1, 0x1.6d1a62681c861p-1,
+    0x1.6b1490aa31a3dp-1, 0x1.691473a88d0c0p-1, 0x1.6719f3601671ap-1, 0x1.6524f853b4aa3p-1,
+    0x1.63356b88ac0dep-1, 0x1.614b36831ae94p-1, 0x1.5f66434292dfcp-1, 0x1.5d867c3ece2a5p-1,
+    0x1.5babcc647fa91p-1, 0x1.59d61f123ccaap-1, 0x1.5805601580560p-1, 0x1.56397ba7c52e2p-1,
+    0x1.54725e6bb82fep-1, 0x1.52aff56a8054bp-1, 0x1.50f22e111c4c5p-1, 0x1.4f38f62dd4c9bp-1,
+    0x1.4d843bedc2c4cp-1, 0x1.4bd3edda68fe1p-1, 0x1.4a27fad76014ap-1, 0x1.4880522014880p-1,
+    0x1.46dce34596066p-1, 0x1.453d9e2c776cap-1, 0x1.43a2730abee4dp-1, 0x1.420b5265e5951p-1,
+    0x1.40782d10e6566p-1, 0x1.3ee8f42a5af07p-1, 0x1.3d5d991aa75c6p-1, 0x1.3bd60d9232955p-1,
+    0x1.3a524387ac822p-1, 0x1.38d22d366088ep-1, 0x1.3755bd1c945eep-1, 0x1.35dce5f9f2af8p-1,
+    0x1.34679ace01346p-1, 0x1.32f5ced6a1dfap-1, 0x1.3187758e9ebb6p-1, 0x1.301c82ac40260p-1,
+    0x1.2eb4ea1fed14bp-1, 0x1.2d50a012d50a0p-1, 0x1.2bef98e5a3711p-1, 0x1.2a91c92f3c105p-1,
+    0x1.293725bb804a5p-1, 0x1.27dfa38a1ce4dp-1, 0x1.268b37cd60127p-1, 0x1.2539d7e9177b2p-1,
+    0x1.23eb79717605bp-1, 0x1.22a0122a0122ap-1, 0x1.21579804855e6p-1, 0x1.2012012012012p-1,
+    0x1.1ecf43c7fb84cp-1, 0x1.1d8f5672e4abdp-1, 0x1.1c522fc1ce059p-1, 0x1.1b17c67f2bae3p-1,
+    0x1.19e0119e0119ep-1, 0x1.18ab083902bdbp-1, 0x1.1778a191bd684p-1, 0x1.1648d50fc3201p-1,
+    0x1.151b9a3fdd5c9p-1, 0x1.13f0e8d344724p-1, 0x1.12c8b89edc0acp-1, 0x1.11a3019a74826p-1,
+    0x1.107fbbe011080p-1, 0x1.0f5edfab325a2p-1, 0x1.0e40655826011p-1, 0x1.0d24456359e3ap-1,
+    0x1.0c0a7868b4171p-1, 0x1.0af2f722eecb5p-1, 0x1.09ddba6af8360p-1, 0x1.08cabb37565e2p-1,
+    0x1.07b9f29b8eae2p-1, 0x1.06ab59c7912fbp-1, 0x1.059eea0727586p-1, 0x1.04949cc1664c5p-1,
+    0x1.038c6b78247fcp-1, 0x1.02864fc7729e9p-1, 0x1.0182436517a37p-1, 0x1.0080402010080p-1,
+};
+PB_TABLE double kLogLc[128] = {
+    0x1.ff00aa2b10ba0p-9, 0x1.7dc475f810a69p-7, 0x1.3cea44346a584p-6, 0x1.b9fc027af919ap-6,
+    0x1.1b0d98923d97fp-5, 0x1.58a5bafc8e4d3p-5, 0x1.95c830ec8e3f2p-5, 0x1.d276b8adb0b56p-5,
+    0x1.075983598e471p-4, 0x1.253f62f0a1417p-4, 0x1.42edcbea646eep-4, 0x1.60658a93750c4p-4,
+    0x1.7da766d7b12d0p-4, 0x1.9ab42462033aep-4, 0x1.b78c82bb0eda0p-4, 0x1.d4313d66cb35dp-4,
+    0x1.f0a30c01162a4p-4, 0x1.0671512ca596fp-3, 0x1.14785846742acp-3, 0x1.2266f190a5acdp-3,
+    0x1.303d718e47fd5p-3, 0x1.3dfc2b0ecc62ap-3, 0x1.4ba36f39a55e5p-3, 0x1.59338d9982085p-3,
+    0x1.66acd4272ad51p-3, 0x1.740f8f54037a3p-3, 0x1.815c0a14357e9p-3, 0x1.8e928de886d41p-3,
+    0x1.9bb362e7dfb85p-3, 0x1.a8becfc882f19p-3, 0x1.b5b519e8fb5a6p-3, 0x1.c2968558c18c2p-3,
+    0x1.cf6354e09c5ddp-3, 0x1.dc1bca0abec7bp-3, 0x1.e8c0252aa5a60p-3, 0x1.f550a564b7b37p-3,
+    0x1.00e6c45ad501dp-2, 0x1.071b85fcd590dp-2, 0x1.0d46b579ab74bp-2, 0x1.136870293a8b0p-2,
+    0x1.1980d2dd4236fp-2, 0x1.1f8ff9e48a2f3p-2, 0x1.2596010df763ap-2, 0x1.2b9303ab89d25p-2,
+    0x1.31871c9544185p-2, 0x1.3772662bfd85cp-2, 0x1.3d54fa5c1f710p-2, 0x1.432ef2a04e813p-2,
+    0x1.49006804009d0p-2, 0x1.4ec9732600269p-2, 0x1.548a2c3add263p-2, 0x1.5a42ab0f4cfe2p-2,
+    0x1.5ff3070a793d4p-2, 0x1.659b57303e1f2p-2, 0x1.6b3bb2235943dp-2, 0x1.70d42e2789236p-2,
+    0x1.7664e1239dbcfp-2, 0x1.7bede0a37afbfp-2, 0x1.816f41da0d495p-2, 0x1.86e919a330ba1p-2,
+    0x1.8c5b7c858b48bp-2, 0x1.91c67eb45a83ep-2, 0x1.972a341135159p-2, 0x1.9c86b02dc0862p-2,
+    0x1.a1dc064d5b995p-2, 0x1.a72a4966bd9e9p-2, 0x1.ac718c258b0e5p-2, 0x1.b1b1e0ebdfc5ap-2,
+    0x1.b6eb59d3cf35cp-2, 0x1.bc1e08b0dad0ap-2, 0x1.c149ff115f027p-2, 0x1.c66f4e3ff6ff9p-2,
+    0x1.cb8e0744d7acap-2, 0x1.d0a63ae721e64p-2, 0x1.d5b7f9ae2c684p-2, 0x1.dac353e2c5955p-2,
+    0x1.dfc859906d5b5p-2, 0x1.e4c71a8687704p-2, 0x1.e9bfa659861f5p-2, 0x1.eeb20c640ddf3p-2,
+    0x1.f39e5bc811e5dp-2, 0x1.f884a36fe9ec1p-2, 0x1.fd64f20f61571p-2, 0x1.011fab125ff8ap-1,
+    0x1.0389eefce633cp-1, 0x1.05f14bd26459cp-1, 0x1.0855c884b450ep-1, 0x1.0ab76bece14d2p-1,
+    0x1.0d163ccb9d6b8p-1, 0x1.0f7241c9b497dp-1, 0x1.11cb81787ccf8p-1, 0x1.1422025243d45p-1,
+    0x1.1675cababa60ep-1, 0x1.18c6e0ff5cf07p-1, 0x1.1b154b57da29ep-1, 0x1.1d610fe677003p-1,
+    0x1.1faa34b87094cp-1, 0x1.21f0bfc65beecp-1, 0x1.2434b6f483934p-1, 0x1.26762013430e0p-1,
+    0x1.28b500df60783p-1, 0x1.2af15f02640acp-1, 0x1.2d2b4012edc9dp-1, 0x1.2f62a99509546p-1,
+    0x1.3197a0fa7fe6ap-1, 0x1.33ca2ba328994p-1, 0x1.35fa4edd36ea0p-1, 0x1.38280fe58797fp-1,
+    0x1.3a5373e7ebdf9p-1, 0x1.3c7c7fff73206p-1, 0x1.3ea33936b2f5bp-1, 0x1.40c7a4880dceap-1,
+    0x1.42e9c6ddf80bfp-1, 0x1.4509a5133bb0ap-1, 0x1.472743f33aaadp-1, 0x1.4942a83a2fc07p-1,
+    0x1.4b5bd6956e273p-1, 0x1.4d72d3a39fd01p-1, 0x1.4f87a3f5026e9p-1, 0x1.519a4c0ba3446p-1,
+    0x1.53aad05b99b7cp-1, 0x1.55b9354b40bcep-1, 0x1.57c57f336f191p-1, 0x1.59cfb25fae87fp-1,
+    0x1.5bd7d30e71c73p-1, 0x1.5ddde57149923p-1, 0x1.5fe1edad18919p-1, 0x1.61e3efda46467p-1,
+};
+struct LogTabDirect {     // host build / staging source
+    PB_HD void get(int i, double& rc, double& lc) const { rc = kLogRc[i]; lc = kLogLc[i]; }
+};
+template <class Tab>
+PB_HD double log_tab(double x, const Tab& tab) {
+#ifdef __CUDA_ARCH__
+    const int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    const int e = (hi >> 20) - 1023;
+    const int idx = (hi >> 13) & 127;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+#else
+    uint64_t bits;
+    memcpy(&bits, &x, 8);
+    const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    const int idx = (int)((bits >> 45) & 127);
+    const uint64_t mb = (bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+    double m;
+    memcpy(&m, &mb, 8);
+#endif
+    double rc, lc;
+    tab.get(idx, rc, lc);
+    const double r = fma(m, rc, -1.0);
+    double p = fma(r, 0.2, -0.25);
+    p = fma(p, r, 0.33333333333333331);
+    p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    return fma((double)e, 0.6931471805599453, fma(p, r, lc));
 }
 
 // ---- per-axis constants of one iteration ------------------------------------
@@ -572,7 +677,7 @@ PB_HD_NOINLINE void pinv_diag_jacobi(const double* Msym /*NP*NP*/, double* diag)
 // Diagonal of inv(M), M symmetric positive definite, packed upper triangle m[idx(k,l)], k <= l.
 // false when the diagonally scaled Cholesky meets a non-positive / tiny pivot.
 template <int NP>
-PB_HD bool inv_diag_cholesky(const double* m, double* diag) {
+PB_HD bool inv_diag_cholesky(const double* m, double* diag, double* min_pivot = nullptr) {
 #define PB_TRI(k, l) ((k) * NP - ((k) * ((k) - 1)) / 2 + ((l) - (k)))
     double d[NP];
     bool ok = true;
@@ -591,6 +696,7 @@ PB_HD bool inv_diag_cholesky(const double* m, double* diag) {
 #pragma unroll
         for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
         ok = ok && (s > 1e-12);
+        if (min_pivot) *min_pivot = s < *min_pivot ? s : *min_pivot;
         rl[j] = rsqrt64(s);
         L[j][j] = s * rl[j];
 #pragma unroll
@@ -774,6 +880,156 @@ PB_HD int crlb_loglik(const Roi& roi, const float th[6], Xf3& xf, float crlb[6],
     if (METHOD == 0) crlb[5] = crlb[4];
     if (bad) st |= 4;
     return st;
+}
+
+// ---- fast CRLB + log-likelihood pass ------------------------------------------------------
+// Same quantities as crlb_row / crlb_loglik with the per-pixel work moved off the FP64 pipe:
+//   * the ten 1/model-weighted pair sums of a row are accumulated in FLOAT32 (the reference forms
+//     dudt[k] * dudt[l] in float32 itself, gaussmle.py:929-932: its Fisher entries carry the same
+//     6e-8 relative rounding), the row factors and the accumulation over rows stay float64;
+//   * ln(model) comes from the 128-entry table (log_tab).
+// A (near-)singular Fisher matrix -- a sigma collapsed onto its floor, where np.linalg.pinv returns
+// exact zeros -- amplifies float32 noise, so the result is only accepted when every pivot of the
+// diagonally scaled Cholesky factorisation is above 1e-2 (error bound ~ 2e-7 / 1e-2); otherwise
+// the caller repeats the pass with crlb_loglik (all float64).  Returns -1 in that case.
+// XfF concept: put(col, f[5]) keeps PSF as double and (d/dmu, d/dsigma) as floats;
+// get(col, double& px, float& c1, float& g1).
+template <int BOX, int METHOD, int NF, class Roi, class XfF, class Tab>
+PB_HD void crlb_row_fast(int j, const double fy[5], const Roi& roi, const XfF& xf, const Tab& tab, double N,
+                         double bg, double M[NF], double& ll) {
+    const double PSFy = fy[0], NPy = N * fy[0];
+    float ac[10];
+#pragma unroll
+    for (int q = 0; q < 10; q++) ac[q] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < BOX; i++) {
+        double px;
+        float c1, g1;
+        xf.get(i, px, c1, g1);
+        const double model = fma(px, NPy, bg);
+        const float pxf = (float)px;
+        const float w = rcp32((float)model);
+        const float c1w = c1 * w, pxw = pxf * w, g1w = g1 * w;
+        ac[0] = fmaf(c1w, c1, ac[0]);    // c1 c1
+        ac[1] = fmaf(c1w, pxf, ac[1]);   // c1 px
+        ac[2] += c1w;                    // c1 1
+        ac[3] = fmaf(c1w, g1, ac[3]);    // c1 g1
+        ac[4] = fmaf(pxw, pxf, ac[4]);   // px px
+        ac[5] += pxw;                    // px 1
+        ac[6] = fmaf(pxw, g1, ac[6]);    // px g1
+        ac[7] += w;                      // 1 1
+        ac[8] += g1w;                    // 1 g1
+        ac[9] = fmaf(g1w, g1, ac[9]);    // g1 g1
+        const float dataf = roi(j * BOX + i);
+        if (model > 0.0) {
+            // d ln(model) - model - f32(d logf(d)) + d  (gaussmle.py:935-945)
+            if (dataf > 0.0f) {
+                const double d = (double)dataf;
+                ll += fma(d, log_tab(model, tab), d - model) - (double)(dataf * logf(dataf));
+            } else {
+                ll -= model;
+            }
+        }
+    }
+#define PB_PR(p, q) (double)ac[((p) < (q) ? (p) : (q)) * 4 - (((p) < (q) ? (p) : (q)) * (((p) < (q) ? (p) : (q)) - 1)) / 2 + \
+                               (((p) < (q) ? (q) : (p)) - ((p) < (q) ? (p) : (q)))]
+    if (METHOD == 1) {
+        const double arow[6] = {NPy, N * fy[1], PSFy, 1.0, NPy, N * fy[3]};
+        constexpr int kind[6] = {0, 1, 1, 2, 3, 1};
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+#pragma unroll
+            for (int l = k; l < 6; l++) {
+                M[q] = fma(arow[k] * arow[l], PB_PR(kind[k], kind[l]), M[q]);
+                q++;
+            }
+    } else {
+        const double arow[4] = {NPy, N * fy[1], PSFy, 1.0};
+        constexpr int kind[4] = {0, 1, 1, 2};
+        const double u = NPy, v = N * fy[3];
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int l = k; l < 4; l++) {
+                M[q] = fma(arow[k] * arow[l], PB_PR(kind[k], kind[l]), M[q]);
+                q++;
+            }
+            M[q] = fma(arow[k], u * PB_PR(kind[k], 3) + v * PB_PR(kind[k], 1), M[q]);
+            q++;
+        }
+        M[q] += u * u * PB_PR(3, 3) + 2.0 * u * v * PB_PR(3, 1) + v * v * PB_PR(1, 1);
+    }
+#undef PB_PR
+}
+
+template <int BOX, int METHOD, class Roi, class XfF, class Tab>
+PB_HD int crlb_loglik_fast(const Roi& roi, const float th[6], XfF& xf, const Tab& tab, float crlb[6],
+                           float* loglik) {
+    constexpr int NP = METHOD == 1 ? 6 : 5;
+    constexpr int NF = NP * (NP + 1) / 2;
+    const double N = (double)th[2], bg = (double)th[3];
+    {
+        const Axis ax = make_axis(th[4]);
+        Edge<METHOD> EA, EB = {};
+#pragma unroll 1
+        for (int k = 0; k < (BOX + 1) / 2; k++) {
+            double f[5];
+            EA = eval_edge<METHOD>(2 * k, th[0], ax);
+            if (k > 0) {
+                pixel_factors<METHOD>(EB, EA, ax, f);
+                xf.put(2 * k - 1, f);
+            }
+            EB = eval_edge<METHOD>(2 * k + 1, th[0], ax);
+            pixel_factors<METHOD>(EA, EB, ax, f);
+            xf.put(2 * k, f);
+        }
+    }
+    double M[NF];
+#pragma unroll
+    for (int q = 0; q < NF; q++) M[q] = 0.0;
+    double ll = 0.0;
+    {
+        const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
+        Edge<METHOD> EA, EB = {};
+#pragma unroll 1
+        for (int k = 0; k < (BOX + 1) / 2; k++) {
+            double fy[5];
+            EA = eval_edge<METHOD>(2 * k, th[1], ay);
+            if (k > 0) {
+                pixel_factors<METHOD>(EB, EA, ay, fy);
+                crlb_row_fast<BOX, METHOD, NF>(2 * k - 1, fy, roi, xf, tab, N, bg, M, ll);
+            }
+            EB = eval_edge<METHOD>(2 * k + 1, th[1], ay);
+            pixel_factors<METHOD>(EA, EB, ay, fy);
+            crlb_row_fast<BOX, METHOD, NF>(2 * k, fy, roi, xf, tab, N, bg, M, ll);
+        }
+    }
+    double dg[NP];
+    double dmin = INFINITY, dmax = 0.0;
+    {
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            dmin = fmin(dmin, M[q]); dmax = fmax(dmax, M[q]);
+            q += NP - k;
+        }
+    }
+    double smin = 1.0;
+    const bool ok = (dmin > 1e-13 * dmax) && inv_diag_cholesky<NP>(M, dg, &smin) && smin > 1e-2 &&
+                    isfinite(ll);
+    if (!ok) return -1;
+    bool bad = false;
+#pragma unroll
+    for (int l = 0; l < NP; l++) {
+        crlb[l] = (float)dg[l];
+        bad = bad || !isfinite(crlb[l]);
+    }
+    if (bad) return -1;
+    if (METHOD == 0) crlb[5] = crlb[4];
+    *loglik = (float)ll;
+    return 0;
 }
 
 }  // namespace tps

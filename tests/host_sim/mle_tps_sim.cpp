@@ -28,6 +28,14 @@ struct Xf3Host {
     void get(int c, double f[3]) const { f[0] = a[c][0]; f[1] = a[c][1]; f[2] = a[c][2]; }
 };
 
+template <int BOX>
+struct XfFHost {      // fast CRLB pass: PSF double, (d/dmu, d/dsigma) float
+    double px[BOX];
+    float c1[BOX], g1[BOX];
+    void put(int c, const double f[5]) { px[c] = f[0]; c1[c] = (float)f[1]; g1[c] = (float)f[3]; }
+    void get(int c, double& p, float& a, float& g) const { p = px[c]; a = c1[c]; g = g1[c]; }
+};
+
 template <int BOX, int METHOD, typename T, typename A>
 void fit_range(const float* spots, long long n, double eps, int max_it, float* thetas, float* crlbs,
                float* logliks, int* iterations, int* status) {
@@ -47,7 +55,13 @@ void fit_range(const float* spots, long long n, double eps, int max_it, float* t
         }
         Xf3Host<BOX> x3;
         float cr[6], ll;
-        st |= tps::crlb_loglik<BOX, METHOD>(roi, th, x3, cr, &ll);
+        int cs = -1;
+        if (sizeof(T) == 4) {      // the float32-pixel kernels use the fast CRLB pass with f64 fallback
+            XfFHost<BOX> xff;
+            cs = tps::crlb_loglik_fast<BOX, METHOD>(roi, th, xff, tps::LogTabDirect{}, cr, &ll);
+        }
+        if (cs < 0) cs = tps::crlb_loglik<BOX, METHOD>(roi, th, x3, cr, &ll);
+        st |= cs;
         for (int l = 0; l < 6; l++) { thetas[s * 6 + l] = th[l]; crlbs[s * 6 + l] = cr[l]; }
         logliks[s] = ll;
         iterations[s] = kk;
