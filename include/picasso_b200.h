@@ -245,6 +245,37 @@ int pb_zfit_dev(size_t n, const float* d_sx, const float* d_sy, const float* d_p
                 const double* cy, double magnification, double pixelsize, int method, float* d_z,
                 float* d_d_zcalib, float* d_lpz, int* d_nfev, void* stream);
 
+/* ---- localisation table: ensure_sanity, z-fit filter, record packing on the device ----------
+ * Replaces lib.ensure_sanity (picasso/lib.py:1786-1832), the tail of zfit._fit_z (picasso/zfit.py:
+ * 356-383: append z / d_zcalib / lpz, ensure_sanity, filter_z_fits :675-704) and the record packing
+ * of io.save_locs (picasso/io.py:2089-2110, locs.to_records(index=False)) for tables whose columns
+ * are all 4 bytes wide (float32 / uint32 / int32 -- every table the fit path produces).
+ *   cols[k]      host pointer to column k (n elements); is_float[k] != 0: float32 (rows with inf /
+ *                NaN are dropped)
+ *   ix, iy       indices of the x / y columns (x < width, y < height in float32), -1 if absent
+ *   nonneg_cols  columns that must be >= 0 (x, y, lpx, lpy, lpz, photons, ellipticity, sx, sy
+ *                as present)
+ *   zfit         nullable: run the astigmatic z fit (pb_zfit_dev) on the resident columns first;
+ *                z, d_zcalib, lpz become columns ncols .. ncols + 2 (lpz joins the >= 0 list) and,
+ *                for filter_range > 0, rows with d_zcalib > range * sqrt(nanmean(d_zcalib^2)) are
+ *                dropped after the sanity pass -- the RMSD reproduces numpy's float32 pairwise
+ *                summation bit for bit
+ *   out          out_records == 0: (ncols [+3], capacity) column block; != 0: n_kept packed records
+ *                of ncols [+3] 4-byte fields (the layout of DataFrame.to_records(index=False))
+ *   kept_index   nullable: original row numbers of the kept rows (capacity int64)
+ *   n_kept       rows kept; above `capacity` the call returns PB_ERR_CAPACITY with the number */
+typedef struct PbZfitSpec {
+    int i_sx, i_sy, i_photons, i_bg, i_sx_unc, i_sy_unc;   /* column indices (-1: absent) */
+    double cx[7], cy[7];                                    /* calibration polynomials z^6 .. z^0 */
+    double magnification, pixelsize;
+    int method;                                             /* as pb_zfit */
+    int filter_range;                                       /* filter_z_fits range; 0 = no filter */
+} PbZfitSpec;
+int pb_locs_filter(size_t n, int ncols, const void* const* cols, const int* is_float, int ix, int iy,
+                   const int* nonneg_cols, int n_nonneg, double width, double height,
+                   const PbZfitSpec* zfit, int out_records, void* out, size_t capacity,
+                   long long* kept_index, size_t* n_kept);
+
 /* ---- AIM drift correction: intersection counting ---------------------------------
  * Replaces the counting core of picasso.aim (picasso/aim.py): _point_intersect_2d :297-344,
  * _point_intersect_3d :377-431, _run_intersections(_multithread) :148-266 and
@@ -321,7 +352,8 @@ int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_l
  * pb_render_band_scatter_dev bucket a rank's share of the localisations by destination band
  * (band b = rows [band_rows[b], band_rows[b+1]), host array of n_bands + 1 ints, <= 64 bands): a
  * localisation goes to every band its 3-sigma window can reach; the scatter writes band b's
- * records at d_offsets[b] of the four send columns (the exchange itself is an NCCL all-to-all). */
+ * (x, y, lpx, lpy) float4 records from record index d_offsets[b] of the send buffer (the exchange
+ * itself is ONE NCCL all-to-all of the records). */
 int pb_render_band_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
                        const float* d_lpy, double oversampling, double y_min, double x_min,
                        double y_max, double x_max, double min_blur_width, int mode, float* d_image,
@@ -338,8 +370,10 @@ int pb_render_band_scatter_dev(size_t n, const float* d_x, const float* d_y, con
                                double y_max, double x_max, double min_blur_width, int mode,
                                int n_pixel_y, int n_pixel_x, int n_bands, const int* band_rows,
                                const unsigned long long* d_offsets, unsigned long long* d_cursor,
-                               float* d_out_x, float* d_out_y, float* d_out_lpx, float* d_out_lpy,
-                               void* stream);
+                               float* d_records, void* stream);
+/* (x, y, lpx, lpy) float4 records (what the scatter writes and the all-to-all moves) -> columns */
+int pb_render_unpack_records_dev(size_t n, const float* d_records, float* d_x, float* d_y,
+                                 float* d_lpx, float* d_lpy, void* stream);
 
 /* ---- RCC cross-correlation ----------------------------------------------------
  * Replaces the FFT work of picasso.imageprocess.xcorr / get_image_shift / rcc

@@ -42,6 +42,9 @@ namespace {
 constexpr int kThreads = 128;            // 4 warps per CTA in all three kernels
 constexpr unsigned kFull = 0xffffffffu;
 
+#ifndef PB_CRLB_MINB
+#define PB_CRLB_MINB 4
+#endif
 #ifndef PB_TPS_MINB
 #define PB_TPS_MINB 4
 #endif
@@ -373,7 +376,7 @@ struct CrlbSmem {
 // FAST: float32 pair sums + table ln() with the all-float64 pass as per-spot fallback
 // (mle_tps_core.cuh, crlb_loglik_fast); !FAST: the all-float64 pass (pb_mle_set_impl(1)).
 template <int BOX, int METHOD, bool FAST>
-__global__ void __launch_bounds__(kThreads) tps_crlb_kernel(const TpsArgs a, long long seg_first,
+__global__ void __launch_bounds__(kThreads, PB_CRLB_MINB) tps_crlb_kernel(const TpsArgs a, long long seg_first,
                                                             long long seg_n) {
     using SM = CrlbSmem<BOX>;
     constexpr int PIX = BOX * BOX;

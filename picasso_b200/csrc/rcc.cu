@@ -23,6 +23,7 @@
 // HBM-bound (cuFFT passes over 2*Y*X*4 B per pair).
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <cufft.h>
 #include <stdlib.h>
 #include <vector>
@@ -654,6 +655,37 @@ struct CufftPlan {
     ~CufftPlan() { if (ok) cufftDestroy(h); }
 };
 
+// Small LRU cache of cuFFT plans (creating a batched 4096^2 plan costs tens of milliseconds -- more than
+// the transforms of a rank's share of the segments on 8 GPUs).  Forward transforms run in groups of at
+// most kR2CBatch segments, so one plan (and its bounded work area) serves any number of segments.
+constexpr int kR2CBatch = 16;
+struct PlanEntry { int dev, Y, X, batch, type; cufftHandle h; unsigned long long used; };
+std::mutex g_plan_mutex;
+std::vector<PlanEntry> g_plans;
+unsigned long long g_plan_clock = 0;
+int cached_plan(int Y, int X, int batch, cufftType type, cufftHandle* out) {
+    int dev = 0;
+    PB_CUDA_CHECK(cudaGetDevice(&dev));
+    for (auto& e : g_plans)
+        if (e.dev == dev && e.Y == Y && e.X == X && e.batch == batch && e.type == (int)type) {
+            e.used = ++g_plan_clock;
+            *out = e.h;
+            return PB_OK;
+        }
+    if (g_plans.size() >= 8) {
+        size_t old = 0;
+        for (size_t k = 1; k < g_plans.size(); k++) if (g_plans[k].used < g_plans[old].used) old = k;
+        cufftDestroy(g_plans[old].h);
+        g_plans.erase(g_plans.begin() + old);
+    }
+    cufftHandle h;
+    int dims[2] = {Y, X};
+    PB_CUFFT_CHECK(cufftPlanMany(&h, 2, dims, nullptr, 1, 0, nullptr, 1, 0, type, batch));
+    g_plans.push_back({dev, Y, X, batch, (int)type, h, ++g_plan_clock});
+    *out = h;
+    return PB_OK;
+}
+
 // -1 auto (pruned when the window covers at most a quarter of the image), 0 cuFFT, 1 pruned
 std::atomic<int> g_rcc_mode{-2};
 int rcc_mode() {
@@ -711,13 +743,20 @@ extern "C" int pb_rcc_spectra_dev(int n_seg, int Y, int X, const float* d_segmen
                                   void* d_spectra, double* d_sums, void* stream) {
     if (n_seg <= 0) return PB_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    CufftPlan plan;
-    int dims[2] = {Y, X};
-    PB_CUFFT_CHECK(cufftPlanMany(&plan.h, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, n_seg));
-    plan.ok = true;
-    PB_CUFFT_CHECK(cufftSetStream(plan.h, s));
-    PB_CUFFT_CHECK(cufftExecR2C(plan.h, const_cast<float*>(d_segments),
-                                static_cast<cufftComplex*>(d_spectra)));
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mutex);
+        const size_t img = (size_t)Y * X, spec = (size_t)Y * (X / 2 + 1);
+        for (int s0 = 0; s0 < n_seg;) {
+            const int nb = std::min(kR2CBatch, n_seg - s0);
+            cufftHandle h;
+            int rc = cached_plan(Y, X, nb, CUFFT_R2C, &h);
+            if (rc != PB_OK) return rc;
+            PB_CUFFT_CHECK(cufftSetStream(h, s));
+            PB_CUFFT_CHECK(cufftExecR2C(h, const_cast<float*>(d_segments) + (size_t)s0 * img,
+                                        static_cast<cufftComplex*>(d_spectra) + (size_t)s0 * spec));
+            s0 += nb;
+        }
+    }
     g_pb_launches++;
     if (d_sums) {
         PB_CUDA_CHECK(cudaMemsetAsync(d_sums, 0, sizeof(double) * n_seg, s));
@@ -726,7 +765,7 @@ extern "C" int pb_rcc_spectra_dev(int n_seg, int Y, int X, const float* d_segmen
         g_pb_launches++;
     }
     PB_CUDA_CHECK(cudaGetLastError());
-    PB_CUDA_CHECK(cudaStreamSynchronize(s));   // plan is destroyed on return
+    PB_CUDA_CHECK(cudaStreamSynchronize(s));
     return PB_OK;
 }
 

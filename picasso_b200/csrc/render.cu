@@ -375,37 +375,67 @@ __device__ __forceinline__ void band_range(const RenderArgs& a, const BandArgs& 
     }
 }
 
-__global__ void render_band_count_kernel(const RenderArgs a, const BandArgs b,
-                                         unsigned long long* __restrict__ counts) {
+// counts per band: warp-aggregated (one ballot per band) into shared counters, one global atomic
+// per band and CTA
+__global__ void __launch_bounds__(256) render_band_count_kernel(const RenderArgs a, const BandArgs b,
+                                                                unsigned long long* __restrict__ counts) {
     __shared__ unsigned int sc[kMaxBands];
     for (int q = threadIdx.x; q < kMaxBands; q += blockDim.x) sc[q] = 0;
     __syncthreads();
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
-         k += (long long)gridDim.x * blockDim.x) {
-        int b0, b1;
-        band_range(a, b, k, b0, b1);
-        for (int q = b0; q <= b1; q++) atomicAdd(&sc[q], 1u);
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (a.n + stride - 1) / stride;
+    for (long long r = 0; r < rounds; r++) {
+        const long long k = r * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        int b0 = 0, b1 = -1;
+        if (k < a.n) band_range(a, b, k, b0, b1);
+        for (int q = 0; q < b.n_bands; q++) {
+            const unsigned m = __ballot_sync(0xffffffffu, q >= b0 && q <= b1);
+            if (lane == 0 && m) atomicAdd(&sc[q], (unsigned)__popc(m));
+        }
     }
     __syncthreads();
     for (int q = threadIdx.x; q < b.n_bands; q += blockDim.x)
         if (sc[q]) atomicAdd(counts + q, (unsigned long long)sc[q]);
 }
 
-// warp-aggregated append of (x, y, lpx, lpy) to the destination band's slice of the send buffers
-__global__ void render_band_scatter_kernel(const RenderArgs a, const BandArgs b,
-                                           const unsigned long long* __restrict__ offsets,
-                                           unsigned long long* __restrict__ cursor,
-                                           float* __restrict__ ox, float* __restrict__ oy,
-                                           float* __restrict__ olx, float* __restrict__ oly) {
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
-         k += (long long)gridDim.x * blockDim.x) {
-        int b0, b1;
-        band_range(a, b, k, b0, b1);
-        for (int q = b0; q <= b1; q++) {
-            const unsigned long long at = offsets[q] + atomicAdd(cursor + q, 1ull);
-            ox[at] = a.x[k]; oy[at] = a.y[k];
-            if (a.mode) { olx[at] = a.lpx[k]; oly[at] = a.lpy[k]; }
+// Append (x, y, lpx, lpy) records to the destination band's slice of the send buffer.  Per tile of
+// 256 localisations the CTA ranks its records per band in shared memory (warp ballots), reserves one
+// range per band with a single global atomic and writes the float4 records -- 2 * n_bands global
+// atomics per 256 localisations instead of one per record on two hot addresses.
+__global__ void __launch_bounds__(256) render_band_scatter_kernel(const RenderArgs a, const BandArgs b,
+                                                                  const unsigned long long* __restrict__ offsets,
+                                                                  unsigned long long* __restrict__ cursor,
+                                                                  float4* __restrict__ out) {
+    __shared__ unsigned int warp_cnt[kMaxBands][8];      // per band, per warp of the CTA
+    __shared__ unsigned long long base[kMaxBands];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (a.n + stride - 1) / stride;
+    for (long long r = 0; r < rounds; r++) {
+        const long long k = r * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        int b0 = 0, b1 = -1;
+        if (k < a.n) band_range(a, b, k, b0, b1);
+        for (int q = 0; q < b.n_bands; q++) {
+            const unsigned m = __ballot_sync(0xffffffffu, q >= b0 && q <= b1);
+            if (lane == 0) warp_cnt[q][warp] = __popc(m);
         }
+        __syncthreads();
+        if (threadIdx.x < b.n_bands) {
+            const int q = threadIdx.x;
+            unsigned tot = 0;
+            for (int w = 0; w < 8; w++) { const unsigned c = warp_cnt[q][w]; warp_cnt[q][w] = tot; tot += c; }
+            base[q] = tot ? offsets[q] + atomicAdd(cursor + q, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < a.n && b1 >= b0) rec = make_float4(a.x[k], a.y[k], a.mode ? a.lpx[k] : 0.f, a.mode ? a.lpy[k] : 0.f);
+        for (int q = 0; q < b.n_bands; q++) {           // same ballots again: rank inside the warp
+            const bool in = q >= b0 && q <= b1;
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) out[base[q] + warp_cnt[q][warp] + __popc(m & ((1u << lane) - 1u))] = rec;
+        }
+        __syncthreads();
     }
 }
 
@@ -438,10 +468,10 @@ extern "C" int pb_render_band_scatter_dev(size_t n, const float* d_x, const floa
                                           double y_max, double x_max, double min_blur_width, int mode,
                                           int n_pixel_y, int n_pixel_x, int n_bands, const int* band_rows,
                                           const unsigned long long* d_offsets, unsigned long long* d_cursor,
-                                          float* d_out_x, float* d_out_y, float* d_out_lpx, float* d_out_lpy,
-                                          void* stream) {
+                                          float* d_records, void* stream) {
     if (mode < 0 || mode > 2) { pb_set_error("blur_method not understood."); return PB_ERR_INVALID; }
     if (n_bands < 1 || n_bands > kMaxBands || !band_rows || !d_offsets || !d_cursor) { pb_set_error("pb_render_band_scatter_dev: bad band list"); return PB_ERR_INVALID; }
+    if (reinterpret_cast<uintptr_t>(d_records) & 15) { pb_set_error("pb_render_band_scatter_dev: records must be 16-byte aligned"); return PB_ERR_INVALID; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     PB_CUDA_CHECK(cudaMemsetAsync(d_cursor, 0, 8 * (size_t)n_bands, s));
     if (n == 0) return PB_OK;
@@ -450,8 +480,32 @@ extern "C" int pb_render_band_scatter_dev(size_t n, const float* d_x, const floa
     BandArgs b;
     b.n_bands = n_bands;
     for (int q = 0; q <= n_bands; q++) b.rows[q] = band_rows[q];
+    const int grid = (int)std::min<long long>(((long long)n + 255) / 256, 148 * 8);
+    render_band_scatter_kernel<<<grid, 256, 0, s>>>(a, b, d_offsets, d_cursor, reinterpret_cast<float4*>(d_records));
+    g_pb_launches++;
+    PB_CUDA_CHECK(cudaGetLastError());
+    return PB_OK;
+}
+
+// (x, y, lpx, lpy) float4 records -> the four float32 columns the renderer reads
+__global__ void __launch_bounds__(256) render_unpack_kernel(const float4* __restrict__ rec, long long n,
+                                                            float* __restrict__ x, float* __restrict__ y,
+                                                            float* __restrict__ lpx, float* __restrict__ lpy) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const float4 r = rec[k];
+        x[k] = r.x; y[k] = r.y; lpx[k] = r.z; lpy[k] = r.w;
+    }
+}
+extern "C" int pb_render_unpack_records_dev(size_t n, const float* d_records, float* d_x, float* d_y, float* d_lpx,
+                                            float* d_lpy, void* stream) {
+    if (n == 0) return PB_OK;
+    if (!d_records || !d_x || !d_y || !d_lpx || !d_lpy || (reinterpret_cast<uintptr_t>(d_records) & 15)) {
+        pb_set_error("pb_render_unpack_records_dev: bad pointer");
+        return PB_ERR_INVALID;
+    }
     const int grid = (int)std::min<long long>(((long long)n + 255) / 256, 148 * 16);
-    render_band_scatter_kernel<<<grid, 256, 0, s>>>(a, b, d_offsets, d_cursor, d_out_x, d_out_y, d_out_lpx, d_out_lpy);
+    render_unpack_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(d_records), (long long)n, d_x, d_y, d_lpx, d_lpy);
     g_pb_launches++;
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;

@@ -400,8 +400,10 @@ def _render_decl(l):
                                            i32, vp, vp, vp]
     l.pb_render_band_count_dev.restype = i32
     l.pb_render_band_scatter_dev.argtypes = [sz, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, i32, i32, i32,
-                                             i32, vp, vp, vp, vp, vp, vp, vp, vp]
+                                             i32, vp, vp, vp, vp, vp]
     l.pb_render_band_scatter_dev.restype = i32
+    l.pb_render_unpack_records_dev.argtypes = [sz, vp, vp, vp, vp, vp, vp]
+    l.pb_render_unpack_records_dev.restype = i32
     l.pb_render_workspace_bytes.restype = C.c_size_t
     l.pb_render_workspace_bytes.argtypes = [sz, i32, i32]
     l._band_declared = True
@@ -414,7 +416,7 @@ def render_bands_device(dist, torch, x, y, lpx, lpy, *, oversampling, viewport, 
 
     1. buckets its localizations by destination band on its GPU (``pb_render_band_count_dev`` /
        ``pb_render_band_scatter_dev``: a localization goes to every band its 3-sigma window reaches),
-    2. exchanges the records with ONE all-to-all per column (NCCL over NVLink),
+    2. exchanges the (x, y, lpx, lpy) records with ONE all-to-all (NCCL over NVLink),
     3. splats what it received into its own band (``pb_render_band_dev``, windows clipped to the
        band) -- no image reduction, and every rank downloads only its band.
 
@@ -461,17 +463,18 @@ def render_bands_device(dist, torch, x, y, lpx, lpy, *, oversampling, viewport, 
         offsets = torch.as_tensor(np.concatenate([[0], np.cumsum(mine)[:-1]]).astype(np.int64), device=dev)
         cursor = torch.zeros(world, dtype=torch.int64, device=dev)
         total = int(mine.sum())
-        send = [torch.empty(max(total, 1), dtype=torch.float32, device=dev) for _ in range(4 if mode else 2)]
+        send = torch.empty((max(total, 1), 4), dtype=torch.float32, device=dev)      # (x, y, lpx, lpy) records
         _lib.check(l.pb_render_band_scatter_dev(n, p(x), p(y), p(lpx), p(lpy), *args, npy, npx, world, rows_c,
-                                                offsets.data_ptr(), cursor.data_ptr(), send[0].data_ptr(),
-                                                send[1].data_ptr(), send[2].data_ptr() if mode else None,
-                                                send[3].data_ptr() if mode else None, st))
+                                                offsets.data_ptr(), cursor.data_ptr(), send.data_ptr(), st))
         mark("bucket")
-        recv = [exchange_variable(dist, torch, t[:total], mine, all_counts) for t in send]
+        recv = exchange_variable(dist, torch, send.view(-1)[: 4 * total], 4 * mine, 4 * all_counts)   # ONE all-to-all
         mark("exchange")
-        x, y = recv[0], recv[1]
-        lpx, lpy = (recv[2], recv[3]) if mode else (None, None)
-        n = int(x.numel())
+        n = int(recv.numel()) // 4
+        cols = torch.empty((4, max(n, 1)), dtype=torch.float32, device=dev)
+        _lib.check(l.pb_render_unpack_records_dev(n, recv.data_ptr() if n else None, cols[0].data_ptr(),
+                                                  cols[1].data_ptr(), cols[2].data_ptr(), cols[3].data_ptr(), st))
+        x, y = cols[0, :n], cols[1, :n]
+        lpx, lpy = (cols[2, :n], cols[3, :n]) if mode else (None, None)
     row0, row1 = rows[rank], rows[rank + 1]
     image = torch.empty((row1 - row0, npx), dtype=torch.float32, device=dev)
     count = torch.zeros(1, dtype=torch.int64, device=dev)

@@ -5,9 +5,11 @@ Drop-in for the fitting part of ``picasso.zfit`` (reference picasso/zfit.py): ``
 ``axial_localization_precision`` :706 and ``axial_localization_precision_astig`` :747 keep their
 signatures, returned DataFrames and error behaviour.  The per-localization
 ``scipy.optimize.minimize_scalar`` loop (:338-355) and the z / d_zcalib / lpz column arithmetic
-run in one CUDA kernel (csrc/zfit.cu) through the C ABI (``pb_zfit``); ``lib.ensure_sanity`` and
-the RMSD filter stay pandas on the host.  ``calibrate_z`` (the calibration itself) is outside
-the hot path.
+run in one CUDA kernel (csrc/zfit.cu) through the C ABI (``pb_zfit``).  For tables of 4-byte columns
+(everything the fit path produces) ``_fit_z`` is ONE fused device call (``pb_locs_filter``,
+csrc/table.cu): upload the columns once, z fit on the resident columns, ``lib.ensure_sanity`` as a
+fused mask + stream compaction, the RMSD filter with numpy's float32 pairwise sum reproduced bit for
+bit, one download of the kept rows.  ``calibrate_z`` (the calibration itself) is outside the hot path.
 """
 from __future__ import annotations
 
@@ -73,21 +75,44 @@ def filter_z_fits(locs: pd.DataFrame, range: int) -> pd.DataFrame:
     return locs
 
 
-def _fit_z(locs, info, calibration, magnification_factor, pixelsize, fitting_method="gausslq",
-           filter=2, progress_callback=None):
-    """Reference ``_fit_z`` (zfit.py:327-383)."""
-    locs = locs.copy()
-    cx = np.array(calibration["X Coefficients"])
-    cy = np.array(calibration["Y Coefficients"])
-    z, dz, lpz = _run(locs, cx, cy, magnification_factor, pixelsize, fitting_method)
+def _progress(n, progress_callback):
     if progress_callback == "console":
         from tqdm import tqdm
 
-        for _ in tqdm(range(len(z)), desc="Fitting z...", unit="locs"):
+        for _ in tqdm(range(n), desc="Fitting z...", unit="locs"):
             pass
     elif callable(progress_callback):
-        for i in range(len(z)):
+        for i in range(n):
             progress_callback(i)
+
+
+def _fit_z(locs, info, calibration, magnification_factor, pixelsize, fitting_method="gausslq",
+           filter=2, progress_callback=None):
+    """Reference ``_fit_z`` (zfit.py:327-383): z fit, ``locs["z" | "d_zcalib" | "lpz"]`` assigned,
+    ``lib.ensure_sanity``, ``filter_z_fits``.  Tables of 4-byte columns take the fused device path."""
+    cx = np.array(calibration["X Coefficients"])
+    cy = np.array(calibration["Y Coefficients"])
+    new_cols = ("z", "d_zcalib", "lpz")
+    base = locs[[c for c in locs.columns if c not in new_cols]] if any(c in locs.columns for c in new_cols) else locs
+    if len(locs) and lib._device_table_ok(base):
+        lib._check_sanity_keys(info)
+        method = _method_id(fitting_method, base.columns)
+        if cx.shape != (7,) or cy.shape != (7,):
+            raise ValueError("calibration needs 7 X and 7 Y coefficients")
+        names = list(base.columns)
+        ci = lambda c: names.index(c) if c in names else -1      # noqa: E731
+        spec = lib.ZfitSpec(ci("sx"), ci("sy"), ci("photons"), ci("bg"),
+                            ci("sx_unc") if method == 2 else -1, ci("sy_unc") if method == 2 else -1,
+                            (C.c_double * 7)(*cx.astype(np.float64)), (C.c_double * 7)(*cy.astype(np.float64)),
+                            float(magnification_factor), float(pixelsize), method, int(filter))
+        out = lib._filter_table(base, info, zspec=spec, extra_names=new_cols)
+        _progress(len(locs), progress_callback)
+        # column order of the reference: existing z / d_zcalib / lpz columns keep their place
+        order = list(locs.columns) + [c for c in new_cols if c not in locs.columns]
+        return out if list(out.columns) == order else out[order]
+    locs = locs.copy()
+    z, dz, lpz = _run(locs, cx, cy, magnification_factor, pixelsize, fitting_method)
+    _progress(len(z), progress_callback)
     locs["z"] = z
     locs["d_zcalib"] = dz
     locs["lpz"] = lpz

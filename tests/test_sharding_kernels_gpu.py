@@ -53,10 +53,17 @@ def test_row_bands_concatenate_to_the_full_render(torch, bm, world):
     offs = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int64)
     offsets = torch.from_numpy(offs).to(dev)
     cursor = torch.zeros(world, dtype=torch.int64, device=dev)
-    send = [torch.empty(int(cnt.sum()) + 1, dtype=torch.float32, device=dev) for _ in range(4)]
+    rec = torch.empty((int(cnt.sum()) + 1, 4), dtype=torch.float32, device=dev)
     _lib.check(l.pb_render_band_scatter_dev(n, p(x), p(y), p(lpx), p(lpy), *args, npy, npx, world, rows_c,
-                                            offsets.data_ptr(), cursor.data_ptr(), *[s.data_ptr() for s in send], None))
+                                            offsets.data_ptr(), cursor.data_ptr(), rec.data_ptr(), None))
     np.testing.assert_array_equal(cursor.cpu().numpy(), cnt)
+    send = [torch.empty(int(cnt.sum()) + 1, dtype=torch.float32, device=dev) for _ in range(4)]
+    _lib.check(l.pb_render_unpack_records_dev(int(cnt.sum()), rec.data_ptr(), *[s.data_ptr() for s in send], None))
+    # every in-view localization was written exactly once per band it reaches: the multiset of records of
+    # all bands contains each in-view localization at least once
+    got = np.sort(send[0][: int(cnt.sum())].cpu().numpy())
+    xin = locs["x"].to_numpy()[(locs["x"] > 0) & (locs["y"] > 0) & (locs["x"] < 48) & (locs["y"] < 64)]
+    assert len(got) >= len(xin) and np.isin(xin, got).all()
     bands, k_sum = [], 0
     for b in range(world):
         sl = slice(int(offs[b]), int(offs[b] + cnt[b]))

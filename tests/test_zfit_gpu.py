@@ -101,3 +101,90 @@ def test_localize_3d_equals_localize_plus_zfit(method):
     with pytest.raises(AssertionError):
         localize.localize_3D(movie, movie_info=minfo, camera_info=cam, box=6, minimum_ng=5000,
                              calibration_3d=calib)
+
+
+def _messy_table(n=200_000, seed=2):
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    t = pd.DataFrame({
+        "frame": rng.integers(0, 1000, n).astype(np.uint32),
+        "x": rng.uniform(-2, 70, n).astype(np.float32), "y": rng.uniform(-2, 50, n).astype(np.float32),
+        "photons": rng.uniform(-10, 5000, n).astype(np.float32), "sx": rng.uniform(-0.1, 2, n).astype(np.float32),
+        "sy": rng.uniform(0.5, 2, n).astype(np.float32), "bg": rng.uniform(0, 50, n).astype(np.float32),
+        "lpx": rng.uniform(-0.01, 0.2, n).astype(np.float32), "lpy": rng.uniform(0.0, 0.2, n).astype(np.float32),
+        "ellipticity": rng.uniform(-0.01, 0.5, n).astype(np.float32),
+        "net_gradient": rng.uniform(-5e3, 5e4, n).astype(np.float32),       # may be negative: not filtered
+        "group": rng.integers(-3, 3, n).astype(np.int32),
+    })
+    for c, v in (("bg", np.nan), ("net_gradient", np.inf), ("lpy", -np.inf), ("x", np.nan)):
+        t.loc[rng.integers(0, n, 50), c] = np.float32(v)
+    return t, [{"Width": 64, "Height": 48, "Frames": 1000, "Pixelsize": 130}]
+
+
+def test_ensure_sanity_device_equals_host_chain():
+    """lib.ensure_sanity on the GPU (fused mask + stream compaction, csrc/table.cu) keeps exactly the
+    rows, index labels, dtypes and values of the reference's filter chain (lib.py:1786-1832; host
+    single-mask form pinned in tests/test_host_logic_cpu.py)."""
+    import pandas as pd
+
+    from picasso_b200 import lib
+
+    t, info = _messy_table()
+    assert lib._device_table_ok(t)
+    got = lib.ensure_sanity(t, info)
+    ref = lib._ensure_sanity_host(t, info)
+    assert 0 < len(ref) < len(t)
+    pd.testing.assert_frame_equal(got, ref)
+    # the reference's own chain, literally
+    r = t.copy()
+    r.replace([np.inf, -np.inf], np.nan, inplace=True)
+    r.dropna(axis=0, how="any", inplace=True)
+    r = r[r["x"] < 64]; r = r[r["y"] < 48]
+    for attr in ["x", "y", "lpx", "lpy", "photons", "ellipticity", "sx", "sy"]:
+        r = r[r[attr] >= 0]
+    pd.testing.assert_frame_equal(got, r)
+    # a non-default index is carried through
+    t2 = t.set_index(np.arange(len(t))[::-1] * 3)
+    pd.testing.assert_frame_equal(lib.ensure_sanity(t2, info), lib._ensure_sanity_host(t2, info))
+    # tables with 8-byte columns take the host path, same rows
+    t3 = t.copy(); t3["n_id"] = np.arange(len(t), dtype=np.int64)
+    assert not lib._device_table_ok(t3)
+    assert lib.ensure_sanity(t3, info).index.equals(ref.index)
+    with pytest.raises(KeyError):
+        lib.ensure_sanity(t, [{"Width": 64, "Height": 48}])
+
+
+def test_locs_to_records_matches_save_locs_packing():
+    """io.save_locs (reference io.py:2089-2110): lib.ensure_sanity(locs, info).to_records(index=False);
+    sanity filter, compaction and the column -> record transposition on the device."""
+    from picasso_b200 import lib
+
+    t, info = _messy_table(50_000, seed=4)
+    rec = lib.locs_to_records(t, info)
+    ref = lib._ensure_sanity_host(t, info).to_records(index=False)
+    assert rec.dtype == ref.dtype and rec.shape == ref.shape
+    assert rec.tobytes() == ref.tobytes()
+
+
+def test_fused_zfit_equals_stepwise_path(g):
+    """The fused device call (upload once -> z fit -> ensure_sanity -> RMSD filter with numpy's float32
+    pairwise sum -> one download) against the step-by-step host path, 150 k localizations, filter 0 / 2
+    / 3, incl. rows the sanity pass removes."""
+    import pandas as pd
+
+    from picasso_b200 import lib
+
+    locs, info, calib = testing.synthetic_zfit_locs(150_000, 7)
+    rng = np.random.default_rng(0)
+    locs.loc[rng.integers(0, len(locs), 300), "photons"] = np.float32(-1.0)
+    locs.loc[rng.integers(0, len(locs), 300), "sx"] = np.float32(np.nan)
+    cx, cy = np.array(calib["X Coefficients"]), np.array(calib["Y Coefficients"])
+    for flt in (0, 2, 3):
+        got = zfit._fit_z(locs, info, calib, calib["Magnification factor"], 130, "gaussmle", flt)
+        step = locs.copy()
+        z, dz, lpz = zfit._run(step, cx, cy, calib["Magnification factor"], 130, "gaussmle")
+        step["z"], step["d_zcalib"], step["lpz"] = z, dz, lpz
+        step = zfit.filter_z_fits(lib._ensure_sanity_host(step, info), flt)
+        assert 0 < len(step) < len(locs)
+        pd.testing.assert_frame_equal(got, step)

@@ -57,7 +57,10 @@ if __name__ == "__main__":
         run_one()
     else:
         print(open('/sys/kernel/mm/transparent_hugepage/enabled').read().strip(), flush=True)
-        for t in (4, 12):
-            env = dict(os.environ, PB_COPY_THREADS=str(t))
-            out = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
-            print(t, out.stdout.strip() or out.stderr[-300:], flush=True)
+        print("cores", os.cpu_count(), flush=True)
+        for t in (4, 8, 12, 16):
+            for stream in (0, 1):
+                env = dict(os.environ, PB_COPY_THREADS=str(t), PB_COPY_STREAM=str(stream))
+                out = subprocess.run([sys.executable, __file__, "one"], env=env, capture_output=True, text=True)
+                print(json.dumps({"threads": t, "streaming_stores": stream}), out.stdout.strip() or out.stderr[-300:],
+                      flush=True)

@@ -211,7 +211,15 @@ def stage_localize(ctx, frames=2000, Y=512, X=512, chunk=100):
     # ---- parity ----
     parity = {}
     if ctx.world > 1:
-        full = torch.cat([gen_movie_chunk(torch, c, chunk, Y, X, ctx.dev) for c in range(nchunks)])
+        # the SAME movie on one GPU: the blocks of all ranks are all-gathered (regenerating them would not
+        # be bit-reproducible -- the generator accumulates overlapping emitters with float atomics)
+        fmax = max(cb[r + 1] - cb[r] for r in range(ctx.world)) * chunk
+        pad = torch.zeros((fmax, Y, X), dtype=torch.int16, device=ctx.dev)
+        pad[:nf] = movie
+        allb = torch.empty((ctx.world, fmax, Y, X), dtype=torch.int16, device=ctx.dev)
+        dist.all_gather_into_tensor(allb.view(-1), pad.view(-1))
+        full = torch.cat([allb[r, : (cb[r + 1] - cb[r]) * chunk] for r in range(ctx.world)])
+        del allb, pad
         one = pbd.localize_device(torch, full, 0, CAM, PARAMS, fitting_method="gausslq")
         same = bool(one.shape == table.shape and torch.equal(one.view(torch.int32), table.view(torch.int32)))
         same_e2e = bool(torch.equal(result["e2e_cols"].view(torch.int32), table.cpu().view(torch.int32)))
