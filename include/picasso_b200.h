@@ -223,6 +223,21 @@ int pb_lq_fit_dev(size_t n, int box, const float* d_spots, float* d_thetas, int*
  * 1 = MINPACK-order Householder qrfac on the m x 6 Jacobian (A/B parity and speed runs) */
 int pb_lq_set_impl(int impl);
 
+/* ---- Gpufit-path least-squares fit ("gausslq-gpu") -----------------------------------------
+ * Replaces the call into the vendored Gpufit 1.2.0 DLL: picasso.gausslq.fit_spots_gpufit
+ * (picasso/gausslq.py:346-395) = _initial_parameters_gpufit (:128-148) + gpufit_fit
+ * (picasso/ext/pygpufit/gpufit.py:40-61; GAUSS_2D_ELLIPTIC, LSE, tolerance, max iterations) +
+ * amplitude * 2 pi sx sy (:393).  Gpufit's published float32 LM algorithm, one thread per fit
+ * (csrc/gpufit_core.cuh); parity with the Windows binary is unpinned.
+ *   spots   (n, box, box) float32, box odd 5..15
+ *   params  (n, 6) float32 [photons, x, y, sx, sy, bg], x / y in pixel indices of the box
+ *   states  (n) int32 nullable: 0 converged, 1 max iterations, 2 singular Hessian (Gpufit's codes)
+ *   chi2    (n) float32 nullable;  n_iterations (n) int32 nullable */
+int pb_gpufit_fit(size_t n, int box, const float* spots, float tolerance, int max_iterations,
+                  float* params, int* states, float* chi2, int* n_iterations);
+int pb_gpufit_fit_dev(size_t n, int box, const float* d_spots, float tolerance, int max_iterations,
+                      float* d_params, int* d_states, float* d_chi2, int* d_n_iterations, void* stream);
+
 /* ---- astigmatic z fit ----------------------------------------------------------
  * Replaces the per-localization loop and column arithmetic of picasso.zfit._fit_z
  * (picasso/zfit.py:327-383, behind zfit.zfit :465-646 / localize.localize_3D

@@ -415,9 +415,11 @@ static int localize_impl(bool on_device, const void* movie, int dtype, size_t n_
                 return rc;
             PB_CUDA_CHECK(cudaEventRecord(P->cut[s], cs));
             if (fit <= 1) rc = pb_mle_fit_dev(n, box, d_sp, eps, max_it, fit, d_th, d_cr, d_ll, d_it, d_st, cs);
-            else rc = pb_lq_fit_dev(n, box, d_sp, d_th, d_it, d_st, cs);
+            else if (fit == 2) rc = pb_lq_fit_dev(n, box, d_sp, d_th, d_it, d_st, cs);
+            else rc = pb_gpufit_fit_dev(n, box, d_sp, 1e-2f, 20, d_th, d_st, d_ll, d_it, cs);   // "gausslq-gpu"
             if (rc != PB_OK) return rc;
-            if ((rc = pb_locs_from_fits_dev(n, fit == 3 ? 4 : fit, box, em, sf, sx, sy, sng, d_th, d_cr, d_ll, d_it,
+            // fit 3: theta is in Gpufit's layout [photons, x, y, sx, sy, bg] -> locs_from_fits_gpufit (kind 3)
+            if ((rc = pb_locs_from_fits_dev(n, fit, box, em, sf, sx, sy, sng, d_th, d_cr, d_ll, d_it,
                                             P->cols.p, dcap, cs)))
                 return rc;
             if (on_device) {

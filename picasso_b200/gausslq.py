@@ -115,26 +115,38 @@ def _initial_parameters_gpufit(spots, size: int) -> np.ndarray:
     return p
 
 
-def fit_spots_gpufit(spots) -> np.ndarray:
-    """GPU least-squares fit with the column layout of the reference's Gpufit
-    path (gausslq.py:346-395): ``[photons, x, y, sx, sy, bg]`` with x, y in box
-    coordinates (0 .. size-1), so ``locs_from_fits_gpufit`` applies unchanged.
+def fit_spots_gpufit(spots, return_info: bool = False) -> np.ndarray:
+    """The reference's Gpufit path (gausslq.py:346-395): start values
+    ``_initial_parameters_gpufit``, Gpufit's float32 Levenberg-Marquardt on ``GAUSS_2D_ELLIPTIC`` with
+    tolerance 1e-2 and at most 20 iterations, then amplitude -> photons (``* 2 pi sx sy``).  Returns
+    ``[photons, x, y, sx, sy, bg]`` with x, y in box coordinates (0 .. size-1), so
+    ``locs_from_fits_gpufit`` applies unchanged.
 
-    The vendored Gpufit binary (Windows, sm_86) cannot run on Linux/B200 and ships
-    without source; this entry point runs the same MINPACK-faithful kernel as
-    ``fit_spots``.  Parity with Gpufit itself is therefore unpinned.
-    """
-    spots = np.asarray(spots)
-    theta = _fit(spots)
-    half = int(spots.shape[1] / 2)
-    out = np.empty_like(theta)
-    out[:, 0] = theta[:, 2]
-    out[:, 1] = theta[:, 0] + half
-    out[:, 2] = theta[:, 1] + half
-    out[:, 3] = theta[:, 4]
-    out[:, 4] = theta[:, 5]
-    out[:, 5] = theta[:, 3]
-    return out
+    The vendored Gpufit 1.2.0 binary (Windows DLL, no source) cannot run on Linux / B200; the kernel
+    (csrc/gpufit_lm.cu) runs Gpufit's PUBLISHED algorithm -- its own start values and trajectory, not
+    the MINPACK result relabelled.  Parity with the binary itself is unpinned (DESIGN.md section 4);
+    the CPU oracle restates the same algorithm, and both agree with ``fit_spots`` within the LQ
+    tolerance (tests/test_lq_gpu.py)."""
+    lib = _lib.load()
+    _lib.require_gpu()
+    vp, i32, sz, f32 = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+    lib.pb_gpufit_fit.argtypes = [sz, i32, vp, f32, i32, vp, vp, vp, vp]
+    lib.pb_gpufit_fit.restype = i32
+    spots = np.ascontiguousarray(spots, dtype=np.float32)
+    if spots.ndim != 3 or spots.shape[1] != spots.shape[2]:
+        raise ValueError("spots must have shape (n_spots, size, size)")
+    n, box, _ = spots.shape
+    params = _lib.pinned_empty((n, 6), np.float32)
+    states = np.zeros(n, np.int32) if return_info else None
+    chi2 = np.zeros(n, np.float32) if return_info else None
+    nit = np.zeros(n, np.int32) if return_info else None
+    if n:
+        p = lambda a: _lib.ptr(a) if a is not None else None      # noqa: E731
+        _lib.check(lib.pb_gpufit_fit(n, box, _lib.ptr(spots), 1e-2, 20, _lib.ptr(params), p(states), p(chi2),
+                                     p(nit)))
+    if return_info:
+        return params, states, chi2, nit
+    return params
 
 
 def localization_precision(photons, s, s_orth, bg, em: bool):

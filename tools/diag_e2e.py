@@ -15,6 +15,43 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def alloc_probe():
+    """pb_host_alloc of 560 MB: time and DMA rate from the block (run once per PB_HOST_HUGEPAGES mode)."""
+    import ctypes as C
+
+    import torch
+
+    from picasso_b200 import _lib
+
+    l = _lib.load()
+    nbytes = 560_000_000
+    torch.zeros(1, device="cuda")
+    res = {"hugepages": os.environ.get("PB_HOST_HUGEPAGES", "default(1)")}
+    ts = []
+    ptrs = []
+    for _ in range(3):
+        p = C.c_void_p()
+        t0 = time.perf_counter()
+        _lib.check(l.pb_host_alloc(C.byref(p), nbytes))
+        ts.append(time.perf_counter() - t0)
+        ptrs.append(p)
+    res["alloc_ms"] = [round(1e3 * t, 1) for t in ts]
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for name, fn in (("h2d", lambda: l.pb_copy_h2d(dev.data_ptr(), ptrs[0], nbytes, st)),
+                     ("d2h", lambda: l.pb_copy_d2h(ptrs[0], dev.data_ptr(), nbytes, st))):
+        best = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        res[name + "_GBs"] = round(nbytes / best / 1e9, 1)
+    t0 = time.perf_counter()
+    for p in ptrs:
+        l.pb_host_free(p)
+    res["free_ms_each"] = round(1e3 * (time.perf_counter() - t0) / 3, 1)
+    print(json.dumps(res), flush=True)
+
+
 def main():
     import torch
 
@@ -88,4 +125,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "alloc":
+        alloc_probe()
+    else:
+        main()
