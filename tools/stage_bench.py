@@ -217,7 +217,7 @@ def stage_localize(ctx, frames=2000, Y=512, X=512, chunk=100):
         pad = torch.zeros((fmax, Y, X), dtype=torch.int16, device=ctx.dev)
         pad[:nf] = movie
         allb = torch.empty((ctx.world, fmax, Y, X), dtype=torch.int16, device=ctx.dev)
-        dist.all_gather_into_tensor(allb.view(-1), pad.view(-1))
+        dist.all_gather_into_tensor(allb.view(torch.uint8).view(-1), pad.view(torch.uint8).view(-1))   # NCCL has no int16
         full = torch.cat([allb[r, : (cb[r + 1] - cb[r]) * chunk] for r in range(ctx.world)])
         del allb, pad
         one = pbd.localize_device(torch, full, 0, CAM, PARAMS, fitting_method="gausslq")
