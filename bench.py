@@ -408,8 +408,21 @@ def main():
     # (picasso_b200.distributed.PeerGather: no SM taken from the running fit, no host blocking),
     # "nccl" = one NCCL all-gather per step (PB_GATHER=nccl).  If the peer mapping cannot be set up
     # on every rank the run falls back to NCCL.
-    gather_mode = os.environ.get("PB_GATHER", "p2p") if world > 1 else "none"
-    gathered, pg = None, None
+    gather_mode = os.environ.get("PB_GATHER", "nvls") if world > 1 else "none"
+    gathered, pg, mcb = None, None, None
+    if world > 1 and gather_mode == "nvls":
+        # fused fit + all-gather: the CRLB kernel stores every spot's results through an NVSwitch multicast
+        # mapping into the gather buffers of all ranks (picasso_b200.distributed.MulticastBuffer)
+        from picasso_b200.distributed import MulticastBuffer
+        import ctypes as C
+        lib.pb_mle_fit_gather_dev.argtypes = [C.c_size_t, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int] + \
+            [C.c_void_p] * 7
+        lib.pb_mle_fit_gather_dev.restype = C.c_int
+        try:
+            mcb = MulticastBuffer(dist, torch, 14 * n * 4, dev)
+        except Exception as exc:      # noqa: BLE001
+            print(f"[bench] rank {rank}: multicast gather unavailable ({exc}); using peer copies", file=sys.stderr)
+            gather_mode = "p2p"
     if world > 1 and gather_mode == "p2p":
         from picasso_b200.distributed import PeerGather
         ok = torch.ones(1, device=dev)
@@ -467,6 +480,11 @@ def main():
         pend = []
         for q in range(parts):
             th, cr, ll, it, base, lo, m = views(flat, q)
+            if mcb is not None:
+                _lib.check(lib.pb_mle_fit_gather_dev(m, BOX, spots[lo:].data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
+                                                     cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
+                                                     mcb.block_mc_ptr() + 14 * lo * 4, stream.cuda_stream))
+                continue
             _lib.check(lib.pb_mle_fit_dev(m, BOX, spots[lo:].data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
                                           cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
                                           stream.cuda_stream))
@@ -524,27 +542,48 @@ def main():
     drain()          # every step's gather has left this rank inside the timed region (max over ranks)
     e1.record()
     barrier()
-    gather_ok = None
-    if world > 1:
-        # the gathered array is complete and correct: per-rank checksums of the last block
-        mine = flats[(args.steps - 1) % len(flats)].view(torch.int32).to(torch.int64).sum().reshape(1)
-        sums = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(sums, mine)
-        if pg is not None:
-            pg.finish()
-            full = pg.to_tensor(torch.int32)
-        else:
-            full = None
-        if full is not None:
-            got = full.view(world, -1).to(torch.int64).sum(1)
-        else:                                  # NCCL: one [world x part] buffer per part
-            got = torch.zeros(world, dtype=torch.int64, device=dev)
-            for gp in gathered_parts.values():
-                got += gp.view(torch.int32).view(world, -1).to(torch.int64).sum(1)
-        gather_ok = bool((got == sums).all().item())
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
+    gather_ok, verified_steps = None, 0
+
+    def gathered_equals_nccl(b):
+        """The gathered array of the step that wrote flats[b], element for element, against an NCCL
+        all-gather of the same blocks (all ranks)."""
+        ref = torch.empty(14 * n * world, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(ref, flats[b])
+        if mcb is not None:
+            full = mcb.local(torch.int32)
+        elif pg is not None:
+            pg.finish()
+            full = pg.to_tensor(torch.int32)
+        else:
+            full = torch.cat([gp.view(torch.int32).view(world, -1) for gp in gathered_parts.values()], 1).reshape(-1)
+        same = torch.tensor([1.0 if torch.equal(full.view(torch.int32), ref.view(torch.int32)) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        return bool(same.item() > 0.5)
+
+    if world > 1:
+        # the gathered array of the LAST timed step is complete and correct on every rank ...
+        gather_ok = gathered_equals_nccl((args.steps - 1) % len(flats))
+        # ... and so is every step of an untimed verification pass (same launches as the timed loop): the
+        # data of each step are perturbed (one spot block is rotated) so that a stale buffer cannot pass
+        if parts == 1:
+            for v in range(args.steps):
+                spots[:4096] = torch.roll(spots[:4096], shifts=v + 1, dims=0)
+                b = v % len(flats)
+                wait_all(works[b])
+                works[b] = fit_and_gather(flats[b], b)
+                drain()
+                barrier()
+                if not gathered_equals_nccl(b):
+                    gather_ok = False
+                    break
+                verified_steps += 1
+                barrier()
+            works[0] = fit_and_gather(flats[0], 0)      # flats[0] again holds the fit of the final `spots`
+            drain()
+            barrier()
     ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
     k3 = np.zeros(3, np.float32)          # {start values, iterations, CRLB} of the last step
     if lib.pb_mle_get_impl() != 0:
@@ -678,11 +717,16 @@ def main():
                        "parallelism": f"spots sharded by index over {world} GPU(s)"
                                       + ({"nccl": "; one NCCL all-gather of the packed outputs per step, "
                                                   "overlapped with the next step's fit",
+                                          "nvls": "; all-gather of the packed outputs FUSED into the fit: the kernel that "
+                                                  "finishes a spot stores its 56 B of results through an NVSwitch "
+                                                  "multicast mapping (multimem.st) into the gather buffers of all "
+                                                  "ranks (PB_GATHER=p2p / nccl select the unfused variants)",
                                           "p2p": "; all-gather of the packed outputs per step by copy-engine "
                                                  "peer writes into IPC-shared buffers over NVLink "
                                                  "(PeerGather; PB_GATHER=nccl selects one NCCL all-gather), "
                                                  "overlapped with the next step's fit"}.get(gather_mode, "")),
-                       "gather": gather_mode, "gather_verified": gather_ok, "parts_per_step": parts},
+                       "gather": gather_mode, "gather_verified": gather_ok,
+                       "gather_verified_steps": verified_steps, "parts_per_step": parts},
             "roofline": roof,
             # instruction-side view of the dominant kernel from the committed ncu --set full
             # capture (profiles/r01_mle_tps_ncu.md): what actually bounds the fit
@@ -717,6 +761,8 @@ def main():
         _emit(line)
     if pg is not None:
         pg.close()
+    if mcb is not None:
+        mcb.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -260,6 +260,30 @@ int pb_zfit_dev(size_t n, const float* d_sx, const float* d_sy, const float* d_p
                 const double* cy, double magnification, double pixelsize, int method, float* d_z,
                 float* d_d_zcalib, float* d_lpz, int* d_nfev, void* stream);
 
+/* ---- NVSwitch multicast (NVLS) buffers and the fused fit + all-gather ------------------------
+ * the sharded fit exchanges one thing, the all-gather of every rank's packed output
+ * block.  A multicast object binds memory of all N GPUs at the same offsets; a store to the
+ * multicast mapping is replicated by the switch into every GPU's copy.  One process per GPU:
+ *   rank 0        pb_mc_create -> POSIX file descriptor, passed to the other ranks (Unix socket)
+ *   other ranks   pb_mc_import(fd)
+ *   all ranks     pb_mc_add_device; BARRIER; pb_mc_bind_map -> uc_ptr (this GPU's copy, ordinary
+ *                 pointer) and mc_ptr (multicast mapping, store-only); BARRIER before first use
+ * pb_mle_fit_gather_dev is pb_mle_fit_dev whose finishing kernel also stores each spot's 14 output
+ * words through `mc_block` = mc_ptr + this rank's block offset, block layout
+ * [thetas 6n | crlbs 6n | logliks n | iterations n] (n even): compute and collective in one kernel.
+ * pb_mc_copy_async pushes an existing device buffer through the mapping (a few CTAs). */
+int pb_mc_supported(void);
+int pb_mc_padded_size(size_t bytes, int n_devices, size_t* padded);
+int pb_mc_create(size_t padded_bytes, int n_devices, void** handle, int* export_fd);
+int pb_mc_import(int fd, size_t padded_bytes, int n_devices, void** handle);
+int pb_mc_add_device(void* handle);
+int pb_mc_bind_map(void* handle, void** uc_ptr, void** mc_ptr);
+int pb_mc_destroy(void* handle);
+int pb_mc_copy_async(void* mc_dst, const void* d_src, size_t bytes, int n_ctas, void* stream);
+int pb_mle_fit_gather_dev(size_t n, int box, const float* d_spots, double eps, int max_it, int method,
+                          float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
+                          int* d_status, void* mc_block, void* stream);
+
 /* ---- localisation table: ensure_sanity, z-fit filter, record packing on the device ----------
  * Replaces lib.ensure_sanity (picasso/lib.py:1786-1832), the tail of zfit._fit_z (picasso/zfit.py:
  * 356-383: append z / d_zcalib / lpz, ensure_sanity, filter_z_fits :675-704) and the record packing

@@ -294,6 +294,8 @@ static int localize_impl(bool on_device, const void* movie, int dtype, size_t n_
         const long v = atol(e);
         if (v >= 1) chunk = (size_t)v;
     }
+    if (on_device) chunk = std::max<size_t>(chunk, ((size_t)512 << 20) / fsz);   // resident movie: no staging limit,
+                                                                                 // fewer per-chunk count read-backs
     chunk = std::min(chunk, std::min<size_t>(n_frames, (size_t)1 << 22));
     const bool pinned_src = on_device || pb_host_is_pinned(movie);
     for (int s = 0; s < 2 && !on_device; s++) {

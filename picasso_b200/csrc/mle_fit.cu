@@ -883,7 +883,7 @@ int dispatch_box(int box, const MleArgs& a, cudaStream_t stream) {
 bool pb_mle_tps_supports(int box);
 int pb_mle_tps_fit(size_t n, int box, const float* d_spots, double eps, int max_it, int method,
                    float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
-                   int* d_status, cudaStream_t stream, int pixel_f32);
+                   int* d_status, cudaStream_t stream, int pixel_f32, float* mc_block = nullptr);
 
 // Implementation selector: 0 = lane-group kernel (this file), 1 = thread-per-spot with float64
 // per-pixel sums, 2 = thread-per-spot with float32 per-pixel sums (default for box <= 13).
@@ -934,4 +934,34 @@ extern "C" int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double ep
         return pb_mle_tps_fit(n, box, d_spots, eps, max_it, method, d_thetas, d_crlbs, d_logliks,
                               d_iterations, d_status, s, impl == 2);
     return method == 1 ? dispatch_box<1>(box, a, s) : dispatch_box<0>(box, a, s);
+}
+
+// Fused fit + all-gather (multi-GPU): as pb_mle_fit_dev, and the kernel that finishes a spot (CRLB /
+// log-likelihood pass) also stores the spot's 14 output words through `mc_block`, the NVSwitch
+// MULTICAST address of this rank's block [thetas 6n | crlbs 6n | logliks n | iterations n] of the gather
+// buffer (csrc/multicast.cu): the switch replicates every store into all ranks' buffers, so the
+// all-gather of the results costs one store stream per rank and no copy, kernel or collective after the
+// fit.  The data are complete on all ranks once every rank's stream has passed the call and the ranks
+// have synchronised (barrier).
+extern "C" int pb_mle_fit_gather_dev(size_t n, int box, const float* d_spots, double eps, int max_it,
+                                     int method, float* d_thetas, float* d_crlbs, float* d_logliks,
+                                     int* d_iterations, int* d_status, void* mc_block, void* stream) {
+    if (method != 0 && method != 1) { pb_set_error("Method not available."); return PB_ERR_INVALID; }
+    if (n == 0) return PB_OK;
+    if (!d_spots || !d_thetas || !d_crlbs || !d_logliks || !d_iterations || !mc_block) {
+        pb_set_error("pb_mle_fit_gather_dev: null device pointer");
+        return PB_ERR_INVALID;
+    }
+    if ((reinterpret_cast<uintptr_t>(mc_block) & 15) || (n & 1)) {
+        pb_set_error("pb_mle_fit_gather_dev: the gather block must be 16-byte aligned and n even");
+        return PB_ERR_INVALID;
+    }
+    const int impl = mle_impl();
+    if (impl == 0 || !pb_mle_tps_supports(box)) {
+        pb_set_error("pb_mle_fit_gather_dev: needs the thread-per-spot kernels (box <= 13, impl 1 or 2)");
+        return PB_ERR_INVALID;
+    }
+    if (max_it < 0) max_it = 0;
+    return pb_mle_tps_fit(n, box, d_spots, eps, max_it, method, d_thetas, d_crlbs, d_logliks, d_iterations,
+                          d_status, reinterpret_cast<cudaStream_t>(stream), impl == 2, static_cast<float*>(mc_block));
 }

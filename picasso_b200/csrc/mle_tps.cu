@@ -60,7 +60,17 @@ struct TpsArgs {
     int* iterations;
     int* status;
     unsigned long long* counter;
+    float* mc_block;     // multicast address of this rank's gather block (fused all-gather), or null
 };
+
+// multimem.st: a store to a multicast address, replicated by the NVSwitch into the bound memory of
+// every device of the team (SASS: STG.E.STRONG.SYS on a multicast mapping)
+__device__ __forceinline__ void mc_st_v2(float* p, float a, float b) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mc_st_b32(void* p, unsigned v) {
+    asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ---- accessors -----------------------------------------------------------------
 struct RoiSlot {   // one spot's pixels, contiguous floats in shared memory
@@ -414,6 +424,16 @@ __global__ void __launch_bounds__(kThreads, PB_CRLB_MINB) tps_crlb_kernel(const 
         out[2] = make_float2(cr[4], cr[5]);
         a.logliks[s] = ll;
         if (a.status && st) a.status[s] |= st;
+        if (a.mc_block) {
+            // fused all-gather: this spot's 14 output words go through the multicast mapping into the
+            // gather buffers of ALL ranks, block layout [thetas 6n | crlbs 6n | logliks n | iterations n]
+            float* mt = a.mc_block + s * 6;
+            mc_st_v2(mt, th[0], th[1]); mc_st_v2(mt + 2, th[2], th[3]); mc_st_v2(mt + 4, th[4], th[5]);
+            float* mc = a.mc_block + 6 * a.n + s * 6;
+            mc_st_v2(mc, cr[0], cr[1]); mc_st_v2(mc + 2, cr[2], cr[3]); mc_st_v2(mc + 4, cr[4], cr[5]);
+            mc_st_b32(a.mc_block + 12 * a.n + s, __float_as_uint(ll));
+            mc_st_b32(a.mc_block + 13 * a.n + s, (unsigned)a.iterations[s]);
+        }
     }
 }
 
@@ -545,9 +565,9 @@ bool pb_mle_tps_supports(int box) { return box >= 5 && box <= 13 && (box & 1); }
 
 int pb_mle_tps_fit(size_t n, int box, const float* d_spots, double eps, int max_it, int method,
                    float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
-                   int* d_status, cudaStream_t stream, int pixel_f32) {
+                   int* d_status, cudaStream_t stream, int pixel_f32, float* mc_block) {
     TpsArgs a{d_spots, (long long)n, eps, max_it, d_thetas, d_crlbs, d_logliks, d_iterations,
-              d_status, nullptr};
+              d_status, nullptr, mc_block};
     if (method == 1)
         return pixel_f32 ? dispatch_tps<1, float>(box, a, stream) : dispatch_tps<1, double>(box, a, stream);
     return pixel_f32 ? dispatch_tps<0, float>(box, a, stream) : dispatch_tps<0, double>(box, a, stream);

@@ -276,11 +276,15 @@ __global__ void render_scatter_kernel(const RenderArgs a, const int* __restrict_
 // far inside the 1e-4 render tolerance).
 constexpr int kMaxWin = 16;               // windows wider than this take the generic path
 
-// PB_RENDER_FIXED=0 selects the float atomicAdd accumulation (A/B measurement); default: fixed point
+// PB_RENDER_FIXED=1 selects the fixed-point accumulation (A/B measurement only).  Measured on B200
+// (profiles/r02_summary.md): 6.61 ms instead of 6.99 ms for 50 M localisations -- ATOMS.CAST.SPIN retries
+// in hardware, so the float update is ~5 instructions, not a 12-instruction software loop, and the pass is
+// bound by the rate of shared-memory atomics of either kind -- while its 2.3e-7-of-the-bound resolution
+// misses the 1e-6-of-the-maximum absolute pixel tolerance on dim pixels.  Default: float32 atomicAdd.
 bool render_fixed_point() {
     static const bool on = [] {
         if (const char* e = getenv("PB_RENDER_FIXED")) return atoi(e) != 0;
-        return true;
+        return false;
     }();
     return on;
 }

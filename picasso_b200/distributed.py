@@ -816,3 +816,128 @@ def localize_device(torch, movie, frame_offset, camera_info, parameters, *, fitt
             continue
         _lib.check(rc)
         return cols[:, : int(found.value)]
+
+
+# ---- NVSwitch multicast buffer (NVLS): the fused fit + all-gather ---------------------------------
+class MulticastBuffer:
+    """A gather buffer of ``world`` equal blocks that exists on every rank and is written THROUGH THE
+    SWITCH: memory of all GPUs is bound to one NVSwitch multicast object (csrc/multicast.cu), so a store
+    to ``mc_ptr + offset`` lands at ``uc_ptr + offset`` on every rank.  ``pb_mle_fit_gather_dev`` stores
+    each finished spot's results through ``block_mc_ptr()`` -- the all-gather of the fit results is part
+    of the fit kernel (one store stream per rank, 1/(N-1) of the NVLink egress of unicast copies, no copy
+    engine, no collective kernel).
+
+    One process per GPU: rank 0 creates the object and hands its POSIX file descriptor to the other
+    ranks over a Unix-domain socket (SCM_RIGHTS); ``torch.distributed`` carries only the socket path and
+    the barriers.  Raises ``RuntimeError`` when the GPUs / driver have no multicast support."""
+
+    def __init__(self, dist, torch, block_bytes: int, device):
+        import ctypes as C
+        import os
+        import socket
+        import tempfile
+
+        from . import _lib
+
+        self.dist, self.torch, self._lib = dist, torch, _lib
+        self.l = l = _lib.load()
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        l.pb_mc_padded_size.argtypes = [sz, i32, C.POINTER(sz)]
+        l.pb_mc_create.argtypes = [sz, i32, C.POINTER(vp), C.POINTER(i32)]
+        l.pb_mc_import.argtypes = [i32, sz, i32, C.POINTER(vp)]
+        l.pb_mc_add_device.argtypes = [vp]
+        l.pb_mc_bind_map.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        l.pb_mc_destroy.argtypes = [vp]
+        l.pb_mc_copy_async.argtypes = [vp, vp, sz, i32, vp]
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.block_bytes = int(block_bytes)
+        self.device = device
+        self.handle = None
+        ok = torch.tensor([float(l.pb_mc_supported())], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 0.5:
+            raise RuntimeError("NVSwitch multicast (NVLS) is not supported on every rank")
+        padded = sz(0)
+        _lib.check(l.pb_mc_padded_size(self.block_bytes * self.world, self.world, C.byref(padded)))
+        self.nbytes = int(padded.value)
+        h = vp()
+        status = torch.ones(1, device=device)
+        path = [None]
+        srv = None
+        try:
+            if self.rank == 0:
+                fd = i32(-1)
+                _lib.check(l.pb_mc_create(self.nbytes, self.world, C.byref(h), C.byref(fd)))
+                path[0] = os.path.join(tempfile.gettempdir(), f"pb_mc_{os.getpid()}_{id(self) & 0xffffff:x}.sock")
+                if os.path.exists(path[0]):
+                    os.unlink(path[0])
+                srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                srv.bind(path[0])
+                srv.listen(self.world)
+            dist.broadcast_object_list(path, src=0)
+            if self.rank == 0:
+                for _ in range(self.world - 1):
+                    conn, _a = srv.accept()
+                    socket.send_fds(conn, [b"mc"], [fd.value])
+                    conn.recv(2)                      # the peer has imported the handle
+                    conn.close()
+                os.close(fd.value)
+            else:
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.connect(path[0])
+                _msg, fds, _f, _a = socket.recv_fds(c, 16, 1)
+                _lib.check(l.pb_mc_import(fds[0], self.nbytes, self.world, C.byref(h)))
+                c.send(b"ok")
+                c.close()
+        except Exception:
+            status.zero_()
+            raise
+        finally:
+            if srv is not None:
+                srv.close()
+                try:
+                    os.unlink(path[0])
+                except OSError:
+                    pass
+        self.handle = h
+        _lib.check(l.pb_mc_add_device(h))
+        dist.barrier()                                # every device has joined the team
+        uc, mc = vp(), vp()
+        _lib.check(l.pb_mc_bind_map(h, C.byref(uc), C.byref(mc)))
+        self.uc_ptr, self.mc_ptr = uc.value, mc.value
+        dist.barrier()                                # every rank's memory is bound before anyone stores
+
+    def block_mc_ptr(self, rank=None) -> int:
+        """Multicast address of a rank's block (default: this rank's)."""
+        return self.mc_ptr + (self.rank if rank is None else rank) * self.block_bytes
+
+    def local(self, dtype):
+        """This rank's copy of the whole gather buffer as a torch tensor (no copy)."""
+        torch = self.torch
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        n = self.block_bytes * self.world // itemsize
+
+        class _Raw:
+            pass
+
+        raw = _Raw()
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1", torch.int64: "<i8"}[dtype]
+        raw.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (self.uc_ptr, False), "version": 2}
+        t = torch.as_tensor(raw, device=self.device)
+        self._keep = raw
+        return t
+
+    def copy_in(self, block, stream=None, n_ctas: int = 16):
+        """Push an existing device tensor (this rank's block) through the multicast mapping."""
+        torch = self.torch
+        st = stream or torch.cuda.current_stream(self.device)
+        nbytes = block.numel() * block.element_size()
+        assert block.is_contiguous() and nbytes <= self.block_bytes and nbytes % 16 == 0
+        self._lib.check(self.l.pb_mc_copy_async(self.block_mc_ptr(), block.data_ptr(), nbytes, n_ctas, st.cuda_stream))
+
+    def close(self):
+        if self.handle is not None:
+            self.torch.cuda.synchronize(self.device)
+            self.dist.barrier()
+            self.l.pb_mc_destroy(self.handle)
+            self.handle = None

@@ -65,3 +65,20 @@ def test_scalable_sharding_agrees_with_one_gpu():
     u = out["undrift_segments"]
     assert u["max_abs_drift_dev_px"] < 1e-5 and u["max_abs_row_dev_px"] < 1e-4
     assert u["rows_total"] == u["rows_ref"]
+
+
+def test_multicast_fused_gather_equals_nccl():
+    """NVSwitch multicast buffer + the fit kernel's fused all-gather (multimem.st) against NCCL."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "tools", "check_multicast.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    if not out.get("supported"):
+        pytest.skip("no NVSwitch multicast support on this box: " + out.get("why", ""))
+    assert out["copy_equals_nccl"] is True
+    assert out["fused_fit_gather_equals_nccl"] == [True, True]
