@@ -437,7 +437,7 @@ def main():
                 pg.close()
             pg, gather_mode = None, "nccl"
     gathered_parts = {}
-    if world > 1 and gather_mode != "p2p":
+    if world > 1 and gather_mode not in ("p2p", "nvls"):
         gather_mode = "nccl"
         gathered = torch.empty(14 * n * world, dtype=torch.float32, device=dev)
 
