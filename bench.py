@@ -410,6 +410,11 @@ def main():
     # on every rank the run falls back to NCCL.
     gather_mode = os.environ.get("PB_GATHER", "nvls") if world > 1 else "none"
     gathered, pg, mcb = None, None, None
+    nvls_variant = None
+    if world > 1 and gather_mode.startswith("nvls"):
+        nvls_variant = {"nvls": "fused", "nvls-split": "split", "nvls-split-kernel": "split-kernel",
+                        "nvls-ce": "ce"}.get(gather_mode, "fused")
+        gather_mode = "nvls"
     if world > 1 and gather_mode == "nvls":
         # fused fit + all-gather: the CRLB kernel stores every spot's results through an NVSwitch multicast
         # mapping into the gather buffers of all ranks (picasso_b200.distributed.MulticastBuffer)
@@ -418,8 +423,11 @@ def main():
         lib.pb_mle_fit_gather_dev.argtypes = [C.c_size_t, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int] + \
             [C.c_void_p] * 7
         lib.pb_mle_fit_gather_dev.restype = C.c_int
+        lib.pb_mle_fit_gather_mode.argtypes = [C.c_int]
         try:
             mcb = MulticastBuffer(dist, torch, 14 * n * 4, dev)
+            _lib.check(lib.pb_mle_fit_gather_mode(2 if nvls_variant.startswith("split") else 1))
+            mc_side = torch.cuda.Stream(dev, priority=-1)       # copies of the CRLB half behind the next step
         except Exception as exc:      # noqa: BLE001
             print(f"[bench] rank {rank}: multicast gather unavailable ({exc}); using peer copies", file=sys.stderr)
             gather_mode = "p2p"
@@ -450,7 +458,8 @@ def main():
             if self.work is not None:
                 self.work.wait()
             if self.events is not None:
-                PeerGather.wait(self.events, stream)
+                for ev in self.events:
+                    stream.wait_event(ev)
 
     def launch_gather(part, offset_bytes):
         if gather_mode == "p2p":
@@ -481,9 +490,34 @@ def main():
         for q in range(parts):
             th, cr, ll, it, base, lo, m = views(flat, q)
             if mcb is not None:
+                if nvls_variant == "ce":
+                    # unfused reference point: plain fit, then ONE copy-engine copy of the block through the
+                    # multicast mapping on a side stream (overlaps the next step)
+                    _lib.check(lib.pb_mle_fit_dev(m, BOX, spots[lo:].data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
+                                                  cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
+                                                  stream.cuda_stream))
+                    ready = torch.cuda.Event(); ready.record(stream)
+                    mc_side.wait_event(ready)
+                    _lib.check(lib.pb_copy_d2d_async(mcb.block_mc_ptr() + 14 * lo * 4, base.data_ptr(), 14 * m * 4,
+                                                     mc_side.cuda_stream))
+                    done = torch.cuda.Event(); done.record(mc_side)
+                    pend.append(_Pending(events=[done]))
+                    continue
                 _lib.check(lib.pb_mle_fit_gather_dev(m, BOX, spots[lo:].data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
                                                      cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
                                                      mcb.block_mc_ptr() + 14 * lo * 4, stream.cuda_stream))
+                if nvls_variant.startswith("split"):
+                    # theta + iterations left from the iteration kernel; the CRLB / logL half ([6m, 13m) floats of
+                    # the block) follows through the mapping behind the next step: copy engine or a few CTAs
+                    ready = torch.cuda.Event(); ready.record(stream)
+                    mc_side.wait_event(ready)
+                    dst = mcb.block_mc_ptr() + (14 * lo + 6 * m) * 4
+                    if nvls_variant == "split":
+                        _lib.check(lib.pb_copy_d2d_async(dst, cr.data_ptr(), 7 * m * 4, mc_side.cuda_stream))
+                    else:
+                        _lib.check(lib.pb_mc_copy_async(dst, cr.data_ptr(), 7 * m * 4, 16, mc_side.cuda_stream))
+                    done = torch.cuda.Event(); done.record(mc_side)
+                    pend.append(_Pending(events=[done]))
                 continue
             _lib.check(lib.pb_mle_fit_dev(m, BOX, spots[lo:].data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
                                           cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
@@ -725,7 +759,8 @@ def main():
                                                  "peer writes into IPC-shared buffers over NVLink "
                                                  "(PeerGather; PB_GATHER=nccl selects one NCCL all-gather), "
                                                  "overlapped with the next step's fit"}.get(gather_mode, "")),
-                       "gather": gather_mode, "gather_verified": gather_ok,
+                       "gather": gather_mode + (f" ({nvls_variant})" if nvls_variant else ""),
+                       "gather_verified": gather_ok,
                        "gather_verified_steps": verified_steps, "parts_per_step": parts},
             "roofline": roof,
             # instruction-side view of the dominant kernel from the committed ncu --set full

@@ -283,6 +283,11 @@ int pb_mc_copy_async(void* mc_dst, const void* d_src, size_t bytes, int n_ctas, 
 int pb_mle_fit_gather_dev(size_t n, int box, const float* d_spots, double eps, int max_it, int method,
                           float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
                           int* d_status, void* mc_block, void* stream);
+/* which kernel emits what (process-wide): 1 = all 14 words from the finishing (CRLB) kernel; 2 = thetas +
+ * iterations from the iteration kernel as lanes finish -- spread over the whole step, which keeps the
+ * inbound NVLink rate of an N-rank gather low -- while the caller pushes the CRLB / logL half of its
+ * block ([6n, 13n) floats) through the mapping behind the next step */
+int pb_mle_fit_gather_mode(int mode);
 
 /* ---- localisation table: ensure_sanity, z-fit filter, record packing on the device ----------
  * Replaces lib.ensure_sanity (picasso/lib.py:1786-1832), the tail of zfit._fit_z (picasso/zfit.py:

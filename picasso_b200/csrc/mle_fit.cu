@@ -883,7 +883,8 @@ int dispatch_box(int box, const MleArgs& a, cudaStream_t stream) {
 bool pb_mle_tps_supports(int box);
 int pb_mle_tps_fit(size_t n, int box, const float* d_spots, double eps, int max_it, int method,
                    float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
-                   int* d_status, cudaStream_t stream, int pixel_f32, float* mc_block = nullptr);
+                   int* d_status, cudaStream_t stream, int pixel_f32, float* mc_block = nullptr,
+                   int mc_mode = 1);
 
 // Implementation selector: 0 = lane-group kernel (this file), 1 = thread-per-spot with float64
 // per-pixel sums, 2 = thread-per-spot with float32 per-pixel sums (default for box <= 13).
@@ -943,6 +944,16 @@ extern "C" int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double ep
 // all-gather of the results costs one store stream per rank and no copy, kernel or collective after the
 // fit.  The data are complete on all ranks once every rank's stream has passed the call and the ranks
 // have synchronised (barrier).
+// 1 (default): the finishing kernel stores all 14 words of a spot; 2: theta + iterations leave from the
+// iteration kernel as lanes finish (spread over the step), CRLB + logL are not stored -- the caller copies
+// that half of its block through the mapping (pb_mc_copy_async / a copy-engine copy) behind the next step.
+static std::atomic<int> g_gather_mode{1};
+extern "C" int pb_mle_fit_gather_mode(int mode) {
+    if (mode != 1 && mode != 2) { pb_set_error("pb_mle_fit_gather_mode: 1 or 2"); return PB_ERR_INVALID; }
+    g_gather_mode.store(mode);
+    return PB_OK;
+}
+
 extern "C" int pb_mle_fit_gather_dev(size_t n, int box, const float* d_spots, double eps, int max_it,
                                      int method, float* d_thetas, float* d_crlbs, float* d_logliks,
                                      int* d_iterations, int* d_status, void* mc_block, void* stream) {
@@ -963,5 +974,6 @@ extern "C" int pb_mle_fit_gather_dev(size_t n, int box, const float* d_spots, do
     }
     if (max_it < 0) max_it = 0;
     return pb_mle_tps_fit(n, box, d_spots, eps, max_it, method, d_thetas, d_crlbs, d_logliks, d_iterations,
-                          d_status, reinterpret_cast<cudaStream_t>(stream), impl == 2, static_cast<float*>(mc_block));
+                          d_status, reinterpret_cast<cudaStream_t>(stream), impl == 2, static_cast<float*>(mc_block),
+                          g_gather_mode.load());
 }

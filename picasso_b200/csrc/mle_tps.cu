@@ -61,6 +61,9 @@ struct TpsArgs {
     int* status;
     unsigned long long* counter;
     float* mc_block;     // multicast address of this rank's gather block (fused all-gather), or null
+    int mc_mode;         // 1: the CRLB kernel stores all 14 words; 2: the iteration kernel stores theta +
+                         //    iterations when a lane finishes its spot (spread over the whole kernel), the
+                         //    CRLB / logL half is left to the caller (copy through the multicast mapping)
 };
 
 // multimem.st: a store to a multicast address, replicated by the NVSwitch into the bound memory of
@@ -366,6 +369,11 @@ __global__ void __launch_bounds__(kThreads, PB_TPS_MINB) tps_iter_kernel(const T
                 out[1] = make_float2(th[2], th[3]);
                 out[2] = make_float2(th[4], th[5]);
                 a.iterations[idx] = kk;
+                if (a.mc_block && a.mc_mode == 2) {
+                    float* mt = a.mc_block + idx * 6;
+                    mc_st_v2(mt, th[0], th[1]); mc_st_v2(mt + 2, th[2], th[3]); mc_st_v2(mt + 4, th[4], th[5]);
+                    mc_st_b32(a.mc_block + 13 * a.n + idx, (unsigned)kk);
+                }
                 idx = -1;
             }
         }
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, PB_CRLB_MINB) tps_crlb_kernel(const 
         out[2] = make_float2(cr[4], cr[5]);
         a.logliks[s] = ll;
         if (a.status && st) a.status[s] |= st;
-        if (a.mc_block) {
+        if (a.mc_block && a.mc_mode == 1) {
             // fused all-gather: this spot's 14 output words go through the multicast mapping into the
             // gather buffers of ALL ranks, block layout [thetas 6n | crlbs 6n | logliks n | iterations n]
             float* mt = a.mc_block + s * 6;
@@ -565,9 +573,9 @@ bool pb_mle_tps_supports(int box) { return box >= 5 && box <= 13 && (box & 1); }
 
 int pb_mle_tps_fit(size_t n, int box, const float* d_spots, double eps, int max_it, int method,
                    float* d_thetas, float* d_crlbs, float* d_logliks, int* d_iterations,
-                   int* d_status, cudaStream_t stream, int pixel_f32, float* mc_block) {
+                   int* d_status, cudaStream_t stream, int pixel_f32, float* mc_block, int mc_mode) {
     TpsArgs a{d_spots, (long long)n, eps, max_it, d_thetas, d_crlbs, d_logliks, d_iterations,
-              d_status, nullptr, mc_block};
+              d_status, nullptr, mc_block, mc_mode};
     if (method == 1)
         return pixel_f32 ? dispatch_tps<1, float>(box, a, stream) : dispatch_tps<1, double>(box, a, stream);
     return pixel_f32 ? dispatch_tps<0, float>(box, a, stream) : dispatch_tps<0, double>(box, a, stream);
