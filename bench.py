@@ -408,7 +408,13 @@ def main():
     # (picasso_b200.distributed.PeerGather: no SM taken from the running fit, no host blocking),
     # "nccl" = one NCCL all-gather per step (PB_GATHER=nccl).  If the peer mapping cannot be set up
     # on every rank the run falls back to NCCL.
-    gather_mode = os.environ.get("PB_GATHER", "nvls") if world > 1 else "none"
+    # Default ("auto"): at 2 ranks the all-gather is FUSED into the fit kernel (multimem.st through an NVSwitch
+    # multicast mapping); from 4 ranks on it is done by copy-engine peer writes behind the next step's fit --
+    # measured at 8 ranks (profiles/r02_summary.md): fused 20.9 ms/step (every GPU would have to take in 3.9 GB
+    # within the 3.3 ms of the CRLB kernel), peer copies 18.4 ms/step.
+    gather_mode = os.environ.get("PB_GATHER", "auto") if world > 1 else "none"
+    if gather_mode == "auto":
+        gather_mode = "nvls" if world <= 2 else "p2p"
     gathered, pg, mcb = None, None, None
     nvls_variant = None
     if world > 1 and gather_mode.startswith("nvls"):
