@@ -467,8 +467,14 @@ def main():
                 for ev in self.events:
                     stream.wait_event(ev)
 
-    def launch_gather(part, offset_bytes):
+    def launch_gather(part, offset_bytes, b=0):
         if gather_mode == "p2p":
+            if p2p_early:
+                m_ = part.numel() // 14
+                evs = pg.gather_async(part[: 6 * m_], stream, offset_bytes, after_event=phase_events[b])
+                evs += pg.gather_async(part[13 * m_:], stream, offset_bytes + 13 * m_ * 4, after_event=phase_events[b])
+                evs += pg.gather_async(part[6 * m_: 13 * m_], stream, offset_bytes + 6 * m_ * 4)
+                return _Pending(events=evs)
             return _Pending(events=pg.gather_async(part, stream, offset_bytes))
         # NCCL: one all-gather per part into the part's own gather buffer (part-major as well)
         return _Pending(work=dist.all_gather_into_tensor(
@@ -482,6 +488,20 @@ def main():
     parts = int(os.environ.get("PB_BENCH_PARTS", "1"))
     parts = max(1, min(parts, 64))
     pb = [((n * q) // parts) // 4096 * 4096 for q in range(parts)] + [n]     # part edges, 4096-spot aligned
+
+    # p2p: thetas + iterations are final after the iteration kernel -- the library records a phase event
+    # there, and that half of the block leaves while the CRLB kernel still runs (PB_P2P_EARLY=0: one copy
+    # of the whole block after the fit)
+    p2p_early = os.environ.get("PB_P2P_EARLY", "1") != "0" and parts == 1
+    phase_events = []
+    if gather_mode == "p2p" and p2p_early:
+        import ctypes as C
+        lib.pb_mle_set_phase_event.argtypes = [C.c_void_p]
+        for _ in range(2):
+            ev = torch.cuda.Event()
+            ev.record(stream)                    # creates the underlying cudaEvent
+            phase_events.append(ev)
+
 
     def views(flat, q=None):
         if q is None:                      # all parts: only meaningful for parts == 1
@@ -525,11 +545,15 @@ def main():
                     done = torch.cuda.Event(); done.record(mc_side)
                     pend.append(_Pending(events=[done]))
                 continue
+            if phase_events:
+                _lib.check(lib.pb_mle_set_phase_event(phase_events[b].cuda_event))
             _lib.check(lib.pb_mle_fit_dev(m, BOX, spots[lo:].data_ptr(), EPS, MAX_IT, 1, th.data_ptr(),
                                           cr.data_ptr(), ll.data_ptr(), it.data_ptr(), None,
                                           stream.cuda_stream))
+            if phase_events:
+                _lib.check(lib.pb_mle_set_phase_event(None))
             if world > 1:
-                pend.append(launch_gather(base, 14 * lo * 4))
+                pend.append(launch_gather(base, 14 * lo * 4, b))
         return pend
 
     if gather_mode == "nccl":

@@ -109,6 +109,10 @@ int pb_mle_get_impl(void);
  * the launch stream around its three kernels; pb_mle_profile_read waits for the most recent
  * call and returns their durations in ms: {start values, Newton iterations, CRLB + logL}. */
 int pb_mle_profile(int enable);
+/* Phase hook for multi-GPU callers: a cudaEvent_t (NULL clears it) that the following thread-per-spot fits
+ * record on their launch stream after the iteration kernel: thetas and iterations are final from there on
+ * and can be sent to the peers while the CRLB kernel runs. */
+int pb_mle_set_phase_event(void* cuda_event);
 int pb_mle_profile_read(float* ms3);
 
 /* ---- spot identification ------------------------------------------------

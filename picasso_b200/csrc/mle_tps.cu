@@ -15,8 +15,11 @@
 //                     lane-level refill no lane ever waits for a slower neighbour, and there
 //                     are no shuffles, no cross-lane reductions and no idle lanes inside an
 //                     iteration.
-//   tps_crlb_kernel   thread per spot, staged like init; Fisher matrix, Cholesky inverse
-//                     diagonal (Jacobi pseudo-inverse fallback), log-likelihood
+//   tps_crlb_kernel   thread per spot, staged like init; Fisher matrix (float32 pair sums per pixel
+//                     row, float64 across rows; all-float64 repeat for near-singular matrices),
+//                     Cholesky inverse diagonal (Jacobi pseudo-inverse fallback), log-likelihood with
+//                     a table-driven ln(); on multi-GPU runs it can also store the spot's results
+//                     through an NVSwitch multicast mapping (fused all-gather, csrc/multicast.cu)
 //
 // The start-value and CRLB passes are separate kernels so that each runs with all 32 lanes
 // busy (inside the iteration kernel they would execute for the ~4 lanes per trip that
@@ -487,6 +490,11 @@ struct TpsProfile {
 };
 TpsProfile g_prof;
 
+// Optional phase event (pb_mle_set_phase_event): recorded on the launch stream after the iteration kernel
+// of the next thread-per-spot call(s) -- thetas and iterations are final from there on, so a multi-GPU
+// caller can start moving that half of the results while the CRLB kernel still runs.
+std::atomic<cudaEvent_t> g_phase_event{nullptr};
+
 template <int BOX, int METHOD, typename T>
 int launch_tps(const TpsArgs& a0, cudaStream_t stream) {
     constexpr int PIX = BOX * BOX;
@@ -544,6 +552,7 @@ int launch_tps(const TpsArgs& a0, cudaStream_t stream) {
             g_pb_launches++;
         }
         if (p) cudaEventRecord(g_prof.ev[2], stream);
+        if (cudaEvent_t pe = g_phase_event.load()) cudaEventRecord(pe, stream);
         k_crlb<<<chunks, kThreads, CSM::kTotal, stream>>>(a, first, m);
         g_pb_launches++;
         if (p) { cudaEventRecord(g_prof.ev[3], stream); g_prof.recorded = true; }
@@ -587,6 +596,10 @@ extern "C" int pb_mle_profile(int enable) {
     if (enable && g_prof.ev[0] == nullptr)
         for (int i = 0; i < 4; i++) PB_CUDA_CHECK(cudaEventCreate(&g_prof.ev[i]));
     g_prof.on.store(enable != 0);
+    return PB_OK;
+}
+extern "C" int pb_mle_set_phase_event(void* cuda_event) {
+    g_phase_event.store(reinterpret_cast<cudaEvent_t>(cuda_event));
     return PB_OK;
 }
 extern "C" int pb_mle_profile_read(float* ms3) {

@@ -896,7 +896,7 @@ PB_HD int crlb_loglik(const Roi& roi, const float th[6], Xf3& xf, float crlb[6],
 // get(col, double& px, float& c1, float& g1).
 template <int BOX, int METHOD, int NF, class Roi, class XfF, class Tab>
 PB_HD void crlb_row_fast(int j, const double fy[5], const Roi& roi, const XfF& xf, const Tab& tab, double N,
-                         double bg, double M[NF], double& ll) {
+                         double bg, float M[NF], double& ll) {
     const double PSFy = fy[0], NPy = N * fy[0];
     float ac[10];
 #pragma unroll
@@ -931,35 +931,36 @@ PB_HD void crlb_row_fast(int j, const double fy[5], const Roi& roi, const XfF& x
             }
         }
     }
-#define PB_PR(p, q) (double)ac[((p) < (q) ? (p) : (q)) * 4 - (((p) < (q) ? (p) : (q)) * (((p) < (q) ? (p) : (q)) - 1)) / 2 + \
+#define PB_PR(p, q) ac[((p) < (q) ? (p) : (q)) * 4 - (((p) < (q) ? (p) : (q)) * (((p) < (q) ? (p) : (q)) - 1)) / 2 + \
                                (((p) < (q) ? (q) : (p)) - ((p) < (q) ? (p) : (q)))]
     if (METHOD == 1) {
-        const double arow[6] = {NPy, N * fy[1], PSFy, 1.0, NPy, N * fy[3]};
+        // row factors and their products in float32 as well: the pair sums carry float32 rounding anyway
+        const float arow[6] = {(float)NPy, (float)(N * fy[1]), (float)PSFy, 1.0f, (float)NPy, (float)(N * fy[3])};
         constexpr int kind[6] = {0, 1, 1, 2, 3, 1};
         int q = 0;
 #pragma unroll
         for (int k = 0; k < 6; k++)
 #pragma unroll
             for (int l = k; l < 6; l++) {
-                M[q] = fma(arow[k] * arow[l], PB_PR(kind[k], kind[l]), M[q]);
+                M[q] = fmaf(arow[k] * arow[l], PB_PR(kind[k], kind[l]), M[q]);
                 q++;
             }
     } else {
-        const double arow[4] = {NPy, N * fy[1], PSFy, 1.0};
+        const float arow[4] = {(float)NPy, (float)(N * fy[1]), (float)PSFy, 1.0f};
         constexpr int kind[4] = {0, 1, 1, 2};
-        const double u = NPy, v = N * fy[3];
+        const float u = (float)NPy, v = (float)(N * fy[3]);
         int q = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
 #pragma unroll
             for (int l = k; l < 4; l++) {
-                M[q] = fma(arow[k] * arow[l], PB_PR(kind[k], kind[l]), M[q]);
+                M[q] = fmaf(arow[k] * arow[l], PB_PR(kind[k], kind[l]), M[q]);
                 q++;
             }
-            M[q] = fma(arow[k], u * PB_PR(kind[k], 3) + v * PB_PR(kind[k], 1), M[q]);
+            M[q] = fmaf(arow[k], u * PB_PR(kind[k], 3) + v * PB_PR(kind[k], 1), M[q]);
             q++;
         }
-        M[q] += u * u * PB_PR(3, 3) + 2.0 * u * v * PB_PR(3, 1) + v * v * PB_PR(1, 1);
+        M[q] += u * u * PB_PR(3, 3) + 2.0f * u * v * PB_PR(3, 1) + v * v * PB_PR(1, 1);
     }
 #undef PB_PR
 }
@@ -986,9 +987,9 @@ PB_HD int crlb_loglik_fast(const Roi& roi, const float th[6], XfF& xf, const Tab
             xf.put(2 * k, f);
         }
     }
-    double M[NF];
+    float Mf[NF];
 #pragma unroll
-    for (int q = 0; q < NF; q++) M[q] = 0.0;
+    for (int q = 0; q < NF; q++) Mf[q] = 0.0f;
     double ll = 0.0;
     {
         const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
@@ -999,13 +1000,18 @@ PB_HD int crlb_loglik_fast(const Roi& roi, const float th[6], XfF& xf, const Tab
             EA = eval_edge<METHOD>(2 * k, th[1], ay);
             if (k > 0) {
                 pixel_factors<METHOD>(EB, EA, ay, fy);
-                crlb_row_fast<BOX, METHOD, NF>(2 * k - 1, fy, roi, xf, tab, N, bg, M, ll);
+                crlb_row_fast<BOX, METHOD, NF>(2 * k - 1, fy, roi, xf, tab, N, bg, Mf, ll);
             }
             EB = eval_edge<METHOD>(2 * k + 1, th[1], ay);
             pixel_factors<METHOD>(EA, EB, ay, fy);
-            crlb_row_fast<BOX, METHOD, NF>(2 * k, fy, roi, xf, tab, N, bg, M, ll);
+            crlb_row_fast<BOX, METHOD, NF>(2 * k, fy, roi, xf, tab, N, bg, Mf, ll);
         }
     }
+    double M[NF];
+    bool finite = true;
+#pragma unroll
+    for (int q = 0; q < NF; q++) { M[q] = (double)Mf[q]; finite = finite && isfinite(Mf[q]); }
+    if (!finite) return -1;           // float32 overflow of a row-factor product: repeat in float64
     double dg[NP];
     double dmin = INFINITY, dmax = 0.0;
     {

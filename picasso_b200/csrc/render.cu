@@ -612,7 +612,8 @@ extern "C" int pb_render_band_dev(size_t n, const float* d_x, const float* d_y, 
     // The tiled pass costs ~10 ns per 64 x 64 tile (zeroing and flushing its shared copy, mostly idle
     // CTAs) plus 0.13 ns per localisation; the direct splat 0.32 ns per localisation.  Sparse images --
     // the 100 k-localisation segments of an undrift run on 4096^2 pixels: 24 per tile -- are faster
-    // direct (measured: 0.24 -> 0.05 ms per segment); dense ones (config 4: 1953 per tile) tiled.
+    // direct (measured: 0.24 -> 0.04 ms per segment, 48 -> 7.6 ms for the 200 segments of config 5); dense
+    // ones (config 4: 1953 per tile) tiled.
     const bool tiled = d_workspace && workspace_bytes >= need && n >= 65536 && n < 0xffffffffull &&
                        ntiles >= 64 && (long long)n >= 64 * ntiles &&
                        ((reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0);

@@ -295,17 +295,21 @@ class PeerGather:
         self.streams = [torch.cuda.Stream(device) for _ in range(max(1, min(n_streams, self.world)))]
         dist.barrier()
 
-    def gather_async(self, block, stream=None, offset_bytes: int = 0):
+    def gather_async(self, block, stream=None, offset_bytes: int = 0, after_event=None):
         """Enqueue the copies of ``block`` (a contiguous device tensor; the whole block of this rank,
         or the part of it that starts ``offset_bytes`` into the block) into every rank's buffer,
-        ordered after the work already enqueued on ``stream``; returns the events that complete
-        when the data has left this rank."""
+        ordered after the work already enqueued on ``stream`` -- or after ``after_event`` (e.g. the
+        fit's phase event: the thetas are final before the CRLB kernel has run); returns the events
+        that complete when the data has left this rank."""
         torch = self.torch
         stream = stream or torch.cuda.current_stream(self.device)
         nbytes = block.numel() * block.element_size()
         assert block.is_contiguous() and offset_bytes + nbytes <= self.block_bytes
-        ready = torch.cuda.Event()
-        ready.record(stream)
+        if after_event is not None:
+            ready = after_event
+        else:
+            ready = torch.cuda.Event()
+            ready.record(stream)
         for k in range(self.world):
             r = (self.rank + 1 + k) % self.world           # start with the neighbour: spread the links
             st = self.streams[k % len(self.streams)]
