@@ -92,6 +92,11 @@ struct XfF32 {
         a[c * 32] = make_float4(px, (float)f[1], (float)f[2], (float)f[3]);
         b[c * 32] = make_float2((float)f[4], (float)(f[0] - (double)px));
     }
+    __host__ __device__ __forceinline__ void put_f(int c, double psf, const float d[4]) {
+        const float px = (float)psf;
+        a[c * 32] = make_float4(px, d[0], d[1], d[2]);
+        b[c * 32] = make_float2(d[3], (float)(psf - (double)px));
+    }
     __host__ __device__ __forceinline__ void get(int c, float f[6]) const {
         const float4 v = a[c * 32];
         const float2 w = b[c * 32];
@@ -134,9 +139,9 @@ struct Xf3 {
 // (column stride = kThreads) inside the memory of Xf3, which the float64 fallback re-uses
 struct Xf3F {
     double* p;
-    __host__ __device__ __forceinline__ void put(int c, const double f[5]) {
-        p[(c * 2 + 0) * kThreads] = f[0];
-        reinterpret_cast<float2*>(p)[(c * 2 + 1) * kThreads] = make_float2((float)f[1], (float)f[3]);
+    __host__ __device__ __forceinline__ void put_f(int c, double psf, const float d[4]) {
+        p[(c * 2 + 0) * kThreads] = psf;
+        reinterpret_cast<float2*>(p)[(c * 2 + 1) * kThreads] = make_float2(d[0], d[2]);
     }
     __host__ __device__ __forceinline__ void get(int c, double& px, float& c1, float& g1) const {
         px = p[(c * 2 + 0) * kThreads];
@@ -152,6 +157,32 @@ struct LogTabSmem {
         rc = v.x; lc = v.y;
     }
 };
+
+// erf() table staged in shared memory: (c0, c1) as one double2 and (c2..c5) as one float4 per interval
+// (tps::kErfTabA / kErfTabB; the interval index diverges across lanes, which would serialise
+// constant-bank reads)
+constexpr int kErfN = 97;
+constexpr int kErfBytes = kErfN * 32;
+struct ErfTabSmem {
+    const double2* a;
+    const float4* b;
+    __device__ __forceinline__ void get(int k, double& c0, double& c1, float& c2, float& c3, float& c4,
+                                        float& c5) const {
+        const double2 u = a[k];
+        const float4 v = b[k];
+        c0 = u.x; c1 = u.y;
+        c2 = v.x; c3 = v.y; c4 = v.z; c5 = v.w;
+    }
+};
+__device__ __forceinline__ ErfTabSmem stage_erf_table(unsigned char* dst) {
+    double2* a = reinterpret_cast<double2*>(dst);
+    float4* b = reinterpret_cast<float4*>(dst + kErfN * 16);
+    for (int k = threadIdx.x; k < kErfN; k += blockDim.x) {
+        a[k] = make_double2(tps::kErfTabA[k][0], tps::kErfTabA[k][1]);
+        b[k] = make_float4(tps::kErfTabB[k][0], tps::kErfTabB[k][1], tps::kErfTabB[k][2], tps::kErfTabB[k][3]);
+    }
+    return ErfTabSmem{a, b};
+}
 
 template <typename T> struct XfSel;
 template <> struct XfSel<float> {
@@ -222,7 +253,8 @@ struct IterSmem {
     static constexpr int kXf = ((32 * BOX * XfSel<T>::kBytesPerLaneCol + 15) / 16) * 16;
     static constexpr int kMs = 32 * 6 * 4;
     static constexpr int kPerWarp = ((kRoi + kXf + kMs + 127) / 128) * 128;
-    static constexpr int kTotal = kPerWarp * (kThreads / 32);
+    static constexpr int kWarps = kPerWarp * (kThreads / 32);
+    static constexpr int kTotal = kWarps + kErfBytes;                           // + the erf table
 };
 
 template <int BOX, int METHOD, typename T>
@@ -249,6 +281,8 @@ __global__ void __launch_bounds__(kThreads, PB_TPS_MINB) tps_iter_kernel(const T
     }
     const RoiSlot roi{roi_w + lane * PIX};
     const long long seg_end = seg_first + seg_n;
+    const ErfTabSmem etab = stage_erf_table(smem_raw + SM::kWarps);
+    __syncthreads();               // the only CTA-wide barrier: the warps are autonomous from here on
 
     long long idx = -1;            // spot owned by this lane (-1: none)
     // Two claimed blocks of up to 32 spot indices per warp (warp-uniform): `cur` is being handed
@@ -358,9 +392,9 @@ __global__ void __launch_bounds__(kThreads, PB_TPS_MINB) tps_iter_kernel(const T
 
         // ---- one Newton iteration on every lane that owns a spot -------------------------
         if (idx >= 0) {
-            tps::column_stage<BOX, METHOD, T>(th, xf);
+            tps::column_stage<BOX, METHOD, T>(th, xf, etab);
             T num[6], den[6];   // float32 pixel sums also run the row stage in float32
-            tps::newton_sums<BOX, METHOD, T, T>(roi, th, xf, num, den);
+            tps::newton_sums<BOX, METHOD, T, T>(roi, th, xf, num, den, etab);
             float ms[6];
 #pragma unroll
             for (int l = 0; l < 6; l++) ms[l] = ms_s[l * 32 + lane];
@@ -391,7 +425,7 @@ struct CrlbSmem {
     static constexpr int kRoi = ((kThreads * PIX * 4 + 15) / 16) * 16;
     static constexpr int kXf = kThreads * BOX * 3 * 8;
     static constexpr int kTab = 128 * 16;
-    static constexpr int kTotal = kRoi + kXf + kTab + 16;
+    static constexpr int kTotal = kRoi + kXf + kTab + 16 + kErfBytes;
 };
 
 // FAST: float32 pair sums + table ln() with the all-float64 pass as per-spot fallback
@@ -409,9 +443,11 @@ __global__ void __launch_bounds__(kThreads, PB_CRLB_MINB) tps_crlb_kernel(const 
     const long long first = seg_first + (long long)blockIdx.x * kThreads;
     const long long rem = seg_first + seg_n - first;
     const int count = rem < kThreads ? (int)rem : kThreads;
+    ErfTabSmem etab{nullptr, nullptr};
     if (FAST) {
         static_assert(kThreads == 128, "one table entry per thread");
         tabp[threadIdx.x] = make_double2(tps::kLogRc[threadIdx.x], tps::kLogLc[threadIdx.x]);
+        etab = stage_erf_table(smem_raw + SM::kRoi + SM::kXf + SM::kTab + 16);
     }
     stage_chunk<PIX>(a.spots, first, count, sm, bar);      // (its __syncthreads publishes the table)
     if ((int)threadIdx.x < count) {
@@ -426,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, PB_CRLB_MINB) tps_crlb_kernel(const 
         if (FAST) {
             Xf3F xff{xfp + threadIdx.x};
             const LogTabSmem tab{tabp};
-            st = tps::crlb_loglik_fast<BOX, METHOD>(roi, th, xff, tab, cr, &ll);
+            st = tps::crlb_loglik_fast<BOX, METHOD>(roi, th, xff, tab, etab, cr, &ll);
         }
         if (st < 0) st = tps::crlb_loglik<BOX, METHOD>(roi, th, xf, cr, &ll);
         float2* out = reinterpret_cast<float2*>(a.crlbs + s * 6);

@@ -36,6 +36,8 @@
 #define PB_TABLE static const
 #endif
 
+#include "erf_table.cuh"
+
 namespace tps {
 
 constexpr double kInvSqrt2Pi = 0.3989422804014326779;   // 1/sqrt(2*pi)
@@ -352,6 +354,147 @@ PB_HD void pixel_factors(const Edge<METHOD>& lo, const Edge<METHOD>& hi, const A
     }
 }
 
+// ---- float32-pixel kernels: table-driven erf, float32 derivative factors -------------------------
+// Only the PSF (a difference of two erf values that is multiplied into the model and cancels against
+// the data) needs more than float32, and it needs ~1e-9 absolute (measured: rounding erf to 1e-9 leaves
+// the iteration counts of 200 000 spots unchanged; 1e-7 still passes the parity bar).  So
+//   * erf(z)/2 comes from a 97-interval table (erf_table.cuh, tools/gen_erf_table.py): k = rint(16 |z|),
+//     d = |z| - k/16, degree 5 with float64 c0, c1 and a float32 tail -- 5 FP64 instructions and two
+//     16-byte table loads instead of a reciprocal plus a degree-16 float64 polynomial; max abs error 1.2e-11;
+//   * the Gaussian edge term and everything derived from it (d/dmu, d2/dmu2, d/dsigma, d2/dsigma2) run in
+//     float32 with the hardware exp2: the reference stores dudt / d2udt2 in float32 arrays anyway
+//     (gaussmle.py:776-779) and accumulates their products in float32.
+// Per edge this leaves 7 FP64 instructions (FP64 issues at half rate on sm_100) of the 87 the all-float64
+// evaluation needs.
+struct ErfTabDirect {     // host build / staging source
+    PB_HD void get(int k, double& c0, double& c1, float& c2, float& c3, float& c4, float& c5) const {
+        c0 = kErfTabA[k][0]; c1 = kErfTabA[k][1];
+        c2 = kErfTabB[k][0]; c3 = kErfTabB[k][1]; c4 = kErfTabB[k][2]; c5 = kErfTabB[k][3];
+    }
+};
+// erf(z) / 2;  NaN propagates, |z| >= 6 (and inf) gives +-0.5
+template <class Tab>
+PB_HD double half_erf_tab(double z, const Tab& tab) {
+#ifdef __CUDA_ARCH__
+    const int zhi = __double2hiint(z);
+    const int ahi = zhi & 0x7fffffff;
+    const bool big = (unsigned)(ahi - 0x40180000) <= (0x7ff00000u - 0x40180000u);    // 6 <= |z| <= inf
+    const double a = __hiloint2double(big ? 0x40180000 : ahi, big ? 0 : __double2loint(z));
+    const double t = fma(a, 16.0, 6755399441055744.0);      // 1.5 * 2^52: rint(16 a) in the low word
+    unsigned k = (unsigned)__double2loint(t);
+#else
+    double a = fabs(z);
+    a = a >= 6.0 ? 6.0 : a;
+    const double t = fma(a, 16.0, 6755399441055744.0);
+    uint64_t bits;
+    memcpy(&bits, &t, 8);
+    unsigned k = (unsigned)(bits & 0xffffffffu);
+#endif
+    k = k > 96u ? 96u : k;                                   // (NaN: any in-range entry; d is NaN)
+    const double n = t - 6755399441055744.0;
+    const double d = fma(n, -0.0625, a);
+    double c0, c1;
+    float c2, c3, c4, c5;
+    tab.get((int)k, c0, c1, c2, c3, c4, c5);
+    const float df = (float)d;
+    float pf = fmaf(c5, df, c4);
+    pf = fmaf(pf, df, c3);
+    pf = fmaf(pf, df, c2);
+    const double r = fma(fma((double)pf, d, c1), d, c0);
+    return copysign(r, z);
+}
+// exp(-q), q >= 0, float32 (device: MUFU.EX2, 2 ulp; underflows to 0)
+PB_HD float exp_neg_f(float q) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q * -1.4426950408889634f));
+    return r;
+#else
+    return exp2f(q * -1.4426950408889634f);
+#endif
+}
+struct AxisF {
+    double c;                  // 1 / (sqrt2 sigma): the erf argument scale
+    float rs;                  // 1 / sigma
+    float rho;                 // sigma^2 / f32(sigma^2) - 1   (_G's exponent, :306-316)
+    float k1, k2, k3, k5, k32; // METHOD 1: rs c, r3 c, r2 c, r5 c, 2 r3 c   (c = 1/sqrt(2 pi))
+    float m0, m3, m4a, m4b;    // METHOD 0: rs/sqrt2, rs/sqrt(pi), r2/sqrt(pi), rs f32(1/sigma)/sqrt(pi)
+};
+template <int METHOD>
+PB_HD AxisF make_axis_f(float sig) {
+    AxisF x;
+    const float s2f = sig * sig;
+    const float s3f = sig * s2f;
+    const float s5f = sig * (s2f * s2f);
+    const double rsd = rcp64((double)sig);
+    x.c = rsd * kInvSqrt2;
+    x.rs = (float)rsd;
+    // (IEEE divisions: per axis, not per edge -- the approximate reciprocal's ulp would be noise on
+    // every derivative factor of the axis)
+    const float r2 = 1.0f / s2f, r3 = 1.0f / s3f;
+    x.rho = fmaf(sig, sig, -s2f) * r2;                       // the product's rounding error is exact in fmaf
+    x.k1 = x.rs * (float)kInvSqrt2Pi;
+    x.k2 = r3 * (float)kInvSqrt2Pi;
+    if (METHOD == 1) {
+        x.k3 = r2 * (float)kInvSqrt2Pi;
+        x.k5 = (1.0f / s5f) * (float)kInvSqrt2Pi;
+        x.k32 = 2.0f * x.k2;
+        x.m0 = x.m3 = x.m4a = x.m4b = 0.f;
+    } else {
+        x.k3 = x.k5 = x.k32 = 0.f;
+        x.m0 = x.rs * (float)kInvSqrt2;
+        x.m3 = x.rs * (float)kInvSqrtPi;
+        x.m4a = r2 * (float)kInvSqrtPi;
+        x.m4b = x.m3 * (1.0f / sig);
+    }
+    return x;
+}
+template <int METHOD>
+struct EdgeF {
+    double E;          // erf(e / (sqrt2 sigma)) / 2, float64: the PSF is a difference of two of these
+    float A, eA, u, v; // as in Edge, float32
+};
+// e = (g - mu) - 1/2 of edge g
+template <int METHOD, class Tab>
+PB_HD EdgeF<METHOD> eval_edge_f(double e, const AxisF& ax, const Tab& tab) {
+    EdgeF<METHOD> r;
+    r.E = half_erf_tab(e * ax.c, tab);
+    const float ef = (float)e;
+    const float t = ef * ax.rs;
+    const float q = 0.5f * t * t;
+    const float Af = exp_neg_f(q);
+    r.A = Af;
+    r.eA = ef * Af;
+    if (METHOD == 1) {
+        const float z = -q * ax.rho;
+        const float AG = fmaf(Af, fmaf(0.5f * z, z, z), Af);
+        r.u = ef * AG;
+        r.v = ef * ef * r.u;
+    } else {
+        const float am = ef * ax.m0;
+        r.u = am * Af;
+        r.v = r.u * (1.0f - 2.0f * am * am);
+    }
+    return r;
+}
+// psf = PSF (float64); d[0..3] = d/dmu, d2/dmu2, d/dsigma, d2/dsigma2 parts (float32)
+template <int METHOD>
+PB_HD void pixel_factors_f(const EdgeF<METHOD>& lo, const EdgeF<METHOD>& hi, const AxisF& ax, double& psf,
+                           float d[4]) {
+    psf = hi.E - lo.E;
+    d[0] = (lo.A - hi.A) * ax.k1;
+    d[1] = (lo.eA - hi.eA) * ax.k2;
+    if (METHOD == 1) {
+        const float w1 = lo.u - hi.u, w3 = lo.v - hi.v;
+        d[2] = w1 * ax.k3;
+        d[3] = fmaf(w3, ax.k5, -(w1 * ax.k32));
+    } else {
+        const float F = lo.u - hi.u;
+        d[2] = F * ax.m3;
+        d[3] = fmaf(hi.v - lo.v, ax.m4b, -(F * ax.m4a));
+    }
+}
+
 // ---- start values (gaussmle.py:28-168) ---------------------------------------
 // roi(p) returns pixel p = row * BOX + col as float.  Returns status flags
 // (bit 0: a centre-row/column sum was exactly 0 -- the reference raises there).
@@ -443,8 +586,28 @@ PB_HD void max_steps(const float th0[6], float ms[6]) {
 // the device) by stage 1 and read back per pixel by stage 2; the y factors are formed on
 // the fly, one row at a time.  Xf concept: void put(int col, const double f[5]);
 // void get(int col, T f[5]) const.
-template <int BOX, int METHOD, typename T, class Xf>
-PB_HD void column_stage(const float th[6], Xf& xf) {
+template <int BOX, int METHOD, typename T, class Xf, class Tab>
+PB_HD void column_stage(const float th[6], Xf& xf, const Tab& tab) {
+    if constexpr (sizeof(T) == 4) {
+        const AxisF ax = make_axis_f<METHOD>(th[4]);
+        EdgeF<METHOD> A, B = {};
+        double e = -(double)th[0] - 0.5;      // edge 0; edges are 1 apart (exact in float64)
+#pragma unroll 1
+        for (int k = 0; k < (BOX + 1) / 2; k++) {
+            double psf;
+            float d[4];
+            A = eval_edge_f<METHOD>(e, ax, tab);
+            if (k > 0) {
+                pixel_factors_f<METHOD>(B, A, ax, psf, d);
+                xf.put_f(2 * k - 1, psf, d);
+            }
+            B = eval_edge_f<METHOD>(e + 1.0, ax, tab);
+            pixel_factors_f<METHOD>(A, B, ax, psf, d);
+            xf.put_f(2 * k, psf, d);
+            e += 2.0;
+        }
+        return;
+    }
     const Axis ax = make_axis(th[4]);
     // edges are evaluated in pairs into two fixed register sets (A: even edges, B: odd edges):
     // no loop-carried copies, and the two evaluations of a trip are independent (ILP)
@@ -467,17 +630,19 @@ PB_HD void column_stage(const float th[6], Xf& xf) {
 // row in type T, then the row factors fy applied and accumulated over rows in type A
 // (A = double: f64 row stage; A = float: everything after the edge terms runs on the FP32
 // pipe -- the reference itself accumulates all b*b terms in float32, gaussmle.py:836-839).
-template <int BOX, int METHOD, typename T, typename A, class Roi, class Xf>
-PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& xf, float Nf, float bgf,
+template <int BOX, int METHOD, typename T, typename A, typename FY, class Roi, class Xf>
+PB_HD void accumulate_row(int j, double psf_y, const FY fyd[4], const Roi& roi, const Xf& xf, float Nf, float bgf,
                           A num[6], A den[6]) {
+    // fy[0] = PSF of the row (float64), fy[1..4] = its derivative factors (FY = double or float)
+    const double fy0 = psf_y;
     const A N = (A)Nf;
-    const A PSFy = (A)fy[0];
+    const A PSFy = (A)fy0;
     const A NPy = N * PSFy;
     const T NPy_t = (T)NPy, bg_t = (T)bgf;
     // float32 pixels: the residual data - model cancels to ~sqrt(model), so it is formed in
     // float-float arithmetic (N PSFy and PSFx carry a low word); everything downstream of the
     // residual is well conditioned and stays plain float32
-    const float NPy_lo = (sizeof(T) == 4) ? (float)((double)Nf * fy[0] - (double)(float)NPy_t) : 0.f;
+    const float NPy_lo = (sizeof(T) == 4) ? (float)((double)Nf * fy0 - (double)(float)NPy_t) : 0.f;
     T c0 = 0, cpx = 0, cc1 = 0, cc2 = 0, cg1 = 0, cg2 = 0;
     T d0 = 0, dpx2 = 0, dc1 = 0, dg1 = 0, dgp = 0;
 #pragma unroll
@@ -528,7 +693,7 @@ PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& x
         dg1 = tfma<T>(df, f[3] * f[3], dg1);
         if (METHOD == 0) dgp = tfma<T>(df, f[3] * f[0], dgp);
     }
-    const A Ncy1 = N * (A)fy[1], Ncy2 = N * (A)fy[2];
+    const A Ncy1 = N * (A)fyd[0], Ncy2 = N * (A)fyd[1];
     const A cpx_a = (A)cpx, dpx2_a = (A)dpx2;
     num[0] = tfma<A>(NPy, (A)cc1, num[0]);
     den[0] += NPy * (A)cc2 - NPy * NPy * (A)dc1;
@@ -539,7 +704,7 @@ PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& x
     num[3] += (A)c0;
     den[3] -= (A)d0;
     if (METHOD == 1) {
-        const A Ngy1 = N * (A)fy[3], Ngy2 = N * (A)fy[4];
+        const A Ngy1 = N * (A)fyd[2], Ngy2 = N * (A)fyd[3];
         num[4] = tfma<A>(NPy, (A)cg1, num[4]);
         den[4] += NPy * (A)cg2 - NPy * NPy * (A)dg1;
         num[5] = tfma<A>(Ngy1, cpx_a, num[5]);
@@ -547,7 +712,7 @@ PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& x
     } else {
         // dudt = N (PSFy dPx + PSFx dPy); the reference's d2udt2 has photons on the
         // first term only (gaussmle.py:380-382)
-        const A gy1 = (A)fy[3], gy2 = (A)fy[4];
+        const A gy1 = (A)fyd[2], gy2 = (A)fyd[3];
         num[4] += N * (PSFy * (A)cg1 + gy1 * cpx_a);
         den[4] += (NPy * (A)cg2 + (A)2 * gy1 * (A)cg1 + gy2 * cpx_a) -
                   N * N * (PSFy * PSFy * (A)dg1 + (A)2 * PSFy * gy1 * (A)dgp +
@@ -555,11 +720,31 @@ PB_HD void accumulate_row(int j, const double fy[5], const Roi& roi, const Xf& x
     }
 }
 
-template <int BOX, int METHOD, typename T, typename A, class Roi, class Xf>
-PB_HD void newton_sums(const Roi& roi, const float th[6], const Xf& xf, A num[6], A den[6]) {
-    const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
+template <int BOX, int METHOD, typename T, typename A, class Roi, class Xf, class Tab>
+PB_HD void newton_sums(const Roi& roi, const float th[6], const Xf& xf, A num[6], A den[6], const Tab& tab) {
 #pragma unroll
     for (int l = 0; l < 6; l++) { num[l] = 0; den[l] = 0; }
+    if constexpr (sizeof(T) == 4) {
+        const AxisF ay = make_axis_f<METHOD>(METHOD == 1 ? th[5] : th[4]);
+        EdgeF<METHOD> EA, EB = {};
+        double e = -(double)th[1] - 0.5;
+#pragma unroll 1
+        for (int k = 0; k < (BOX + 1) / 2; k++) {
+            double psf;
+            float d[4];
+            EA = eval_edge_f<METHOD>(e, ay, tab);
+            if (k > 0) {
+                pixel_factors_f<METHOD>(EB, EA, ay, psf, d);
+                accumulate_row<BOX, METHOD, T, A>(2 * k - 1, psf, d, roi, xf, th[2], th[3], num, den);
+            }
+            EB = eval_edge_f<METHOD>(e + 1.0, ay, tab);
+            pixel_factors_f<METHOD>(EA, EB, ay, psf, d);
+            accumulate_row<BOX, METHOD, T, A>(2 * k, psf, d, roi, xf, th[2], th[3], num, den);
+            e += 2.0;
+        }
+        return;
+    }
+    const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
     Edge<METHOD> EA, EB = {};
 #pragma unroll 1
     for (int k = 0; k < (BOX + 1) / 2; k++) {
@@ -567,11 +752,11 @@ PB_HD void newton_sums(const Roi& roi, const float th[6], const Xf& xf, A num[6]
         EA = eval_edge<METHOD>(2 * k, th[1], ay);
         if (k > 0) {
             pixel_factors<METHOD>(EB, EA, ay, fy);
-            accumulate_row<BOX, METHOD, T, A>(2 * k - 1, fy, roi, xf, th[2], th[3], num, den);
+            accumulate_row<BOX, METHOD, T, A>(2 * k - 1, fy[0], fy + 1, roi, xf, th[2], th[3], num, den);
         }
         EB = eval_edge<METHOD>(2 * k + 1, th[1], ay);
         pixel_factors<METHOD>(EA, EB, ay, fy);
-        accumulate_row<BOX, METHOD, T, A>(2 * k, fy, roi, xf, th[2], th[3], num, den);
+        accumulate_row<BOX, METHOD, T, A>(2 * k, fy[0], fy + 1, roi, xf, th[2], th[3], num, den);
     }
 }
 
@@ -892,12 +1077,13 @@ PB_HD int crlb_loglik(const Roi& roi, const float th[6], Xf3& xf, float crlb[6],
 // exact zeros -- amplifies float32 noise, so the result is only accepted when every pivot of the
 // diagonally scaled Cholesky factorisation is above 1e-2 (error bound ~ 2e-7 / 1e-2); otherwise
 // the caller repeats the pass with crlb_loglik (all float64).  Returns -1 in that case.
-// XfF concept: put(col, f[5]) keeps PSF as double and (d/dmu, d/dsigma) as floats;
+// XfF concept: put_f(col, psf, d[4]) keeps PSF as double and (d/dmu, d/dsigma) as floats;
 // get(col, double& px, float& c1, float& g1).
 template <int BOX, int METHOD, int NF, class Roi, class XfF, class Tab>
-PB_HD void crlb_row_fast(int j, const double fy[5], const Roi& roi, const XfF& xf, const Tab& tab, double N,
-                         double bg, float M[NF], double& ll) {
-    const double PSFy = fy[0], NPy = N * fy[0];
+PB_HD void crlb_row_fast(int j, double PSFy, const float fyd[4], const Roi& roi, const XfF& xf, const Tab& tab,
+                         double N, double bg, float M[NF], double& ll) {
+    const double NPy = N * PSFy;
+    const float Nf = (float)N;
     float ac[10];
 #pragma unroll
     for (int q = 0; q < 10; q++) ac[q] = 0.0f;
@@ -935,7 +1121,7 @@ PB_HD void crlb_row_fast(int j, const double fy[5], const Roi& roi, const XfF& x
                                (((p) < (q) ? (q) : (p)) - ((p) < (q) ? (p) : (q)))]
     if (METHOD == 1) {
         // row factors and their products in float32 as well: the pair sums carry float32 rounding anyway
-        const float arow[6] = {(float)NPy, (float)(N * fy[1]), (float)PSFy, 1.0f, (float)NPy, (float)(N * fy[3])};
+        const float arow[6] = {(float)NPy, Nf * fyd[0], (float)PSFy, 1.0f, (float)NPy, Nf * fyd[2]};
         constexpr int kind[6] = {0, 1, 1, 2, 3, 1};
         int q = 0;
 #pragma unroll
@@ -946,9 +1132,9 @@ PB_HD void crlb_row_fast(int j, const double fy[5], const Roi& roi, const XfF& x
                 q++;
             }
     } else {
-        const float arow[4] = {(float)NPy, (float)(N * fy[1]), (float)PSFy, 1.0f};
+        const float arow[4] = {(float)NPy, Nf * fyd[0], (float)PSFy, 1.0f};
         constexpr int kind[4] = {0, 1, 1, 2};
-        const float u = (float)NPy, v = (float)(N * fy[3]);
+        const float u = (float)NPy, v = Nf * fyd[2];
         int q = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -965,26 +1151,29 @@ PB_HD void crlb_row_fast(int j, const double fy[5], const Roi& roi, const XfF& x
 #undef PB_PR
 }
 
-template <int BOX, int METHOD, class Roi, class XfF, class Tab>
-PB_HD int crlb_loglik_fast(const Roi& roi, const float th[6], XfF& xf, const Tab& tab, float crlb[6],
-                           float* loglik) {
+template <int BOX, int METHOD, class Roi, class XfF, class Tab, class ETab>
+PB_HD int crlb_loglik_fast(const Roi& roi, const float th[6], XfF& xf, const Tab& tab, const ETab& etab,
+                           float crlb[6], float* loglik) {
     constexpr int NP = METHOD == 1 ? 6 : 5;
     constexpr int NF = NP * (NP + 1) / 2;
     const double N = (double)th[2], bg = (double)th[3];
     {
-        const Axis ax = make_axis(th[4]);
-        Edge<METHOD> EA, EB = {};
+        const AxisF ax = make_axis_f<METHOD>(th[4]);
+        EdgeF<METHOD> EA, EB = {};
+        double e = -(double)th[0] - 0.5;
 #pragma unroll 1
         for (int k = 0; k < (BOX + 1) / 2; k++) {
-            double f[5];
-            EA = eval_edge<METHOD>(2 * k, th[0], ax);
+            double psf;
+            float d[4];
+            EA = eval_edge_f<METHOD>(e, ax, etab);
             if (k > 0) {
-                pixel_factors<METHOD>(EB, EA, ax, f);
-                xf.put(2 * k - 1, f);
+                pixel_factors_f<METHOD>(EB, EA, ax, psf, d);
+                xf.put_f(2 * k - 1, psf, d);
             }
-            EB = eval_edge<METHOD>(2 * k + 1, th[0], ax);
-            pixel_factors<METHOD>(EA, EB, ax, f);
-            xf.put(2 * k, f);
+            EB = eval_edge_f<METHOD>(e + 1.0, ax, etab);
+            pixel_factors_f<METHOD>(EA, EB, ax, psf, d);
+            xf.put_f(2 * k, psf, d);
+            e += 2.0;
         }
     }
     float Mf[NF];
@@ -992,19 +1181,22 @@ PB_HD int crlb_loglik_fast(const Roi& roi, const float th[6], XfF& xf, const Tab
     for (int q = 0; q < NF; q++) Mf[q] = 0.0f;
     double ll = 0.0;
     {
-        const Axis ay = make_axis(METHOD == 1 ? th[5] : th[4]);
-        Edge<METHOD> EA, EB = {};
+        const AxisF ay = make_axis_f<METHOD>(METHOD == 1 ? th[5] : th[4]);
+        EdgeF<METHOD> EA, EB = {};
+        double e = -(double)th[1] - 0.5;
 #pragma unroll 1
         for (int k = 0; k < (BOX + 1) / 2; k++) {
-            double fy[5];
-            EA = eval_edge<METHOD>(2 * k, th[1], ay);
+            double psf;
+            float d[4];
+            EA = eval_edge_f<METHOD>(e, ay, etab);
             if (k > 0) {
-                pixel_factors<METHOD>(EB, EA, ay, fy);
-                crlb_row_fast<BOX, METHOD, NF>(2 * k - 1, fy, roi, xf, tab, N, bg, Mf, ll);
+                pixel_factors_f<METHOD>(EB, EA, ay, psf, d);
+                crlb_row_fast<BOX, METHOD, NF>(2 * k - 1, psf, d, roi, xf, tab, N, bg, Mf, ll);
             }
-            EB = eval_edge<METHOD>(2 * k + 1, th[1], ay);
-            pixel_factors<METHOD>(EA, EB, ay, fy);
-            crlb_row_fast<BOX, METHOD, NF>(2 * k, fy, roi, xf, tab, N, bg, Mf, ll);
+            EB = eval_edge_f<METHOD>(e + 1.0, ay, etab);
+            pixel_factors_f<METHOD>(EA, EB, ay, psf, d);
+            crlb_row_fast<BOX, METHOD, NF>(2 * k, psf, d, roi, xf, tab, N, bg, Mf, ll);
+            e += 2.0;
         }
     }
     double M[NF];

@@ -19,6 +19,11 @@ struct XfHost {
         for (int k = 0; k < 5; k++) a[c][k] = (T)f[k];
         a[c][5] = (T)(f[0] - (double)a[c][0]);     // low word of PSFx (0 for T = double)
     }
+    void put_f(int c, double psf, const float d[4]) {
+        a[c][0] = (T)psf;
+        for (int k = 0; k < 4; k++) a[c][k + 1] = (T)d[k];
+        a[c][5] = (T)(psf - (double)a[c][0]);
+    }
     void get(int c, T f[6]) const { for (int k = 0; k < 6; k++) f[k] = a[c][k]; }
 };
 template <int BOX>
@@ -32,7 +37,7 @@ template <int BOX>
 struct XfFHost {      // fast CRLB pass: PSF double, (d/dmu, d/dsigma) float
     double px[BOX];
     float c1[BOX], g1[BOX];
-    void put(int c, const double f[5]) { px[c] = f[0]; c1[c] = (float)f[1]; g1[c] = (float)f[3]; }
+    void put_f(int c, double psf, const float d[4]) { px[c] = psf; c1[c] = d[0]; g1[c] = d[2]; }
     void get(int c, double& p, float& a, float& g) const { p = px[c]; a = c1[c]; g = g1[c]; }
 };
 
@@ -48,9 +53,9 @@ void fit_range(const float* spots, long long n, double eps, int max_it, float* t
         while (kk < max_it) {
             kk++;
             XfHost<BOX, T> xf;
-            tps::column_stage<BOX, METHOD, T>(th, xf);
+            tps::column_stage<BOX, METHOD, T>(th, xf, tps::ErfTabDirect{});
             A num[6], den[6];
-            tps::newton_sums<BOX, METHOD, T, A>(roi, th, xf, num, den);
+            tps::newton_sums<BOX, METHOD, T, A>(roi, th, xf, num, den, tps::ErfTabDirect{});
             if (tps::update_theta<BOX, METHOD, A>(th, ms, num, den, eps)) break;
         }
         Xf3Host<BOX> x3;
@@ -58,7 +63,7 @@ void fit_range(const float* spots, long long n, double eps, int max_it, float* t
         int cs = -1;
         if (sizeof(T) == 4) {      // the float32-pixel kernels use the fast CRLB pass with f64 fallback
             XfFHost<BOX> xff;
-            cs = tps::crlb_loglik_fast<BOX, METHOD>(roi, th, xff, tps::LogTabDirect{}, cr, &ll);
+            cs = tps::crlb_loglik_fast<BOX, METHOD>(roi, th, xff, tps::LogTabDirect{}, tps::ErfTabDirect{}, cr, &ll);
         }
         if (cs < 0) cs = tps::crlb_loglik<BOX, METHOD>(roi, th, x3, cr, &ll);
         st |= cs;

@@ -78,5 +78,5 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
     sp = testing.synthetic_spots(n, 7, seed=3)
     for m in ("sigmaxy", "sigma"):
-        for f32 in (0, 1):
+        for f32 in (0, 1, 2):
             report(sp, m, f32)
