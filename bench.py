@@ -81,7 +81,7 @@ def mle_kernel_source_hash():
     import hashlib
 
     h = hashlib.sha256()
-    for name in ("mle_tps.cu", "mle_tps_core.cuh"):
+    for name in ("mle_tps.cu", "mle_tps_core.cuh", "erf_table.cuh"):
         with open(os.path.join(ROOT, "picasso_b200", "csrc", name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()
@@ -758,7 +758,7 @@ def main():
                     "note": "algorithmic 248 B/spot for the iteration kernel (252 B/spot for the "
                             "whole fit; the three kernels together move 720 B/spot = "
                             f"{PIPELINE_DRAM_BYTES_PER_SPOT * n / (ms_kernel * 1e-3) / 1e9 / peak:.1%} of "
-                            "HBM peak). The fit is instruction-issue / FP64-pipe bound, not HBM "
+                            "HBM peak). The fit is instruction-issue / FP32-pipe bound, not HBM "
                             "bound (SURVEY.md 8d) -- see `compute` and DESIGN.md 5.1"}
         else:
             ach = BYTES_PER_SPOT * n / (ms_kernel * 1e-3) / 1e9
@@ -771,7 +771,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f64 edge terms / f32 pixel sums with float-float residual / f32 state",
+            "dtype": "f64 PSF (table erf) / f32 derivative factors and pixel sums with float-float residual / f32 state",
             "data": "synthetic",
             "config": {"workload": "configs[1]: 10M synthetic 7x7 spots/GPU, gaussmle sigmaxy "
                                    "eps=1e-3 max_it=100", "box": BOX, "method": METHOD,

@@ -383,6 +383,11 @@ int pb_link_reduce(size_t n, const int* link_group, int n_groups, int n_cols,
  * the tile-binned shared-memory path; without it the direct-atomics path is used.
  * Unknown mode -> PB_ERR_INVALID, message "blur_method not understood." (render.py:174). */
 size_t pb_render_workspace_bytes(size_t n, int n_pixel_y, int n_pixel_x);
+/* Accumulation pass of the binned path (measurement hook, like pb_mle_set_impl): 0 = 64x64 tiles with
+ * shared-memory atomics (default), 1 = warp-owned strips without shared-memory atomics (measured
+ * slower; csrc/render.cu).  Same results within float32 summation order. */
+int pb_render_set_impl(int impl);
+int pb_render_get_impl(void);
 int pb_render(size_t n, const float* x, const float* y, const float* lpx, const float* lpy,
               double oversampling, double y_min, double x_min, double y_max, double x_max,
               double min_blur_width, int mode, float* image, int n_pixel_y, int n_pixel_x,

@@ -44,6 +44,9 @@ def _declare(lib):
     lib.pb_mle_fit.argtypes = [sz, i32, vp, f64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.pb_mle_fit_dev.argtypes = [sz, i32, vp, f64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.pb_mle_set_impl.argtypes = [i32]
+    lib.pb_render_set_impl.argtypes = [i32]
+    lib.pb_render_set_impl.restype = i32
+    lib.pb_render_get_impl.restype = i32
     lib.pb_mle_profile.argtypes = [i32]
     lib.pb_mle_profile_read.argtypes = [vp]
     for name in ("pb_set_device", "pb_synchronize", "pb_host_alloc", "pb_host_free",

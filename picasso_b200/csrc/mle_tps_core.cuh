@@ -176,7 +176,7 @@ PB_HD double log_pos(double x) {
 
 // Table-driven ln(x) for a positive, finite, normal x (tools/gen_log_table.py; max abs error
 // 1.8e-15 for x < 1e5):  x = m 2^e, m in [1, 2);  i = top 7 mantissa bits;  r = fma(m, rc_i, -1),
-// |r| < 2^-8;  ln x = e ln2 + lc_i + log1p(r) with a degree-5 Taylor sum -- 8 FP64 instructions
+// |r| < 2^-8;  ln x = e ln2 + lc_i + log1p(r) with a degree-4 Taylor sum -- 7 FP64 instructions
 // plus two table loads (log_pos above: 20 FP64 + a reciprocal).  `tab(i)` returns (rc_i, lc_i);
 // on the device the table is staged in shared memory (the index diverges across lanes, which
 // would serialise constant-bank reads).
@@ -271,8 +271,8 @@ PB_HD double log_tab(double x, const Tab& tab) {
     double rc, lc;
     tab.get(idx, rc, lc);
     const double r = fma(m, rc, -1.0);
-    double p = fma(r, 0.2, -0.25);
-    p = fma(p, r, 0.33333333333333331);
+    // log1p(r) = r - r^2/2 + r^3/3 - ...; |r| < 2^-8: the degree-4 truncation error is below 2e-13
+    double p = fma(r, -0.25, 0.33333333333333331);
     p = fma(p, r, -0.5);
     p = fma(p, r, 1.0);
     return fma((double)e, 0.6931471805599453, fma(p, r, lc));
@@ -1107,15 +1107,12 @@ PB_HD void crlb_row_fast(int j, double PSFy, const float fyd[4], const Roi& roi,
         ac[8] += g1w;                    // 1 g1
         ac[9] = fmaf(g1w, g1, ac[9]);    // g1 g1
         const float dataf = roi(j * BOX + i);
-        if (model > 0.0) {
-            // d ln(model) - model - f32(d logf(d)) + d  (gaussmle.py:935-945)
-            if (dataf > 0.0f) {
-                const double d = (double)dataf;
-                ll += fma(d, log_tab(model, tab), d - model) - (double)(dataf * logf(dataf));
-            } else {
-                ll -= model;
-            }
-        }
+        // d ln(model) - model - f32(d logf(d)) + d  (gaussmle.py:935-945); -model for d <= 0, nothing
+        // for model <= 0.  Branch-free: the logs of non-positive arguments are discarded by the selects.
+        const double d = (double)dataf;
+        const double tpos = fma(d, log_tab(model, tab), d - model) - (double)(dataf * logf(dataf));
+        const double t = dataf > 0.0f ? tpos : -model;
+        ll += model > 0.0 ? t : 0.0;
     }
 #define PB_PR(p, q) ac[((p) < (q) ? (p) : (q)) * 4 - (((p) < (q) ? (p) : (q)) * (((p) < (q) ? (p) : (q)) - 1)) / 2 + \
                                (((p) < (q) ? (q) : (p)) - ((p) < (q) ? (p) : (q)))]

@@ -19,12 +19,21 @@
 //                          j, j+8, ...; a row's 8 consecutive pixels share one or
 //                          two 32 B sectors, so the L2 atomic unit sees coalesced
 //                          reductions.  Used for small batches.
-//   render_tiled_kernel    localisations are binned by 64x64-pixel tile (counting
-//                          sort on the device, the float4 records are scattered into
-//                          tile order); one CTA accumulates its tile in shared memory,
-//                          one THREAD per localisation, with shared-memory atomics and
-//                          flushes it once with coalesced reductions; window parts
-//                          that cross the tile edge go straight to global atomics.
+//   render_strip_kernel    (pb_render_set_impl(1); measured slower, kept for the A/B) binned by 16-row x 64-column
+//                          STRIP (counting sort on the device; a window that straddles two strips is
+//                          filed in both).  One WARP owns one strip of its CTA's 64x64 shared-memory tile
+//                          and draws its localisations one after the other, the 32 lanes covering an
+//                          8-column x 8-row block of the window (two pixels per lane) with plain
+//                          load / add / store: no two lanes ever touch the same pixel and no other warp
+//                          touches the strip, so there are NO shared-memory atomics.  The tile is flushed
+//                          once with coalesced reductions; window columns beyond the tile edge go
+//                          straight to global atomics.
+//   render_tiled_kernel    (default for dense images) localisations are binned by 64x64-pixel tile
+//                          (counting sort on the device, the float4 records are scattered into tile
+//                          order); one CTA accumulates its tile in shared memory, one THREAD per
+//                          localisation, with shared-memory atomicAdd, and flushes it once with
+//                          coalesced reductions; window parts that cross the tile edge go straight
+//                          to global atomics.
 #include <algorithm>
 #include <atomic>
 #include <stdlib.h>
@@ -174,8 +183,7 @@ constexpr int kSizeClasses = 4;           // bins per tile: by blur width (windo
 
 // pass 1: tile id per localisation (-1 = not in view) + histogram of tile sizes
 __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restrict__ tile_of,
-                                  unsigned int* __restrict__ tile_count,
-                                  unsigned int* __restrict__ tile_norm /* per tile: max 1/(2 pi sx sy), float bits */) {
+                                  unsigned int* __restrict__ tile_count) {
     unsigned long long local = 0;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
          k += (long long)gridDim.x * blockDim.x) {
@@ -200,15 +208,6 @@ __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restri
                 const int tile = (pyb / kTile) * tiles_x + (px / kTile);
                 t = tile * kSizeClasses + cls;
                 atomicAdd(tile_count + t, 1u);
-                if (tile_norm) {
-                    // upper bound of this localisation's pixel values (positive floats order like their bits)
-                    const float bw = __fmul_rn(a.osf, fmaxf(a.lpx[k], a.mbw));
-                    const float bh = __fmul_rn(a.osf, fmaxf(a.lpy[k], a.mbw));
-                    float sx = bw, sy = bh;
-                    if (a.mode == 2) { sy = __fdiv_rn(__fadd_rn(bh, bw), 2.0f); sx = sy; }
-                    const float norm = 1.0f / (6.2831853071795862f * sx * sy) * 1.0001f;
-                    atomicMax(tile_norm + tile, __float_as_uint(norm));
-                }
             }
         }
         tile_of[k] = t;
@@ -276,44 +275,15 @@ __global__ void render_scatter_kernel(const RenderArgs a, const int* __restrict_
 // far inside the 1e-4 render tolerance).
 constexpr int kMaxWin = 16;               // windows wider than this take the generic path
 
-// PB_RENDER_FIXED=1 selects the fixed-point accumulation (A/B measurement only).  Measured on B200
-// (profiles/r02_summary.md): 6.61 ms instead of 6.99 ms for 50 M localisations -- ATOMS.CAST.SPIN retries
-// in hardware, so the float update is ~5 instructions, not a 12-instruction software loop, and the pass is
-// bound by the rate of shared-memory atomics of either kind -- while its 2.3e-7-of-the-bound resolution
-// misses the 1e-6-of-the-maximum absolute pixel tolerance on dim pixels.  Default: float32 atomicAdd.
-bool render_fixed_point() {
-    static const bool on = [] {
-        if (const char* e = getenv("PB_RENDER_FIXED")) return atoi(e) != 0;
-        return false;
-    }();
-    return on;
-}
-
-// FIXED: the shared tile accumulates unsigned 32-bit fixed-point values with native ATOMS.ADD instead
-// of float atomicAdd (a compare-and-swap loop on sm_100: ATOMS.CAST.SPIN, ~12 instructions per update).
-// Every pixel of the tile is bounded by B = (localisations of the tile) x (largest kernel norm among
-// them, from render_bin_kernel), so scale = (2^32 - n - 2^16) / B can never overflow; one update is
-// FMUL + F2I + ATOMS.ADD.  Resolution B / 2^32 per update (2.3e-7 of the bound): deviations stay far
-// inside the render tolerance (rtol 1e-4 on bright pixels, 1e-6 of the maximum elsewhere).
-template <bool FIXED>
 __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, int tiles_x,
                                                            const unsigned int* __restrict__ start,
-                                                           const float4* __restrict__ sorted,
-                                                           const unsigned int* __restrict__ tile_norm) {
+                                                           const float4* __restrict__ sorted) {
     __shared__ float acc[kTile * kTile];
     __shared__ float gxs[kMaxWin][256];
-    unsigned int* accu = reinterpret_cast<unsigned int*>(acc);
     const int tile = blockIdx.x;
     // the tile's localisations: its kSizeClasses consecutive bins, narrow windows first
     const unsigned int first = start[tile * kSizeClasses], last = start[(tile + 1) * kSizeClasses];
     if (first == last) return;
-    float scale = 1.0f, inv_scale = 1.0f;
-    if (FIXED) {
-        const float nt = (float)(last - first);
-        const float B = nt * __uint_as_float(tile_norm[tile]);
-        scale = (4294901760.0f - nt) / B;
-        inv_scale = 1.0f / scale;
-    }
     const int ty0 = a.row0 + (tile / tiles_x) * kTile, tx0 = (tile % tiles_x) * kTile;
     const int band_end = a.row0 + a.nrows;
     for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) acc[q] = 0.0f;      // (0.0f == 0u)
@@ -354,19 +324,16 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
             for (int ii = ii0; ii < ii1; ii++) {
                 const float dy = dy0 + (float)ii;
                 const float gy = norm * expf(-dy * dy * inv_2sy2);
-                const float gys = gy * scale;
                 const int i = i_min + ii;
                 const bool iin = (i >= ty0) && (i < ty0 + kTile);
                 float* grow = a.image + (size_t)(i - a.row0) * a.npx;
                 float* srow = acc + (i - ty0) * kTile - tx0;
-                unsigned int* urow = accu + (i - ty0) * kTile - tx0;
 #pragma unroll 1
                 for (int jj = 0; jj < nx; jj++) {
                     const int j = j_min + jj;
                     const float g = gxs[jj][tid];
                     if (iin && j >= tx0 && j < tx0 + kTile) {
-                        if (FIXED) atomicAdd(urow + j, __float2uint_rn(gys * g));
-                        else atomicAdd(srow + j, gy * g);
+                        atomicAdd(srow + j, gy * g);
                     } else {
                         atomicAdd(grow + j, gy * g);
                     }
@@ -387,7 +354,186 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
     __syncthreads();
     for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) {
         const int i = ty0 + q / kTile, j = tx0 + q % kTile;
-        const float v = FIXED ? (float)accu[q] * inv_scale : acc[q];
+        const float v = acc[q];
+        if (v != 0.0f && i < band_end && j < a.npx) atomicAdd(a.image + (size_t)(i - a.row0) * a.npx + j, v);
+    }
+}
+
+// ---- strip path: warp-owned strips, no shared-memory atomics -------------------------------------
+constexpr int kStripRows = 16;            // rows per strip (4 strips = 4 warps per 64x64 tile)
+constexpr int kStripsPerTile = kTile / kStripRows;
+constexpr int kAccStride = kTile + 8;     // padded tile row: the 4 rows x 8 columns a warp touches per step
+                                          // fall into 32 different banks
+constexpr int kTwoStrips = 1 << 30;       // tile_of flag: the window continues in the strip below
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// pass 1: strip bin(s) per localisation + histogram of bin sizes.  tile_of: -1 nothing to draw,
+// -2 window taller than two strips (drawn directly by the scatter pass), else first bin
+// (| kTwoStrips).  Window geometry as make_splat, rows clipped to the band.
+__global__ void render_strip_bin_kernel(const RenderArgs a, int tiles_x, int* __restrict__ tile_of,
+                                        unsigned int* __restrict__ bin_count) {
+    unsigned long long local = 0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const Splat s = make_splat(a, k);
+        int t = -1;
+        if (s.in_view) {
+            if (centre_in_band(a, s.y_)) local++;
+            const int lo = max(s.i_min, a.row0), hi = min(s.i_max, a.row0 + a.nrows);
+            if (lo < hi && s.j_min < s.j_max) {
+                const int s0 = (lo - a.row0) / kStripRows, s1 = (hi - 1 - a.row0) / kStripRows;
+                if (s1 - s0 > 1) {
+                    t = -2;
+                } else {
+                    int px = (int)s.x_;
+                    px = min(max(px, 0), a.npx - 1);
+                    t = s0 * tiles_x + px / kTile;
+                    atomicAdd(bin_count + t, 1u);
+                    if (s1 > s0) {
+                        atomicAdd(bin_count + t + tiles_x, 1u);
+                        t |= kTwoStrips;
+                    }
+                }
+            }
+        }
+        tile_of[k] = t;
+    }
+    __shared__ unsigned long long blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&blk, local);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk) atomicAdd(a.count, blk);
+}
+
+// pass 3: scatter the records into bin order (a straddling window into both strips); the rare very
+// tall windows are drawn here, one thread each, with global atomics and float64 kernels
+__global__ void render_strip_scatter_kernel(const RenderArgs a, int tiles_x, const int* __restrict__ tile_of,
+                                            unsigned int* __restrict__ cursor, float4* __restrict__ sorted) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int t = tile_of[k];
+        if (t >= 0) {
+            const float4 rec = make_float4(a.x[k], a.y[k], a.lpx[k], a.lpy[k]);
+            const int bin = t & (kTwoStrips - 1);
+            sorted[atomicAdd(cursor + bin, 1u)] = rec;
+            if (t & kTwoStrips) sorted[atomicAdd(cursor + bin + tiles_x, 1u)] = rec;
+        } else if (t == -2) {
+            const Splat s = make_splat(a, k);
+            const int lo = max(s.i_min, a.row0), hi = min(s.i_max, a.row0 + a.nrows);
+            for (int i = lo; i < hi; i++) {
+                const float gy = splat_gy(s, i);
+                for (int j = s.j_min; j < s.j_max; j++)
+                    atomicAdd(a.image + (size_t)(i - a.row0) * a.npx + j, __fmul_rn(gy, splat_gx(s, j)));
+            }
+        }
+    }
+}
+
+// pass 4: one CTA per 64x64 tile, one warp per strip.  Per batch of 32 records every lane derives the
+// window of one record (float64 coordinates, float32 sigma, np.int32 truncation: render.py:505-525)
+// and parks it in shared memory; then the warp draws the records one after the other.  For each
+// 8-column x 8-row block of a window lanes 0-7 evaluate the column kernel, lanes 8-15 the row kernel
+// (exp2 of an offset formed in float64; relative deviation from the reference's float64 exp ~1e-6,
+// render tolerance 1e-4), shuffles hand them out and every lane updates its two pixels with plain
+// shared-memory load / add / store.
+__global__ void __launch_bounds__(128) render_strip_kernel(const RenderArgs a, int tiles_x, int strips_y,
+                                                           const unsigned int* __restrict__ start,
+                                                           const float4* __restrict__ sorted) {
+    __shared__ float acc[kTile * kAccStride];
+    __shared__ int4 geo_a[kStripsPerTile][32];     // j_min, first row, columns, rows (inside the strip)
+    __shared__ float4 geo_b[kStripsPerTile][32];   // dx0, dy0, -log2e / (2 sx^2), -log2e / (2 sy^2)
+    __shared__ float geo_c[kStripsPerTile][32];    // 1 / (2 pi sx sy)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_row = blockIdx.x / tiles_x, txi = blockIdx.x % tiles_x;
+    const int ty0 = a.row0 + tile_row * kTile, tx0 = txi * kTile;
+    const int band_end = a.row0 + a.nrows;
+    const int strip = tile_row * kStripsPerTile + warp;
+    unsigned int first = 0, last = 0;
+    if (strip < strips_y) {
+        const long long bin = (long long)strip * tiles_x + txi;
+        first = start[bin];
+        last = start[bin + 1];
+    }
+    if (!__syncthreads_or(first != last)) return;
+    for (int q = threadIdx.x; q < kTile * kAccStride; q += blockDim.x) acc[q] = 0.0f;
+    __syncthreads();
+    const int sy0 = ty0 + warp * kStripRows, sy1 = min(sy0 + kStripRows, band_end);
+    const int c = lane & 7, r2 = lane >> 3;
+    const bool is_row_lane = (lane & 8) != 0;
+    for (unsigned int q0 = first; q0 < last; q0 += 32) {
+        const int cnt = (int)min(32u, last - q0);
+        if (lane < cnt) {
+            const float4 L = sorted[q0 + lane];
+            const double x_ = a.os * ((double)L.x - a.x_min);
+            const double y_ = a.os * ((double)L.y - a.y_min);
+            const float bw = __fmul_rn(a.osf, fmaxf(L.z, a.mbw));
+            const float bh = __fmul_rn(a.osf, fmaxf(L.w, a.mbw));
+            float sx, sy;
+            if (a.mode == 2) { sy = __fdiv_rn(__fadd_rn(bh, bw), 2.0f); sx = sy; }
+            else { sx = bw; sy = bh; }
+            const double moy = 3.0 * (double)sy, mox = 3.0 * (double)sx;
+            const int i_min = max((int)(y_ - moy), 0);
+            const int i_max = min((int)(y_ + moy + 1.0), a.npy);
+            const int j_min = max((int)(x_ - mox), 0);
+            const int j_max = min((int)(x_ + mox) + 1, a.npx);
+            const int lo = max(i_min, sy0), hi = min(i_max, sy1);
+            const int nx = j_max - j_min, nr = hi - lo;
+            geo_a[warp][lane] = make_int4(j_min, lo, (nx > 0 && nr > 0) ? nx : 0, nr > 0 ? nr : 0);
+            geo_b[warp][lane] = make_float4((float)((double)j_min + 0.5 - x_), (float)((double)lo + 0.5 - y_),
+                                            -1.4426950408889634f / (2.0f * sx * sx),
+                                            -1.4426950408889634f / (2.0f * sy * sy));
+            geo_c[warp][lane] = 1.0f / (6.2831853071795862f * sx * sy);
+        }
+        __syncwarp();
+        for (int b = 0; b < cnt; b++) {
+            const int4 A = geo_a[warp][b];
+            const float4 B = geo_b[warp][b];
+            const float nrm = geo_c[warp][b];
+            for (int rr = 0; rr < A.w; rr += 8) {
+                for (int cc = 0; cc < A.z; cc += 8) {
+                    // lanes 0-7 (and 16-23): column kernel of column cc + c; lanes 8-15 (24-31): row kernel
+                    const float off = (is_row_lane ? B.y : B.x) + (float)((is_row_lane ? rr : cc) + c);
+                    float g = ex2_approx(off * off * (is_row_lane ? B.w : B.z));
+                    if (is_row_lane) g *= nrm;
+                    const float gx = __shfl_sync(0xffffffffu, g, c);
+                    const float gy0 = __shfl_sync(0xffffffffu, g, 8 + r2);
+                    const float gy1 = __shfl_sync(0xffffffffu, g, 12 + r2);
+                    const int col = cc + c;
+                    if (col < A.z) {
+                        const int j = A.x + col;
+                        const bool intile = (unsigned)(j - tx0) < (unsigned)kTile;
+                        const int ra = rr + r2, rb = rr + r2 + 4;
+                        if (ra < A.w) {
+                            const int i = A.y + ra;
+                            const float v = gy0 * gx;
+                            if (intile) acc[(i - ty0) * kAccStride + (j - tx0)] += v;
+                            else atomicAdd(a.image + (size_t)(i - a.row0) * a.npx + j, v);
+                        }
+                        if (rb < A.w) {
+                            const int i = A.y + rb;
+                            const float v = gy1 * gx;
+                            if (intile) acc[(i - ty0) * kAccStride + (j - tx0)] += v;
+                            else atomicAdd(a.image + (size_t)(i - a.row0) * a.npx + j, v);
+                        }
+                    }
+                    __syncwarp();      // the next block / record may touch the same pixels from other lanes
+                }
+            }
+        }
+        __syncwarp();                  // geo_* are rewritten by the next batch
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < kTile * kTile; q += blockDim.x) {
+        const int r = q / kTile, cq = q % kTile;
+        const int i = ty0 + r, j = tx0 + cq;
+        const float v = acc[r * kAccStride + cq];
         if (v != 0.0f && i < band_end && j < a.npx) atomicAdd(a.image + (size_t)(i - a.row0) * a.npx + j, v);
     }
 }
@@ -558,12 +704,39 @@ extern "C" int pb_render_unpack_records_dev(size_t n, const float* d_records, fl
     return PB_OK;
 }
 
-// Workspace (bytes) pb_render_dev needs for the tiled path; 0 => use the direct path.
+// Workspace (bytes) pb_render_dev needs for the binned paths.  Strip path: up to two float4 records per
+// localisation (a window straddling two strips) + one int32 bin word, and count / start / cursor per bin
+// (16-row x 64-column strips); the 64x64-tile layout of the round-1 pass fits inside.
 extern "C" size_t pb_render_workspace_bytes(size_t n, int n_pixel_y, int n_pixel_x) {
-    const size_t tiles = (size_t)((n_pixel_y + kTile - 1) / kTile) * ((n_pixel_x + kTile - 1) / kTile);
-    // tile_of (4 B) + sorted float4 (16 B) per loc; count / start / cursor per bin; norm bound per tile
-    return n * 20 + (tiles * kSizeClasses + 1) * 12 + tiles * 4 + 256;
+    const size_t tiles_x = (size_t)((n_pixel_x + kTile - 1) / kTile);
+    const size_t strips = (size_t)((n_pixel_y + kStripRows - 1) / kStripRows) * tiles_x;
+    const size_t tiles4 = (size_t)((n_pixel_y + kTile - 1) / kTile) * tiles_x * kSizeClasses;
+    return n * 36 + (std::max(strips, tiles4) + 1) * 12 + 256;
 }
+
+// Accumulation pass of the binned path: 0 = 64x64 tiles, one thread per localisation, shared-memory
+// atomicAdd (default); 1 = warp-owned 16-row strips, plain load / add / store (no shared-memory atomics).
+// Measured on B200, 50 M localisations -> 10240^2 (profiles/r02_summary.md): 7.15 ms vs 12.4 ms -- the
+// strip pass needs 205 warp instructions per localisation (8x8 blocks of 3..11-pixel windows keep 38 % of
+// the lanes busy, ~60 instructions of geometry, kernel evaluation, shuffles and index arithmetic per
+// block) against 141 for the atomic pass, so removing the atomics does not pay.  Kept selectable
+// (pb_render_set_impl / PB_RENDER_IMPL) so the A/B stays reproducible.
+static std::atomic<int> g_render_impl{-1};
+static int render_impl() {
+    int v = g_render_impl.load();
+    if (v < 0) {
+        v = 0;
+        if (const char* e = getenv("PB_RENDER_IMPL")) v = atoi(e) == 1 ? 1 : 0;
+        g_render_impl.store(v);
+    }
+    return v;
+}
+extern "C" int pb_render_set_impl(int impl) {
+    if (impl != 0 && impl != 1) { pb_set_error("pb_render_set_impl: impl must be 0 or 1"); return PB_ERR_INVALID; }
+    g_render_impl.store(impl);
+    return PB_OK;
+}
+extern "C" int pb_render_get_impl(void) { return render_impl(); }
 
 extern "C" int pb_render_dev(size_t n, const float* d_x, const float* d_y, const float* d_lpx,
                              const float* d_lpy, double oversampling, double y_min, double x_min,
@@ -614,7 +787,7 @@ extern "C" int pb_render_band_dev(size_t n, const float* d_x, const float* d_y, 
     // the 100 k-localisation segments of an undrift run on 4096^2 pixels: 24 per tile -- are faster
     // direct (measured: 0.24 -> 0.04 ms per segment, 48 -> 7.6 ms for the 200 segments of config 5); dense
     // ones (config 4: 1953 per tile) tiled.
-    const bool tiled = d_workspace && workspace_bytes >= need && n >= 65536 && n < 0xffffffffull &&
+    const bool tiled = d_workspace && workspace_bytes >= need && n >= 65536 && n < 0x7fffffffull &&
                        ntiles >= 64 && (long long)n >= 64 * ntiles &&
                        ((reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0);
     if (!tiled) {
@@ -625,24 +798,32 @@ extern "C" int pb_render_band_dev(size_t n, const float* d_x, const float* d_y, 
         PB_CUDA_CHECK(cudaGetLastError());
         return PB_OK;
     }
-    // workspace layout: sorted[n] float4 | tile_of[n] i32 | count[T] | start[T+1] | cursor[T]
+    // workspace layout: sorted[2n] float4 | tile_of[n] i32 | count[B] | start[B+1] | cursor[B]
     char* w = static_cast<char*>(d_workspace);
     float4* sorted = reinterpret_cast<float4*>(w);
-    int* tile_of = reinterpret_cast<int*>(w + n * 16);
-    unsigned int* tcount = reinterpret_cast<unsigned int*>(w + n * 20);
-    const long long nbins = ntiles * kSizeClasses;
-    unsigned int* tstart = tcount + nbins;
-    unsigned int* tcursor = tstart + nbins + 1;
-    unsigned int* tnorm = tcursor + nbins;
-    const bool fixed = render_fixed_point();
-    PB_CUDA_CHECK(cudaMemsetAsync(tcount, 0, nbins * 4, s));
-    if (fixed) PB_CUDA_CHECK(cudaMemsetAsync(tnorm, 0, ntiles * 4, s));
+    int* tile_of = reinterpret_cast<int*>(w + n * 32);
+    unsigned int* tcount = reinterpret_cast<unsigned int*>(w + n * 36);
     int grid = (int)std::min<long long>(((long long)n + threads - 1) / threads, 148 * 16);
-    render_bin_kernel<<<grid, threads, 0, s>>>(a, tiles_x, tile_of, tcount, fixed ? tnorm : nullptr);
-    render_scan_kernel<<<1, 1024, 0, s>>>(tcount, tstart, tcursor, (int)nbins);
-    render_scatter_kernel<<<grid, threads, 0, s>>>(a, tile_of, tcursor, sorted);
-    if (fixed) render_tiled_kernel<true><<<(unsigned)ntiles, 256, 0, s>>>(a, tiles_x, tstart, sorted, tnorm);
-    else render_tiled_kernel<false><<<(unsigned)ntiles, 256, 0, s>>>(a, tiles_x, tstart, sorted, nullptr);
+    if (render_impl() == 0) {
+        const long long nbins = ntiles * kSizeClasses;
+        unsigned int* tstart = tcount + nbins;
+        unsigned int* tcursor = tstart + nbins + 1;
+        PB_CUDA_CHECK(cudaMemsetAsync(tcount, 0, nbins * 4, s));
+        render_bin_kernel<<<grid, threads, 0, s>>>(a, tiles_x, tile_of, tcount);
+        render_scan_kernel<<<1, 1024, 0, s>>>(tcount, tstart, tcursor, (int)nbins);
+        render_scatter_kernel<<<grid, threads, 0, s>>>(a, tile_of, tcursor, sorted);
+        render_tiled_kernel<<<(unsigned)ntiles, 256, 0, s>>>(a, tiles_x, tstart, sorted);
+    } else {
+        const int strips_y = (n_rows + kStripRows - 1) / kStripRows;
+        const long long nbins = (long long)strips_y * tiles_x;
+        unsigned int* tstart = tcount + nbins;
+        unsigned int* tcursor = tstart + nbins + 1;
+        PB_CUDA_CHECK(cudaMemsetAsync(tcount, 0, nbins * 4, s));
+        render_strip_bin_kernel<<<grid, threads, 0, s>>>(a, tiles_x, tile_of, tcount);
+        render_scan_kernel<<<1, 1024, 0, s>>>(tcount, tstart, tcursor, (int)nbins);
+        render_strip_scatter_kernel<<<grid, threads, 0, s>>>(a, tiles_x, tile_of, tcursor, sorted);
+        render_strip_kernel<<<(unsigned)ntiles, 128, 0, s>>>(a, tiles_x, strips_y, tstart, sorted);
+    }
     g_pb_launches += 4;
     PB_CUDA_CHECK(cudaGetLastError());
     return PB_OK;

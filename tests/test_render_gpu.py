@@ -61,10 +61,31 @@ def test_render_bundled_testdata(golden_dir):
         _close(img, g[f"render_{bm}_image"])
 
 
+@pytest.fixture
+def render_impl():
+    """Select the accumulation pass of the binned path for one test (0 = tile atomics, the default;
+    1 = warp-owned strips) and restore the default afterwards."""
+    from picasso_b200 import _lib
+
+    lib = _lib.load()
+    default = lib.pb_render_get_impl()
+
+    def select(impl):
+        _lib.check(lib.pb_render_set_impl(impl))
+
+    yield select
+    lib.pb_render_set_impl(default)
+
+
 @pytest.mark.filterwarnings("ignore::DeprecationWarning")
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("bm", ["gaussian", "gaussian_iso", None])
-def test_render_large_tiled_vs_oracle(oracle, bm):
-    """300k localisations at oversampling 20 -> the tile-binned shared-memory path."""
+def test_render_large_tiled_vs_oracle(oracle, bm, impl, render_impl):
+    """300k localisations at oversampling 20 -> the binned shared-memory paths (both accumulation
+    passes: tile atomics and warp-owned strips)."""
+    if bm is None and impl == 1:
+        pytest.skip("the histogram has no binned path")
+    render_impl(impl)
     rng = np.random.default_rng(2)
     n = 300_000
     locs = pd.DataFrame({"x": rng.uniform(0, 64, n).astype(np.float32),
@@ -78,6 +99,26 @@ def test_render_large_tiled_vs_oracle(oracle, bm):
     if bm is None:
         np.testing.assert_array_equal(img, oimg)
     else:
+        _close(img, oimg)
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+@pytest.mark.parametrize("impl", [0, 1])
+def test_render_binned_wide_windows(oracle, impl, render_impl):
+    """Windows wider than the per-thread column cache (16 px) / taller than two strips among ordinary
+    ones: both accumulation passes route them through their generic branches."""
+    render_impl(impl)
+    rng = np.random.default_rng(5)
+    n = 200_000
+    lp = rng.uniform(0.02, 0.08, (2, n)).astype(np.float32)
+    lp[:, :2000] = rng.uniform(0.15, 0.45, (2, 2000)).astype(np.float32)
+    locs = pd.DataFrame({"x": rng.uniform(0, 64, n).astype(np.float32),
+                         "y": rng.uniform(0, 48, n).astype(np.float32), "lpx": lp[0], "lpy": lp[1]})
+    info = [{"Height": 48, "Width": 64, "Frames": 1, "Pixelsize": 130}]
+    for bm in ("gaussian", "gaussian_iso"):
+        k, img = pbrender.render(locs, info, oversampling=20, blur_method=bm)
+        ok, oimg = oracle.render(locs, info, oversampling=20, blur_method=bm)
+        assert k == ok
         _close(img, oimg)
 
 
