@@ -376,21 +376,22 @@ struct ErfTabDirect {     // host build / staging source
 template <class Tab>
 PB_HD double half_erf_tab(double z, const Tab& tab) {
 #ifdef __CUDA_ARCH__
-    const int zhi = __double2hiint(z);
-    const int ahi = zhi & 0x7fffffff;
-    const bool big = (unsigned)(ahi - 0x40180000) <= (0x7ff00000u - 0x40180000u);    // 6 <= |z| <= inf
-    const double a = __hiloint2double(big ? 0x40180000 : ahi, big ? 0 : __double2loint(z));
+    // |z| >= 6 (and inf) is resolved by a select at the END, off the dependent chain
+    // |z| -> interval -> table -> polynomial; NaN fails the test and propagates through d
+    const unsigned ahi = (unsigned)__double2hiint(z) & 0x7fffffffu;
+    const bool big = (ahi - 0x40180000u) <= (0x7ff00000u - 0x40180000u);
+    const double a = fabs(z);
     const double t = fma(a, 16.0, 6755399441055744.0);      // 1.5 * 2^52: rint(16 a) in the low word
     unsigned k = (unsigned)__double2loint(t);
 #else
-    double a = fabs(z);
-    a = a >= 6.0 ? 6.0 : a;
+    const double a = fabs(z);
+    const bool big = a >= 6.0;
     const double t = fma(a, 16.0, 6755399441055744.0);
     uint64_t bits;
     memcpy(&bits, &t, 8);
     unsigned k = (unsigned)(bits & 0xffffffffu);
 #endif
-    k = k > 96u ? 96u : k;                                   // (NaN: any in-range entry; d is NaN)
+    k = k > 96u ? 96u : k;                                   // (huge / NaN: any in-range entry)
     const double n = t - 6755399441055744.0;
     const double d = fma(n, -0.0625, a);
     double c0, c1;
@@ -400,7 +401,8 @@ PB_HD double half_erf_tab(double z, const Tab& tab) {
     float pf = fmaf(c5, df, c4);
     pf = fmaf(pf, df, c3);
     pf = fmaf(pf, df, c2);
-    const double r = fma(fma((double)pf, d, c1), d, c0);
+    double r = fma(fma((double)pf, d, c1), d, c0);
+    r = big ? 0.5 : r;
     return copysign(r, z);
 }
 // exp(-q), q >= 0, float32 (device: MUFU.EX2, 2 ulp; underflows to 0)
@@ -454,12 +456,12 @@ struct EdgeF {
     double E;          // erf(e / (sqrt2 sigma)) / 2, float64: the PSF is a difference of two of these
     float A, eA, u, v; // as in Edge, float32
 };
-// e = (g - mu) - 1/2 of edge g
+// e = (g - mu) - 1/2 of edge g in float64 (for the erf argument) and, formed independently, in float32
+// (for the Gaussian term: no conversion on the way)
 template <int METHOD, class Tab>
-PB_HD EdgeF<METHOD> eval_edge_f(double e, const AxisF& ax, const Tab& tab) {
+PB_HD EdgeF<METHOD> eval_edge_f(double e, float ef, const AxisF& ax, const Tab& tab) {
     EdgeF<METHOD> r;
     r.E = half_erf_tab(e * ax.c, tab);
-    const float ef = (float)e;
     const float t = ef * ax.rs;
     const float q = 0.5f * t * t;
     const float Af = exp_neg_f(q);
@@ -592,19 +594,21 @@ PB_HD void column_stage(const float th[6], Xf& xf, const Tab& tab) {
         const AxisF ax = make_axis_f<METHOD>(th[4]);
         EdgeF<METHOD> A, B = {};
         double e = -(double)th[0] - 0.5;      // edge 0; edges are 1 apart (exact in float64)
+        float gf = 0.0f;                  // edge index as float32 (exact)
 #pragma unroll 1
         for (int k = 0; k < (BOX + 1) / 2; k++) {
             double psf;
             float d[4];
-            A = eval_edge_f<METHOD>(e, ax, tab);
+            A = eval_edge_f<METHOD>(e, (gf - th[0]) - 0.5f, ax, tab);
             if (k > 0) {
                 pixel_factors_f<METHOD>(B, A, ax, psf, d);
                 xf.put_f(2 * k - 1, psf, d);
             }
-            B = eval_edge_f<METHOD>(e + 1.0, ax, tab);
+            B = eval_edge_f<METHOD>(e + 1.0, (gf - th[0]) + 0.5f, ax, tab);
             pixel_factors_f<METHOD>(A, B, ax, psf, d);
             xf.put_f(2 * k, psf, d);
             e += 2.0;
+            gf += 2.0f;
         }
         return;
     }
@@ -728,19 +732,21 @@ PB_HD void newton_sums(const Roi& roi, const float th[6], const Xf& xf, A num[6]
         const AxisF ay = make_axis_f<METHOD>(METHOD == 1 ? th[5] : th[4]);
         EdgeF<METHOD> EA, EB = {};
         double e = -(double)th[1] - 0.5;
+        float gf = 0.0f;
 #pragma unroll 1
         for (int k = 0; k < (BOX + 1) / 2; k++) {
             double psf;
             float d[4];
-            EA = eval_edge_f<METHOD>(e, ay, tab);
+            EA = eval_edge_f<METHOD>(e, (gf - th[1]) - 0.5f, ay, tab);
             if (k > 0) {
                 pixel_factors_f<METHOD>(EB, EA, ay, psf, d);
                 accumulate_row<BOX, METHOD, T, A>(2 * k - 1, psf, d, roi, xf, th[2], th[3], num, den);
             }
-            EB = eval_edge_f<METHOD>(e + 1.0, ay, tab);
+            EB = eval_edge_f<METHOD>(e + 1.0, (gf - th[1]) + 0.5f, ay, tab);
             pixel_factors_f<METHOD>(EA, EB, ay, psf, d);
             accumulate_row<BOX, METHOD, T, A>(2 * k, psf, d, roi, xf, th[2], th[3], num, den);
             e += 2.0;
+            gf += 2.0f;
         }
         return;
     }
@@ -1158,19 +1164,21 @@ PB_HD int crlb_loglik_fast(const Roi& roi, const float th[6], XfF& xf, const Tab
         const AxisF ax = make_axis_f<METHOD>(th[4]);
         EdgeF<METHOD> EA, EB = {};
         double e = -(double)th[0] - 0.5;
+        float gf = 0.0f;                  // edge index as float32 (exact)
 #pragma unroll 1
         for (int k = 0; k < (BOX + 1) / 2; k++) {
             double psf;
             float d[4];
-            EA = eval_edge_f<METHOD>(e, ax, etab);
+            EA = eval_edge_f<METHOD>(e, (gf - th[0]) - 0.5f, ax, etab);
             if (k > 0) {
                 pixel_factors_f<METHOD>(EB, EA, ax, psf, d);
                 xf.put_f(2 * k - 1, psf, d);
             }
-            EB = eval_edge_f<METHOD>(e + 1.0, ax, etab);
+            EB = eval_edge_f<METHOD>(e + 1.0, (gf - th[0]) + 0.5f, ax, etab);
             pixel_factors_f<METHOD>(EA, EB, ax, psf, d);
             xf.put_f(2 * k, psf, d);
             e += 2.0;
+            gf += 2.0f;
         }
     }
     float Mf[NF];
@@ -1181,19 +1189,21 @@ PB_HD int crlb_loglik_fast(const Roi& roi, const float th[6], XfF& xf, const Tab
         const AxisF ay = make_axis_f<METHOD>(METHOD == 1 ? th[5] : th[4]);
         EdgeF<METHOD> EA, EB = {};
         double e = -(double)th[1] - 0.5;
+        float gf = 0.0f;
 #pragma unroll 1
         for (int k = 0; k < (BOX + 1) / 2; k++) {
             double psf;
             float d[4];
-            EA = eval_edge_f<METHOD>(e, ay, etab);
+            EA = eval_edge_f<METHOD>(e, (gf - th[1]) - 0.5f, ay, etab);
             if (k > 0) {
                 pixel_factors_f<METHOD>(EB, EA, ay, psf, d);
                 crlb_row_fast<BOX, METHOD, NF>(2 * k - 1, psf, d, roi, xf, tab, N, bg, Mf, ll);
             }
-            EB = eval_edge_f<METHOD>(e + 1.0, ay, etab);
+            EB = eval_edge_f<METHOD>(e + 1.0, (gf - th[1]) + 0.5f, ay, etab);
             pixel_factors_f<METHOD>(EA, EB, ay, psf, d);
             crlb_row_fast<BOX, METHOD, NF>(2 * k, psf, d, roi, xf, tab, N, bg, Mf, ll);
             e += 2.0;
+            gf += 2.0f;
         }
     }
     double M[NF];
