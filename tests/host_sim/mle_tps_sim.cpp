@@ -105,3 +105,9 @@ extern "C" int sim_mle_tps(const float* spots, long long n, int box, double eps,
         default: return -1;
     }
 }
+
+// erf(z)/2 of the float32-pixel kernels (97-interval table), for the accuracy test
+extern "C" void sim_half_erf(const double* z, long long n, double* out) {
+    for (long long i = 0; i < n; i++) out[i] = tps::half_erf_tab(z[i], tps::ErfTabDirect{});
+}
+

@@ -90,3 +90,29 @@ def test_sim_float_spots(sim, golden_dir, tag, eps, max_it, method, f32):
     if max_it == 0:
         assert (it == 0).all()
         np.testing.assert_array_equal(th, gth)      # start values are bit-exact
+
+
+def test_table_erf_accuracy(sim):
+    """The 97-interval erf table of the float32-pixel kernels (erf_table.cuh, tools/gen_erf_table.py)
+    against math.erf: max abs error of erf(z)/2 below 2e-11 on [-7, 7] (the fit needs ~1e-9, DESIGN.md
+    5.1), odd symmetry, saturation beyond |z| = 6, NaN propagation."""
+    import ctypes as C
+    import math
+
+    import sim_mle_tps
+
+    lib = C.CDLL(sim_mle_tps.SIM_LIB)
+    lib.sim_half_erf.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
+    rng = np.random.default_rng(0)
+    z = np.concatenate([rng.uniform(-7, 7, 200_000), np.arange(-97, 98) / 16.0,
+                        np.arange(-97, 98) / 16.0 + 1 / 32, [0.0, -0.0, 6.0, -6.0, 1e300, -1e300, np.inf, -np.inf]])
+    out = np.empty_like(z)
+    lib.sim_half_erf(z.ctypes.data, len(z), out.ctypes.data)
+    ref = np.array([0.5 * math.erf(v) for v in z])
+    assert np.abs(out - ref).max() <= 2e-11, np.abs(out - ref).max()
+    np.testing.assert_array_equal(out[np.abs(z) >= 6], 0.5 * np.sign(z[np.abs(z) >= 6]))
+    zn = np.array([np.nan, 0.3])
+    on = np.empty(2)
+    lib.sim_half_erf(zn.ctypes.data, 2, on.ctypes.data)
+    assert np.isnan(on[0]) and abs(on[1] - 0.5 * math.erf(0.3)) <= 2e-11
+
