@@ -99,8 +99,9 @@ int pb_mle_fit_dev(size_t n, int box, const float* d_spots, double eps, int max_
 
 /* Kernel selection for pb_mle_fit* (tuning / A-B measurement; results agree within the parity
  * bar for all three): 0 = lane-group kernel (8/16/32 lanes per spot, csrc/mle_fit.cu),
- * 1 = thread-per-spot kernels with float64 per-pixel sums, 2 = thread-per-spot with float32
- * per-pixel sums (csrc/mle_tps.cu; default for box <= 13).  PB_MLE_IMPL in the environment
+ * 1 = thread-per-spot kernels with float64 edge terms and per-pixel sums, 2 = thread-per-spot with a
+ * table-driven float64 PSF, float32 derivative factors and float32 per-pixel sums over a float-float
+ * residual (csrc/mle_tps.cu; default for box <= 13).  PB_MLE_IMPL in the environment
  * sets the initial value.  Boxes above 13 always use the lane-group kernel. */
 int pb_mle_set_impl(int impl);
 int pb_mle_get_impl(void);
