@@ -111,6 +111,40 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+NVLINK_WHY = []     # why the counters could not be read (reported in the JSON line)
+
+
+def nvlink_counters(index):
+    """(tx_bytes, rx_bytes) moved over all NVLink ports of GPU `index` since driver load: NVML field values
+    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX (payload KiB, summed over the links with scope id
+    UINT_MAX), else the per-link lines of `nvidia-smi nvlink -gt d`.  None when neither is exposed."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                   (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        if all(v.nvmlReturn == 0 for v in vals):
+            return tuple(int(v.value.ullVal) * 1024 for v in vals)
+        NVLINK_WHY.append("NVML field values: nvmlReturn " + "/".join(str(v.nvmlReturn) for v in vals))
+    except Exception as e:      # noqa: BLE001
+        NVLINK_WHY.append(f"NVML: {type(e).__name__}: {e}")
+    try:
+        import re
+
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True,
+                             text=True, timeout=20).stdout
+        tx = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+        rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+        if tx and rx:
+            return sum(tx) * 1024, sum(rx) * 1024
+        NVLINK_WHY.append("nvidia-smi nvlink -gt d: " + (out.strip().splitlines()[-1][:120] if out.strip() else "no output"))
+    except Exception as e:      # noqa: BLE001
+        NVLINK_WHY.append(f"nvidia-smi nvlink: {type(e).__name__}: {e}")
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -596,6 +630,7 @@ def main():
     k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
+    nvl0 = nvlink_counters(local) if world > 1 else None
     e0.record()
     for i in range(args.steps):
         b = i % len(flats)
@@ -606,10 +641,28 @@ def main():
     drain()          # every step's gather has left this rank inside the timed region (max over ranks)
     e1.record()
     barrier()
+    nvl1 = nvlink_counters(local) if world > 1 else None
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     gather_ok, verified_steps = None, 0
+    nvlink = None
+    if world > 1:
+        # NVLink payload bytes of this rank's GPU over the timed region (counters read outside it), max over ranks
+        ok = nvl0 is not None and nvl1 is not None
+        t = torch.tensor([float(nvl1[0] - nvl0[0]) if ok else -1.0, float(nvl1[1] - nvl0[1]) if ok else -1.0],
+                         dtype=torch.float64, device=dev)
+        lo = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        if float(lo.min().item()) >= 0.0:
+            nvlink = {"tx_bytes_per_step": float(t[0].item()) / args.steps,
+                      "rx_bytes_per_step": float(t[1].item()) / args.steps,
+                      "algorithmic_rx_bytes_per_step": (world - 1) * 56 * n,
+                      "source": "NVML NVLINK_THROUGHPUT_DATA_TX / _RX (payload, all links of the rank's GPU; what "
+                                "`nvidia-smi nvlink -gt d` prints), read before and after the timed region, max over ranks"}
+        else:
+            nvlink = {"unavailable": "; ".join(dict.fromkeys(NVLINK_WHY)) or "counters not exposed on another rank"}
 
     def gathered_equals_nccl(b):
         """The gathered array of the step that wrote flats[b], element for element, against an NCCL
@@ -794,10 +847,12 @@ def main():
                        "gather_verified_steps": verified_steps, "parts_per_step": parts},
             "roofline": roof,
             # instruction-side view of the dominant kernel from the committed ncu --set full
-            # capture (profiles/r01_mle_tps_ncu.md): what actually bounds the fit
+            # capture (profiles/mle_ncu_compute.json): what actually bounds the fit
             "compute": comp,
             "clocks": clocks, "gpu_launches": launches,
         }
+        if nvlink is not None:
+            line["nvlink"] = nvlink
         if e2e is not None:
             line["e2e"] = e2e
         if e2e_python is not None:
