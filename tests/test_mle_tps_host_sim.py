@@ -116,3 +116,13 @@ def test_table_erf_accuracy(sim):
     lib.sim_half_erf(zn.ctypes.data, 2, on.ctypes.data)
     assert np.isnan(on[0]) and abs(on[1] - 0.5 * math.erf(0.3)) <= 2e-11
 
+
+def test_erf_table_is_the_generators_output():
+    """csrc/erf_table.cuh is exactly what tools/gen_erf_table.py prints (no hand edits)."""
+    import subprocess
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_erf_table.py")], capture_output=True,
+                         text=True, check=True).stdout
+    with open(os.path.join(ROOT, "picasso_b200", "csrc", "erf_table.cuh")) as f:
+        assert f.read() == out
+

@@ -14,7 +14,7 @@ hs = _lib.PinnedArray((n, 7, 7), np.float32); torch.from_numpy(hs.array).copy_(s
 hth = _lib.PinnedArray((n, 6), np.float32); hcr = _lib.PinnedArray((n, 6), np.float32)
 hll = _lib.PinnedArray((n,), np.float32); hit = _lib.PinnedArray((n,), np.int32)
 del spots
-for mb in (16, 32, 64, 128, 256, 512):
+for mb in (8, 16, 32, 64, 128, 256):
     os.environ["PB_MLE_CHUNK_MB"] = str(mb)
     def go():
         _lib.check(lib.pb_mle_fit(n, 7, _lib.ptr(hs.array), 0.001, 100, 1, _lib.ptr(hth.array),
