@@ -20,6 +20,8 @@
 //     appends (frame, y, x, ng) if ng > minimum_ng.
 // HBM-bound by design: each pixel is read once (+ halo re-reads through L2).
 #include <algorithm>
+#include <cmath>
+#include <stdlib.h>
 #include <atomic>
 #include <numeric>
 #include <vector>
@@ -47,6 +49,7 @@ struct IdArgs {
     int y0, x0, Ys, Xs;     // ROI window (image = frame[y0:y0+Ys, x0:x0+Xs])
     long long frame_offset; // added to the emitted frame number
     double min_ng_d;        // threshold, compared in double like the reference (ng > minimum_ng)
+    double ng_bound;        // |ng| <= (max - min over the (b+2)^2 neighbourhood) * ng_bound; 0: no pre-filter
     long long* out_frame;
     long long* out_x;
     long long* out_y;
@@ -79,6 +82,11 @@ __device__ __forceinline__ T pmax(T a, T b) { return a > b ? a : b; }
 __device__ __forceinline__ unsigned pk_max(unsigned a, unsigned b) {
     unsigned r;
     asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned pk_min(unsigned a, unsigned b) {
+    unsigned r;
+    asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
 }
 // pixels (2k+1, 2k+2) from the words holding (2k, 2k+1) and (2k+2, 2k+3)
@@ -319,6 +327,41 @@ __global__ void __launch_bounds__(kTX) identify_kernel(const IdArgs a) {
         const int tr_c = u + H + 1;                    // tile row of the centre
         float acc = 0.0f;
         if (i > H && jc > H) {
+            // Pre-filter: every gradient entering the sum is a difference of two pixels of the
+            // (b+2) x (b+2) neighbourhood, so |ng| <= (max - min) * sum_q(|ux_q| + |uy_q|).  Noise maxima
+            // (range ~20 counts -> bound ~1 300 against a threshold of 5 000) are dropped without the
+            // 48-term sequential sum; whatever passes is summed exactly as before, so the detections and
+            // their net gradients stay bit-identical.  (A superset of the neighbourhood only loosens the bound.)
+            if (a.ng_bound > 0.0) {
+                float range;
+                if constexpr (PACKED && H <= 6) {
+                    const int w0 = (tcc - H - 1) >> 1;          // aligned words covering the columns
+                    unsigned mn = 0xffffffffu, mx = 0u;
+#pragma unroll 1
+                    for (int rr = -H - 1; rr <= H + 1; rr++) {
+                        const unsigned* rw = reinterpret_cast<const unsigned*>(&tile[tr_c + rr][0]) + w0;
+#pragma unroll
+                        for (int w = 0; w < H + 2; w++) {
+                            const unsigned v = rw[w];
+                            mn = pk_min(mn, v);
+                            mx = pk_max(mx, v);
+                        }
+                    }
+                    const unsigned lo = min(mn & 0xffffu, mn >> 16), hi = max(mx & 0xffffu, mx >> 16);
+                    range = (float)(hi - lo);
+                } else {
+                    T mn = tile[tr_c][tcc], mx = mn;
+#pragma unroll 1
+                    for (int rr = -H - 1; rr <= H + 1; rr++)
+                        for (int cc2 = -H - 1; cc2 <= H + 1; cc2++) {
+                            const T v = tile[tr_c + rr][tcc + cc2];
+                            mn = v < mn ? v : mn;
+                            mx = v > mx ? v : mx;
+                        }
+                    range = PixTraits<T>::diff(mx, mn);
+                }
+                if ((double)range * a.ng_bound <= a.min_ng_d) continue;
+            }
             // interior: every neighbour is in the tile; u16 differences are exact integers
 #pragma unroll 1
             for (int kk = -H; kk <= H; kk++) {
@@ -376,8 +419,23 @@ int launch_identify(const IdArgs& a, int box, cudaStream_t stream) {
     dim3 grid((a.Xs + TXW - 1) / TXW, (a.Ys + ty - 1) / ty, 1);
     // gridDim.z is limited to 65535: loop over frame batches
     const long long zmax = 32768;
+    // pre-filter constant: sum over the b*b - 1 unit vectors of |ux| + |uy| (float64, 0.1 % head room for the
+    // float32 rounding of the sequential sum); PB_IDENTIFY_PREFILTER=0 disables it for A/B runs
+    static const bool prefilter = [] {
+        const char* e = getenv("PB_IDENTIFY_PREFILTER");
+        return !(e && atoi(e) == 0);
+    }();
+    double bound = 0.0;
+    if (prefilter) {
+        const int h = box / 2;
+        for (int ky = -h; ky <= h; ky++)
+            for (int kx = -h; kx <= h; kx++)
+                if (ky || kx) bound += (std::abs((double)ky) + std::abs((double)kx)) / std::sqrt((double)(ky * ky + kx * kx));
+        bound *= 1.001;
+    }
     for (long long f0 = 0; f0 < a.n_frames; f0 += zmax) {
         IdArgs b = a;
+        b.ng_bound = bound;
         const long long nf = std::min(zmax, a.n_frames - f0);
         size_t fsz = (size_t)a.Y * a.X * sizeof(T);
         b.movie = static_cast<const char*>(a.movie) + (size_t)f0 * fsz;
