@@ -124,13 +124,16 @@ __global__ void __launch_bounds__(256) locs_columns_kernel(const ColArgs a) {
 }
 
 // ---- (frame, y, x) ordering of the identifications of one chunk ------------------
+// key = ((frame - frame_offset) * Y + y) * X + x: the linear pixel index inside the chunk, so the radix
+// sort only has to look at ceil(log2(chunk frames * Y * X)) bits (29 for 2000 x 512 x 512: 4 passes, not 8)
 __global__ void sort_keys_kernel(const long long* __restrict__ frame, const long long* __restrict__ x,
                                  const long long* __restrict__ y, long long frame_offset, unsigned n,
+                                 unsigned long long Y, unsigned long long X,
                                  unsigned long long* __restrict__ keys, unsigned* __restrict__ idx) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keys[i] = ((unsigned long long)(frame[i] - frame_offset) << 40) |
-              ((unsigned long long)y[i] << 20) | (unsigned long long)x[i];
+    keys[i] = ((unsigned long long)(frame[i] - frame_offset) * Y + (unsigned long long)y[i]) * X +
+              (unsigned long long)x[i];
     idx[i] = i;
 }
 __global__ void gather_ids_kernel(const unsigned* __restrict__ idx, unsigned n,
@@ -294,8 +297,10 @@ static int localize_impl(bool on_device, const void* movie, int dtype, size_t n_
         const long v = atol(e);
         if (v >= 1) chunk = (size_t)v;
     }
-    if (on_device) chunk = std::max<size_t>(chunk, ((size_t)512 << 20) / fsz);   // resident movie: no staging limit,
-                                                                                 // fewer per-chunk count read-backs
+    // resident movie: no staging limit; one chunk per 2 GB keeps the per-chunk count read-backs rare and gives
+    // the fit kernel all of a block's spots at once (config 3: one identify + one fit launch instead of two
+    // of each, 3.0 -> 2.0 ms; the id / ROI / fit workspace is ~400 B per expected spot = 0.85 GB)
+    if (on_device) chunk = std::max<size_t>(chunk, ((size_t)2048 << 20) / fsz);
     chunk = std::min(chunk, std::min<size_t>(n_frames, (size_t)1 << 22));
     const bool pinned_src = on_device || pb_host_is_pinned(movie);
     for (int s = 0; s < 2 && !on_device; s++) {
@@ -403,9 +408,12 @@ static int localize_impl(bool on_device, const void* movie, int dtype, size_t n_
         if (!overflow && found) {
             const unsigned n = (unsigned)found;
             const unsigned g = (n + 255) / 256;
-            sort_keys_kernel<<<g, 256, 0, cs>>>(uf, ux, uy, foff, n, k_in, i_in);
+            sort_keys_kernel<<<g, 256, 0, cs>>>(uf, ux, uy, foff, n, (unsigned long long)Y, (unsigned long long)X,
+                                                k_in, i_in);
+            int key_bits = 1;
+            while (key_bits < 64 && ((unsigned long long)nf * Y * X - 1) >> key_bits) key_bits++;
             size_t tb = cub_bytes;
-            if (cub::DeviceRadixSort::SortPairs(P->cubtmp.p, tb, k_in, k_out, i_in, i_out, (int)n, 0, 64, cs) !=
+            if (cub::DeviceRadixSort::SortPairs(P->cubtmp.p, tb, k_in, k_out, i_in, i_out, (int)n, 0, key_bits, cs) !=
                 cudaSuccess) {
                 pb_set_error("pb_localize: radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return PB_ERR_CUDA;
