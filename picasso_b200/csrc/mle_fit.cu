@@ -116,6 +116,7 @@ __device__ __noinline__ void pinv_diag_jacobi(const double* Msym /*NP*NP*/, doub
     }
     for (int i = 0; i < NP; i++)
         for (int j = 0; j < NP; j++) V[i * NP + j] = (i == j) ? 1.0 : 0.0;
+    double prev_off = INFINITY;      // stop when a sweep no longer reduces the off-diagonal weight (mle_tps_core.cuh)
     for (int sweep = 0; sweep < 60; sweep++) {
         double off = 0.0, dsum = 0.0;
         for (int i = 0; i < NP; i++)
@@ -123,7 +124,8 @@ __device__ __noinline__ void pinv_diag_jacobi(const double* Msym /*NP*NP*/, doub
                 double v = A[i * NP + j] * A[i * NP + j];
                 if (i != j) off += v; else dsum += v;
             }
-        if (off <= 1e-60 || off <= 1e-34 * dsum) break;
+        if (off <= 1e-60 || off <= 1e-34 * dsum || off >= 0.25 * prev_off) break;
+        prev_off = off;
         for (int p = 0; p < NP - 1; p++)
             for (int q = p + 1; q < NP; q++) {
                 double apq = A[p * NP + q];
