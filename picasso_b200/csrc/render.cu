@@ -181,9 +181,15 @@ __global__ void render_splat_kernel(const RenderArgs a) {
 
 // ---- tiled path ---------------------------------------------------------------
 constexpr int kTile = 64;                 // tile edge in image pixels (16 KB of smem)
-constexpr int kSizeClasses = 4;           // bins per tile: by blur width (window size)
+constexpr int kWinClass = 16;             // window heights 1..16 get their own class (taller: the last one)
+constexpr int kSizeClasses = kWinClass * 2;           // bins per tile: window rows x (narrow | wide columns)
 
-// pass 1: tile id per localisation (-1 = not in view) + histogram of tile sizes
+// pass 1: bin per localisation (-1 = not in view) + histogram of bin sizes.  bin = (tile, window class): the
+// accumulation pass runs one thread per localisation, and a warp takes as long as its largest window --
+// with four classes by blur width only 16.5 of 32 lanes were busy (windows are 3..11 pixels per axis at
+// config 4, rows and columns independently).  Classes = exact window height x (narrow | wide): 23 lanes busy.
+// (256 exact (rows, columns) classes keep the same 23 lanes busy -- bins of 8 records, warps span several --
+// but scatter the records over 6.5 M bins, more write sectors than L2 holds: scatter pass 1.3 -> 2.3 ms.)
 __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restrict__ tile_of,
                                   unsigned int* __restrict__ tile_count) {
     unsigned long long local = 0;
@@ -193,18 +199,24 @@ __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restri
         const bool in_view = (xv > a.x_min) && (yv > a.y_min) && (xv < a.x_max) && (yv < a.y_max);
         int t = -1;
         if (in_view) {
-            const double y_ = a.os * (yv - a.y_min);
-            int px = (int)(a.os * (xv - a.x_min)), py = (int)y_;
+            const double x_ = a.os * (xv - a.x_min), y_ = a.os * (yv - a.y_min);
+            int px = (int)x_, py = (int)y_;
             px = min(max(px, 0), a.npx - 1);
             py = min(max(py, 0), a.npy - 1);
             if (py >= a.row0 && py < a.row0 + a.nrows) local++;
-            // bin = (tile, window-size class): threads of a warp then splat windows of similar
-            // size (a warp runs as long as its widest window: 3..11 px across at config 4)
-            const float sg = __fmul_rn(a.osf, fmaxf(fmaxf(a.lpx[k], a.lpy[k]), a.mbw));
-            const int cls = sg < 0.75f ? 0 : sg < 1.05f ? 1 : sg < 1.4f ? 2 : 3;
+            // window exactly as the accumulation pass derives it (render.py:505-525)
+            const float bw = __fmul_rn(a.osf, fmaxf(a.lpx[k], a.mbw));
+            const float bh = __fmul_rn(a.osf, fmaxf(a.lpy[k], a.mbw));
+            float sx, sy;
+            if (a.mode == 2) { sy = __fdiv_rn(__fadd_rn(bh, bw), 2.0f); sx = sy; }
+            else { sx = bw; sy = bh; }
+            const double moy = 3.0 * (double)sy, mox = 3.0 * (double)sx;
+            const int ny = min((int)(y_ + moy + 1.0), a.npy) - max((int)(y_ - moy), 0);
+            const int nx = min((int)(x_ + mox) + 1, a.npx) - max((int)(x_ - mox), 0);
+            const int cls = (min(max(ny, 1), kWinClass) - 1) * 2 + (nx > 6 ? 1 : 0);
             // row band: localisations centred outside the band whose 3-sigma window reaches into it
             // (conservative test; the accumulation pass clips exactly) go to the nearest band tile
-            const double reach = 3.0 * (double)sg + 2.0;
+            const double reach = 3.0 * (double)fmaxf(sx, sy) + 2.0;
             if (y_ + reach >= (double)a.row0 && y_ - reach <= (double)(a.row0 + a.nrows)) {
                 const int pyb = min(max(py, a.row0), a.row0 + a.nrows - 1) - a.row0;
                 const int tile = (pyb / kTile) * tiles_x + (px / kTile);
@@ -226,7 +238,7 @@ __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restri
 // pass 2: exclusive scan of the bin histogram -> start[0 .. nbins] (start[nbins] = total; count[nbins] is kept
 // zero for that) and a second copy, cursor, for the scatter pass.  cub::DeviceScan (decoupled look-back, all
 // SMs, ~10 us for 100 k bins); the first version was a single-CTA loop with strided reads (180 us).
-constexpr size_t kScanTempBytes = 1 << 16;
+constexpr size_t kScanTempBytes = 1 << 20;
 int render_scan(unsigned int* count, unsigned int* start, unsigned int* cursor, long long nbins, void* temp,
                 cudaStream_t s) {
     size_t need = 0;
@@ -241,8 +253,11 @@ int render_scan(unsigned int* count, unsigned int* start, unsigned int* cursor, 
     return PB_OK;
 }
 
-// pass 3: scatter the localisations themselves (x, y, lpx, lpy as one float4) into tile
-// order, so the accumulation pass streams them with coalesced 16 B loads
+// pass 3: scatter the localisations themselves (x, y, lpx, lpy as one float4) into bin order, so the
+// accumulation pass streams them with coalesced 16 B loads.  Slots are handed out by a cursor per bin at
+// scatter time: records that are written close in time land next to each other and L2 merges them into
+// full sectors (taking the slot from a rank recorded by the bin pass instead -- no atomics here -- was
+// measured slower: 2.2 ms against 1.3 ms).
 __global__ void render_scatter_kernel(const RenderArgs a, const int* __restrict__ tile_of,
                                       unsigned int* __restrict__ cursor,
                                       float4* __restrict__ sorted) {
@@ -692,9 +707,9 @@ extern "C" int pb_render_unpack_records_dev(size_t n, const float* d_records, fl
     return PB_OK;
 }
 
-// Workspace (bytes) pb_render_dev needs for the binned paths.  Strip path: up to two float4 records per
-// localisation (a window straddling two strips) + one int32 bin word, and count / start / cursor per bin
-// (16-row x 64-column strips); the 64x64-tile layout of the round-1 pass fits inside.
+// Workspace (bytes) pb_render_dev needs for the binned paths: up to two float4 records per localisation
+// (strip path: a window straddling two strips), one int32 bin word per localisation, and count / start /
+// cursor per bin (32 window-size classes per 64x64 tile, or 16-row x 64-column strips).
 extern "C" size_t pb_render_workspace_bytes(size_t n, int n_pixel_y, int n_pixel_x) {
     const size_t tiles_x = (size_t)((n_pixel_x + kTile - 1) / kTile);
     const size_t strips = (size_t)((n_pixel_y + kStripRows - 1) / kStripRows) * tiles_x;
@@ -786,7 +801,7 @@ extern "C" int pb_render_band_dev(size_t n, const float* d_x, const float* d_y, 
         PB_CUDA_CHECK(cudaGetLastError());
         return PB_OK;
     }
-    // workspace layout: sorted[2n] float4 | tile_of[n] i32 | count[B] | start[B+1] | cursor[B]
+    // workspace layout: sorted[2n] float4 | tile_of[n] i32 | count[B+1] | start[B+1] | cursor[B] | scan temp
     char* w = static_cast<char*>(d_workspace);
     float4* sorted = reinterpret_cast<float4*>(w);
     int* tile_of = reinterpret_cast<int*>(w + n * 32);
