@@ -187,9 +187,9 @@ constexpr int kSizeClasses = kWinClass * 2;           // bins per tile: window r
 // pass 1: bin per localisation (-1 = not in view) + histogram of bin sizes.  bin = (tile, window class): the
 // accumulation pass runs one thread per localisation, and a warp takes as long as its largest window --
 // with four classes by blur width only 16.5 of 32 lanes were busy (windows are 3..11 pixels per axis at
-// config 4, rows and columns independently).  Classes = exact window height x (narrow | wide): 23 lanes busy.
-// (256 exact (rows, columns) classes keep the same 23 lanes busy -- bins of 8 records, warps span several --
-// but scatter the records over 6.5 M bins, more write sectors than L2 holds: scatter pass 1.3 -> 2.3 ms.)
+// config 4, rows and columns independently).  Classes = exact window height x (narrow | wide): 20 lanes busy.
+// (256 exact (rows, columns) classes reach 23 -- bins of 8 records, warps span several -- but scatter the
+// records over 6.5 M bins, more write sectors than L2 holds: scatter pass 1.3 -> 2.3 ms.)
 __global__ void render_bin_kernel(const RenderArgs a, int tiles_x, int* __restrict__ tile_of,
                                   unsigned int* __restrict__ tile_count) {
     unsigned long long local = 0;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) render_tiled_kernel(const RenderArgs a, i
     __shared__ float acc[kTile * kTile];
     __shared__ float gxs[kMaxWin][256];
     const int tile = blockIdx.x;
-    // the tile's localisations: its kSizeClasses consecutive bins, narrow windows first
+    // the tile's localisations: its kSizeClasses consecutive bins, short windows first
     const unsigned int first = start[tile * kSizeClasses], last = start[(tile + 1) * kSizeClasses];
     if (first == last) return;
     const int ty0 = a.row0 + (tile / tiles_x) * kTile, tx0 = (tile % tiles_x) * kTile;
