@@ -629,8 +629,8 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    nvl0 = nvlink_counters(local) if world > 1 else None     # (before the barrier: the ranks start the timed loop together)
     barrier()
-    nvl0 = nvlink_counters(local) if world > 1 else None
     e0.record()
     for i in range(args.steps):
         b = i % len(flats)
